@@ -1,0 +1,164 @@
+/* qimg_b200.h — C ABI of the B200 (sm_100a) Qwen-Image DiT denoising engine.
+ *
+ * This is the drop-in boundary: plain pointers + sizes + a cudaStream_t,
+ * no torch types.  Every device pointer is bf16 unless stated; the CALLER owns all
+ * allocations (torch tensors on the reference side); the library owns only a process-wide
+ * TMA-descriptor cache.  Every function returns 0 on success, non-zero on error, with a
+ * message available from qimg_last_error() — the Python layer raises RuntimeError so the
+ * reference's worker error path (diffusion/worker/gpu_worker.py:267-274) keeps working.
+ * There is no CPU fallback: on a machine without an sm_100 device calls fail loudly.
+ *
+ * Each entry point names the reference interface (vllm-omni @ be81443, file:line) it replaces.
+ */
+#ifndef QIMG_B200_H
+#define QIMG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* qimg_stream_t; /* cudaStream_t */
+
+/* ---- library / device --------------------------------------------------------------- */
+int qimg_abi_version(void);
+const char* qimg_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x (B200/GB200); fills sm count. */
+int qimg_device_check(int* sm_count);
+/* number of kernels this library launched since the last reset (bench.py "gpu_launches") */
+long long qimg_launch_count(void);
+void qimg_reset_launch_count(void);
+
+/* ---- bandwidth-bound fused ops ------------------------------------------------------ */
+/* y[r,:] = LN(x[r,:]; eps, no affine) * (1 + scale[b,:]) + shift[b,:],  b = r / rows_per_batch.
+ * Replaces AdaLayerNorm.forward_cuda/forward_native, vllm_omni/diffusion/layers/adalayernorm.py:62-68,94-102
+ * (and AdaLayerNormContinuous at qwen_image_transformer.py:797).  mod_stride = elements between
+ * consecutive batches of shift/scale (0 => one modulation row shared by the whole batch). */
+int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
+                     long long mod_stride, float eps, qimg_stream_t stream);
+
+/* x[r,:] += gate[b,:] * y[r,:]  — gated residual, qwen_image_transformer.py:586-587,592,597. */
+int qimg_gate_residual(void* x, const void* y, const void* gate, int rows, int D, int rows_per_batch,
+                       long long gate_stride, qimg_stream_t stream);
+
+/* y = RMSNorm(x; w, eps) over the last dim (vLLM RMSNorm used as txt_norm, qwen_image_transformer.py:669,758). */
+int qimg_rms_norm(const void* x, const void* w, void* y, int rows, int D, float eps, qimg_stream_t stream);
+
+/* y[M, N] (leading dim ldy) = act(x[M,K]) @ W[N,K]^T + bias, small M (<= 64); act_silu != 0 applies
+ * SiLU to x first.  Replaces nn.Sequential(SiLU, Linear) img_mod/txt_mod (qwen_image_transformer.py:478-481,
+ * 494-497,552-557 — all 2*L projections in one call when W is the concatenated weight), the
+ * TimestepEmbedding MLP (:45,50-62) and norm_out.linear (:686). */
+int qimg_linear_small_m(const void* x, const void* W, const void* bias, void* y, int M, long long N, int K,
+                        long long ldy, int act_silu, qimg_stream_t stream);
+
+/* out[B,256] = [cos | sin](1000 * t * f) — diffusers Timesteps(256, flip_sin_to_cos=True, shift 0, scale 1000),
+ * qwen_image_transformer.py:44 (restated in-tree at pipeline_qwen_image.py:135-184).  t is bf16 [B]. */
+int qimg_timestep_sinusoid(const void* t, void* out, int B, qimg_stream_t stream);
+
+/* Fused true-CFG combine + norm rescale + flow-match Euler step on latents [rows, 64]:
+ *   pipeline_qwen_image.py:580-583 and FlowMatchEulerDiscreteScheduler.step at :585.
+ * neg == NULL => no CFG.  latents updated in place: x = bf16(float(x) + bf16((sigma_next - sigma) * noise)). */
+int qimg_cfg_euler_step(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale,
+                        float sigma, float sigma_next, qimg_stream_t stream);
+
+/* ---- tcgen05 GEMM family ------------------------------------------------------------ */
+enum { QIMG_EPI_BIAS = 0, QIMG_EPI_BIAS_GELU = 1, QIMG_EPI_BIAS_GATE_RES = 2, QIMG_EPI_QKV = 3 };
+
+/* One linear problem out = A[M,K] @ W[N,K]^T (+ epilogue).  Up to two problems (image stream,
+ * text stream) are grouped in one launch.  Replaces vLLM QKVParallelLinear/ReplicatedLinear and
+ * diffusers FeedForward linears at qwen_image_transformer.py:380-385,452-456,491,501 together with
+ * the pointwise ops the epilogue absorbs (see csrc/qimg_gemm.cuh). */
+typedef struct qimg_gemm_problem {
+  const void* A;    /* [M, K] row-major, K % 8 == 0 */
+  const void* W;    /* [N, K] row-major (nn.Linear weight) */
+  const void* bias; /* [N] */
+  int M, N, K;
+  int rows_per_batch; /* rows per image of this stream (gate / position lookup) */
+  /* QIMG_EPI_BIAS / _GELU: out [M, ldo].  QIMG_EPI_BIAS_GATE_RES: out is the residual stream x, updated in
+   * place: x = x + gate[b,:] * (A W^T + bias). */
+  void* out;
+  int ldo;
+  const void* gate;
+  long long gate_stride;
+  /* QIMG_EPI_QKV (N = 3*H*128): per-head RMSNorm(q,k) + interleaved RoPE, scattered into joint
+   * head-major q/k/v [B, H, S_joint, 128] at sequence offset pos_off. */
+  void* q;
+  void* k;
+  void* v;
+  const void* norm_q_w;
+  const void* norm_k_w;
+  const void* rope_cos; /* [rows_per_batch, 64] bf16 */
+  const void* rope_sin;
+  int S_joint, pos_off, H;
+  float eps;
+} qimg_gemm_problem;
+
+int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_stream_t stream);
+
+/* ---- joint attention ---------------------------------------------------------------- */
+/* softmax(Q K^T * scale) V over the joint [text; image] sequence, non-causal, no mask.
+ * q,k,v: [B, H, S, 128] head-major (as written by QIMG_EPI_QKV); out_txt [B*T, H*128], out_img
+ * [B*(S-T), H*128].  Replaces Attention.forward -> SDPAImpl.forward (attention/layer.py:54-70,
+ * backends/sdpa.py:46-66) and the cat/split around it (qwen_image_transformer.py:414-416,448-449). */
+int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
+                    int T, float softmax_scale, qimg_stream_t stream);
+
+/* ---- whole-model engine ------------------------------------------------------------- */
+typedef struct qimg_dims {
+  int num_layers, num_heads, head_dim /* must be 128 */, in_channels /* 64 */, out_dim /* 64 */, joint_dim /* 3584 */;
+  float eps;
+} qimg_dims;
+
+typedef struct qimg_block_weights { /* names: SURVEY.md §8c / qwen_image_transformer.py:804-839 */
+  const void *img_mod_w, *img_mod_b, *txt_mod_w, *txt_mod_b;     /* [6D, D], [6D] */
+  const void *to_qkv_w, *to_qkv_b, *add_kv_w, *add_kv_b;         /* [3D, D], [3D] */
+  const void *norm_q, *norm_k, *norm_added_q, *norm_added_k;     /* [128] */
+  const void *to_out_w, *to_out_b, *to_add_out_w, *to_add_out_b; /* [D, D], [D] */
+  const void *img_mlp_w1, *img_mlp_b1, *img_mlp_w2, *img_mlp_b2; /* [4D, D], [4D], [D, 4D], [D] */
+  const void *txt_mlp_w1, *txt_mlp_b1, *txt_mlp_w2, *txt_mlp_b2;
+} qimg_block_weights;
+
+typedef struct qimg_global_weights {
+  const void *t_lin1_w, *t_lin1_b, *t_lin2_w, *t_lin2_b; /* time_text_embed.timestep_embedder.linear_{1,2} */
+  const void* txt_norm_w;
+  const void *img_in_w, *img_in_b, *txt_in_w, *txt_in_b;
+  const void *norm_out_w, *norm_out_b, *proj_out_w, *proj_out_b;
+  /* Optional: all 2*L modulation weights concatenated as [L][img,txt][6D, D] / [L][2][6D]; when
+   * non-NULL the engine computes every block's modulation with ONE small-M launch per forward. */
+  const void *mod_all_w, *mod_all_b;
+} qimg_global_weights;
+
+typedef struct qimg_engine qimg_engine;
+
+int qimg_engine_create(const qimg_dims* dims, const qimg_global_weights* g, const qimg_block_weights* blocks,
+                       qimg_engine** out);
+void qimg_engine_destroy(qimg_engine* e);
+size_t qimg_engine_workspace_bytes(const qimg_engine* e, int B, int S_img, int T);
+
+/* One DiT forward = QwenImageTransformer2DModel.forward (qwen_image_transformer.py:692-802), SP off:
+ *   hidden [B,S_img,64], enc [B,T,joint], timestep bf16 [n_t] (already /1000; n_t = B, or 1 when the
+ *   whole batch shares one timestep as in QwenImagePipeline.diffuse, pipeline_qwen_image.py:552),
+ *   RoPE tables bf16 img [S_img,64] x2, txt [T,64] x2  ->  out [B,S_img,64].
+ * layer_begin/layer_end select a block range (0, num_layers for the full model); prologue/epilogue
+ * run only when the range starts at 0 / ends at num_layers. */
+int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, const void* timestep, int n_t,
+                        const void* img_cos, const void* img_sin, const void* txt_cos, const void* txt_sin, int B,
+                        int S_img, int T, void* out, void* workspace, size_t workspace_bytes, qimg_stream_t stream);
+
+/* Debug/test access: copies of the image / text residual streams after the last forward live in the
+ * workspace at these byte offsets ([B*S_img, D] and [B*T, D] bf16). */
+size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T);
+size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T);
+
+/* ---- self test ------------------------------------------------------------------------ */
+/* Raw tcgen05 probe used by tests: D[128,N] = A[128,K] B[N,K]^T through the same descriptors the
+ * kernels use.  mode 0: A,B K-major from smem.  mode 1: B MN-major ([K,N] row-major in global).
+ * mode 2: A staged through TMEM (tcgen05.st) as the FMHA P operand, B MN-major. */
+int qimg_umma_probe(const void* A, const void* B, float* D, int N, int K, int mode, qimg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QIMG_B200_H */

@@ -1,0 +1,422 @@
+// C-ABI entry points (include/qimg_b200.h) and host launchers for the sm_100a kernels.
+#include "../../include/qimg_b200.h"
+
+#include <cstring>
+#include <vector>
+
+#include "qimg_elementwise.cuh"
+#include "qimg_fmha.cuh"
+#include "qimg_gemm.cuh"
+#include "qimg_host.cuh"
+
+namespace qimg {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launch_count{0};
+
+int device_sm_count() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  cached = n;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptor cache
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t cols, rows, batches;
+  uint32_t box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && cols == o.cols && rows == o.rows && batches == o.batches && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= k.cols * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.rows * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= (k.batches * 1315423911ull + k.box_rows) + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+
+static const CUtensorMap* get_tmap(const void* ptr, uint64_t cols, uint64_t rows, uint64_t batches, uint32_t box_rows) {
+  TmapKey key{ptr, cols, rows, batches, box_rows};
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) return &it->second;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    fail("cuTensorMapEncodeTiled unavailable (no CUDA driver / no GPU)");
+    return nullptr;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (cols % 8)) {
+    fail("TMA operand must be 16-byte aligned with a row length that is a multiple of 8 elements");
+    return nullptr;
+  }
+  CUtensorMap tm;
+  const bool is3d = batches > 0;
+  cuuint64_t gdim[3] = {cols, rows, is3d ? batches : 1};
+  cuuint64_t gstride[2] = {cols * 2, cols * rows * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, is3d ? 3 : 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "CUresult %d (cols=%llu rows=%llu box_rows=%u)", (int)r, (unsigned long long)cols,
+             (unsigned long long)rows, box_rows);
+    fail("cuTensorMapEncodeTiled", buf);
+    return nullptr;
+  }
+  auto ins = g_tmaps.emplace(key, tm);
+  return &ins.first->second;
+}
+const CUtensorMap* get_tmap_2d(const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  return get_tmap(ptr, cols, rows, 0, box_rows);
+}
+const CUtensorMap* get_tmap_3d(const void* ptr, uint64_t cols, uint64_t rows, uint64_t batches, uint32_t box_rows) {
+  return get_tmap(ptr, cols, rows, batches, box_rows);
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM launcher
+// ------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm_inst(const CUtensorMap* tA[2], const CUtensorMap* tB[2], const GemmParams& prm, cudaStream_t st) {
+  static bool attr_set = false;
+  constexpr int smem = gemm_smem_bytes<BN>();
+  if (!attr_set) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int sms = device_sm_count();
+  if (sms <= 0) return fail("no CUDA device");
+  int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
+  gemm_umma_kernel<BN, EPI><<<grid, GEMM_THREADS, smem, st>>>(*tA[0], *tB[0], *tA[1], *tB[1], prm);
+  QIMG_LAUNCH_CHECK("gemm_umma_kernel");
+  return 0;
+}
+
+static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStream_t st) {
+  if (nprob < 1 || nprob > 2) return fail("qimg_gemm: nprob must be 1 or 2");
+  int maxN = 0;
+  for (int i = 0; i < nprob; ++i) maxN = pr[i].N > maxN ? pr[i].N : maxN;
+  const int BN = (maxN <= 64 && epi == QIMG_EPI_BIAS) ? 64 : 256;
+  GemmParams prm;
+  memset(&prm, 0, sizeof prm);
+  prm.nprob = nprob;
+  const CUtensorMap* tA[2] = {nullptr, nullptr};
+  const CUtensorMap* tB[2] = {nullptr, nullptr};
+  int tiles = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const qimg_gemm_problem& s = pr[i];
+    if (s.M <= 0 || s.N <= 0 || s.K <= 0) return fail("qimg_gemm: empty problem");
+    if (s.K % 8 || s.N % 8) return fail("qimg_gemm: K and N must be multiples of 8");
+    if (s.rows_per_batch <= 0) return fail("qimg_gemm: rows_per_batch must be > 0");
+    GemmProblem& d = prm.p[i];
+    d.M = s.M; d.N = s.N; d.K = s.K;
+    d.rows_per_batch = s.rows_per_batch;
+    d.bias = (const bf16*)s.bias;
+    d.out = (bf16*)s.out;
+    d.ldo = s.ldo;
+    d.gate = (const bf16*)s.gate;
+    d.gate_stride = s.gate_stride;
+    d.q = (bf16*)s.q; d.k = (bf16*)s.k; d.v = (bf16*)s.v;
+    d.nq_w = (const bf16*)s.norm_q_w; d.nk_w = (const bf16*)s.norm_k_w;
+    d.cos = (const bf16*)s.rope_cos; d.sin = (const bf16*)s.rope_sin;
+    d.S_joint = s.S_joint; d.pos_off = s.pos_off; d.H = s.H; d.eps = s.eps;
+    if (!s.bias) return fail("qimg_gemm: bias is required");
+    if (epi == QIMG_EPI_QKV) {
+      if (s.N != 3 * s.H * 128) return fail("qimg_gemm: QKV epilogue needs N == 3*H*128");
+      if (!s.q || !s.k || !s.v || !s.norm_q_w || !s.norm_k_w || !s.rope_cos || !s.rope_sin)
+        return fail("qimg_gemm: QKV epilogue pointers missing");
+    } else if (!s.out || s.ldo % 8) {
+      return fail("qimg_gemm: out missing or ldo not a multiple of 8");
+    }
+    if (epi == QIMG_EPI_BIAS_GATE_RES && !s.gate) return fail("qimg_gemm: gate missing");
+    d.m_tiles = (s.M + GEMM_BM - 1) / GEMM_BM;
+    d.n_tiles = (s.N + BN - 1) / BN;
+    d.tile_begin = tiles;
+    tiles += d.m_tiles * d.n_tiles;
+    tA[i] = get_tmap_2d(s.A, (uint64_t)s.K, (uint64_t)s.M, GEMM_BM);
+    tB[i] = get_tmap_2d(s.W, (uint64_t)s.K, (uint64_t)s.N, (uint32_t)BN);
+    if (!tA[i] || !tB[i]) return 1;
+  }
+  if (nprob == 1) {
+    tA[1] = tA[0];
+    tB[1] = tB[0];
+  }
+  prm.total_tiles = tiles;
+  if (BN == 64) return launch_gemm_inst<64, EPI_BIAS>(tA, tB, prm, st);
+  switch (epi) {
+    case QIMG_EPI_BIAS: return launch_gemm_inst<256, EPI_BIAS>(tA, tB, prm, st);
+    case QIMG_EPI_BIAS_GELU: return launch_gemm_inst<256, EPI_BIAS_GELU>(tA, tB, prm, st);
+    case QIMG_EPI_BIAS_GATE_RES: return launch_gemm_inst<256, EPI_BIAS_GATE_RES>(tA, tB, prm, st);
+    case QIMG_EPI_QKV: return launch_gemm_inst<256, EPI_QKV>(tA, tB, prm, st);
+  }
+  return fail("qimg_gemm: unknown epilogue");
+}
+
+// ------------------------------------------------------------------------------------------
+// raw tcgen05 probe (test tool): one CTA, D[128,128] = A[128,128] * B^T, three operand paths
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const bf16* __restrict__ Ag, float* __restrict__ Dg, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536);
+  uint64_t* ld_full = bars;
+  uint64_t* mma_done = bars + 1;
+  uint64_t* p_ready = bars + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(ld_full, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(p_ready, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tD = tmem_base, tP = tmem_base + 128;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(ld_full, 65536);
+      for (int s = 0; s < 2; ++s) {
+        tma_load_2d(sA + s * 16384, &tmA, ld_full, s * 64, 0);
+        tma_load_2d(sB + s * 16384, &tmB, ld_full, s * 64, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(ld_full, 0);
+      if (mode == 2) mbar_wait(p_ready, 0);
+      tc_fence_after();
+      const uint32_t a = smem_u32(sA), b = smem_u32(sB);
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
+        if (mode == 0)
+          umma_ss(tD, make_kmajor_sw128_desc(a + koff), make_kmajor_sw128_desc(b + koff), make_idesc_bf16(128, 128, 0, 0), k != 0);
+        else if (mode == 1)
+          umma_ss(tD, make_kmajor_sw128_desc(a + koff), make_mnmajor_sw128_desc(b + k * 2048, 16384),
+                  make_idesc_bf16(128, 128, 0, 1), k != 0);
+        else
+          umma_ts(tD, tP + k * 8, make_mnmajor_sw128_desc(b + k * 2048, 16384), make_idesc_bf16(128, 128, 0, 1), k != 0);
+      }
+      umma_commit(mma_done);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    if (mode == 2) {
+      // stage A row-per-lane into TMEM as packed bf16 pairs (the FMHA "P" operand path)
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t pk[16];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(Ag + (size_t)row * 128 + cc * 32);
+        for (int i = 0; i < 16; ++i) pk[i] = src[i];
+        tmem_st_32x32b_x16(tP + lane_off + cc * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    mbar_wait(mma_done, 0);
+    tc_fence_after();
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tD + lane_off + cc * 32, r);
+      tmem_ld_wait();
+      for (int i = 0; i < 32; ++i) Dg[(size_t)row * 128 + cc * 32 + i] = __uint_as_float(r[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+}  // namespace qimg
+
+using namespace qimg;
+
+extern "C" {
+
+int qimg_abi_version(void) { return 1; }
+const char* qimg_last_error(void) { return g_last_error.c_str(); }
+long long qimg_launch_count(void) { return g_launch_count.load(); }
+void qimg_reset_launch_count(void) { g_launch_count.store(0); }
+
+int qimg_device_check(int* sm_count) {
+  int dev = 0, major = 0, minor = 0, n = 0;
+  QIMG_CUDA_CHECK(cudaGetDevice(&dev));
+  QIMG_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  QIMG_CUDA_CHECK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  QIMG_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (sm_count) *sm_count = n;
+  if (major != 10) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "device is sm_%d%d", major, minor);
+    return fail("qimg_b200 requires an sm_100 (B200) device", buf);
+  }
+  return 0;
+}
+
+int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
+                     long long mod_stride, float eps, qimg_stream_t stream) {
+  if (rows <= 0) return 0;
+  if (D % 8 || D > EW_MAX_CHUNKS * 256) return fail("qimg_ln_modulate: D must be a multiple of 8 and <= 4096");
+  if (rows_per_batch <= 0) return fail("qimg_ln_modulate: rows_per_batch");
+  ln_modulate_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)shift, (const bf16*)scale,
+                                                                       (bf16*)y, rows, D, rows_per_batch, mod_stride, eps);
+  QIMG_LAUNCH_CHECK("ln_modulate_kernel");
+  return 0;
+}
+
+int qimg_rms_norm(const void* x, const void* w, void* y, int rows, int D, float eps, qimg_stream_t stream) {
+  if (rows <= 0) return 0;
+  if (D % 8 || D > EW_MAX_CHUNKS * 256) return fail("qimg_rms_norm: D must be a multiple of 8 and <= 4096");
+  rms_norm_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rows, D, eps);
+  QIMG_LAUNCH_CHECK("rms_norm_kernel");
+  return 0;
+}
+
+int qimg_gate_residual(void* x, const void* y, const void* gate, int rows, int D, int rows_per_batch,
+                       long long gate_stride, qimg_stream_t stream) {
+  if (rows <= 0) return 0;
+  if (D % 8) return fail("qimg_gate_residual: D must be a multiple of 8");
+  const long long n_vec = (long long)rows * (D / 8);
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gate_residual_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)x, (const bf16*)y, (const bf16*)gate, n_vec, D,
+                                                                      rows_per_batch, gate_stride);
+  QIMG_LAUNCH_CHECK("gate_residual_kernel");
+  return 0;
+}
+
+int qimg_linear_small_m(const void* x, const void* W, const void* bias, void* y, int M, long long N, int K,
+                        long long ldy, int act_silu, qimg_stream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (K % 8) return fail("qimg_linear_small_m: K must be a multiple of 8");
+  if (M > 64) return fail("qimg_linear_small_m: M > 64 (use qimg_gemm)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(linear_small_m_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 2));
+    attr_set = true;
+  }
+  if (K > 4096) return fail("qimg_linear_small_m: K > 4096");
+  const int sms = device_sm_count();
+  for (int m0 = 0; m0 < M; m0 += 8) {
+    const int mm = (M - m0) < 8 ? (M - m0) : 8;
+    long long blocks = (N + 7) / 8;
+    const long long cap = (long long)sms * 8;
+    if (blocks > cap) blocks = cap;
+    linear_small_m_kernel<8><<<(int)blocks, 256, (size_t)mm * K * 2, (cudaStream_t)stream>>>(
+        (const bf16*)x + (size_t)m0 * K, (const bf16*)W, (const bf16*)bias, (bf16*)y + (size_t)m0 * ldy, mm, N, K, ldy, act_silu);
+    QIMG_LAUNCH_CHECK("linear_small_m_kernel");
+  }
+  return 0;
+}
+
+int qimg_timestep_sinusoid(const void* t, void* out, int B, qimg_stream_t stream) {
+  if (B <= 0) return 0;
+  timestep_sinusoid_kernel<<<(B * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const bf16*)t, (bf16*)out, B);
+  QIMG_LAUNCH_CHECK("timestep_sinusoid_kernel");
+  return 0;
+}
+
+int qimg_cfg_euler_step(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale,
+                        float sigma, float sigma_next, qimg_stream_t stream) {
+  if (rows <= 0) return 0;
+  if (C != 64) return fail("qimg_cfg_euler_step: C must be 64 (packed latent channels)");
+  const long long vecs = rows * 8;
+  const float dt = sigma_next - sigma;  // fp32 subtraction, as the scheduler's 0-dim fp32 tensors
+  cfg_euler_step_kernel<<<(int)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)pos, (const bf16*)neg,
+                                                                                     (bf16*)latents, rows, cfg_scale, dt);
+  QIMG_LAUNCH_CHECK("cfg_euler_step_kernel");
+  return 0;
+}
+
+int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_stream_t stream) {
+  if (!problems) return fail("qimg_gemm: null problems");
+  return launch_gemm(problems, nprob, epilogue, (cudaStream_t)stream);
+}
+
+int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
+                    int T, float softmax_scale, qimg_stream_t stream) {
+  if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
+  const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
+  const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, 128);
+  const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, 128);
+  if (!tq || !tk || !tv) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    attr_set = true;
+  }
+  FmhaParams prm;
+  prm.out_txt = (bf16*)out_txt;
+  prm.out_img = (bf16*)out_img;
+  prm.B = B; prm.H = H; prm.S = S; prm.T = T;
+  prm.scale_log2 = softmax_scale * 1.4426950408889634f;
+  dim3 grid((S + 255) / 256, B * H);
+  fmha_joint_kernel<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, (cudaStream_t)stream>>>(*tq, *tk, *tv, prm);
+  QIMG_LAUNCH_CHECK("fmha_joint_kernel");
+  return 0;
+}
+
+int qimg_umma_probe(const void* A, const void* B, float* D, int N, int K, int mode, qimg_stream_t stream) {
+  if (N != 128 || K != 128) return fail("qimg_umma_probe: N and K must be 128");
+  if (mode < 0 || mode > 2) return fail("qimg_umma_probe: mode");
+  // A [128 rows, K] K-major.  B: mode 0 -> [N, K] (K contiguous); modes 1,2 -> [K, N] (N contiguous).
+  const CUtensorMap* ta = get_tmap_2d(A, 128, 128, 128);
+  const CUtensorMap* tb = get_tmap_2d(B, 128, 128, 128);
+  if (!ta || !tb) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024 + 256));
+    attr_set = true;
+  }
+  umma_probe_kernel<<<1, 192, 65536 + 1024 + 256, (cudaStream_t)stream>>>(*ta, *tb, (const bf16*)A, D, mode);
+  QIMG_LAUNCH_CHECK("umma_probe_kernel");
+  return 0;
+}
+
+}  // extern "C"

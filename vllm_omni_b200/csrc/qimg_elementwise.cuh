@@ -1,0 +1,255 @@
+// HBM-bound kernels of the Qwen-Image DiT hot path (sm_100a): 128-bit coalesced accesses,
+// one row per warp with the row held in registers, fp32 math with the reference's bf16
+// rounding points reproduced (rbf).  Grids are sized from the row count; every kernel
+// touches each byte exactly once (algorithmic bytes in DESIGN.md).
+#pragma once
+
+#include "qimg_common.cuh"
+
+namespace qimg {
+
+constexpr int EW_MAX_CHUNKS = 16;  // 16 x 256 = 4096 elements per row max (D=3072, joint_dim=3584)
+
+// y = bf16( bf16( bf16(LN(x)) * bf16(1 + scale) ) + shift )
+// Reference: AdaLayerNorm.forward_native, layers/adalayernorm.py:94-102 (LayerNorm no affine,
+// eps 1e-6, then `* (1 + scale) + shift`, 4 separate ATen kernels there).
+// shift/scale are [*, D] slices of the modulation buffer, row -> batch = row / rows_per_batch.
+__global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
+                                                          const bf16* __restrict__ scale, bf16* __restrict__ y, int rows,
+                                                          int D, int rows_per_batch, long long mod_stride, float eps) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nch = (D + 255) >> 8;
+  const bf16* xr = x + (size_t)row * D;
+  uint4 v[EW_MAX_CHUNKS];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < EW_MAX_CHUNKS; ++i) {
+    const int e = i * 256 + lane * 8;
+    if (i < nch && e < D) {
+      v[i] = ldg_nc_v4(xr + e);
+      sum += bf16lo(v[i].x) + bf16hi(v[i].x) + bf16lo(v[i].y) + bf16hi(v[i].y) + bf16lo(v[i].z) + bf16hi(v[i].z) +
+             bf16lo(v[i].w) + bf16hi(v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < EW_MAX_CHUNKS; ++i) {
+    const int e = i * 256 + lane * 8;
+    if (i < nch && e < D) {
+      uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a = bf16lo(w[k]) - mean, b = bf16hi(w[k]) - mean;
+        sq += a * a + b * b;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+  const int b = row / rows_per_batch;
+  const bf16* sh = shift + (size_t)b * mod_stride;
+  const bf16* sc = scale + (size_t)b * mod_stride;
+  bf16* yr = y + (size_t)row * D;
+#pragma unroll
+  for (int i = 0; i < EW_MAX_CHUNKS; ++i) {
+    const int e = i * 256 + lane * 8;
+    if (i < nch && e < D) {
+      uint4 shv = __ldg(reinterpret_cast<const uint4*>(sh + e));
+      uint4 scv = __ldg(reinterpret_cast<const uint4*>(sc + e));
+      uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint32_t s1[4] = {shv.x, shv.y, shv.z, shv.w}, s2[4] = {scv.x, scv.y, scv.z, scv.w}, o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float n0 = rbf((bf16lo(w[k]) - mean) * rstd), n1 = rbf((bf16hi(w[k]) - mean) * rstd);
+        float g0 = rbf(1.0f + bf16lo(s2[k])), g1 = rbf(1.0f + bf16hi(s2[k]));
+        float o0 = rbf(rbf(n0 * g0) + bf16lo(s1[k])), o1 = rbf(rbf(n1 * g1) + bf16hi(s1[k]));
+        o[k] = pack_bf16x2(o0, o1);
+      }
+      stg_v4(yr + e, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+// y = bf16( bf16(x * rsqrt(mean(x^2) + eps)) * w )     (vLLM RMSNorm, used for txt_norm :758)
+__global__ void __launch_bounds__(128) rms_norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                       bf16* __restrict__ y, int rows, int D, float eps) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nch = (D + 255) >> 8;
+  const bf16* xr = x + (size_t)row * D;
+  uint4 v[EW_MAX_CHUNKS];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < EW_MAX_CHUNKS; ++i) {
+    const int e = i * 256 + lane * 8;
+    if (i < nch && e < D) {
+      v[i] = ldg_nc_v4(xr + e);
+      uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sq += bf16lo(u[k]) * bf16lo(u[k]) + bf16hi(u[k]) * bf16hi(u[k]);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+  bf16* yr = y + (size_t)row * D;
+#pragma unroll
+  for (int i = 0; i < EW_MAX_CHUNKS; ++i) {
+    const int e = i * 256 + lane * 8;
+    if (i < nch && e < D) {
+      uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + e));
+      uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, ww[4] = {wv.x, wv.y, wv.z, wv.w}, o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = pack_bf16x2(rbf(rbf(bf16lo(u[k]) * rstd) * bf16lo(ww[k])), rbf(rbf(bf16hi(u[k]) * rstd) * bf16hi(ww[k])));
+      stg_v4(yr + e, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+// x = bf16( x + bf16(gate * y) )    standalone form of qwen_image_transformer.py:586-587,592,597
+// (the hot path fuses this into the GEMM epilogue; this kernel backs the layer-level plug-in API)
+__global__ void __launch_bounds__(256) gate_residual_kernel(bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                            const bf16* __restrict__ gate, long long n_vec, int D,
+                                                            int rows_per_batch, long long gate_stride) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int dv = D >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const long long row = i / dv;
+    const int col = (int)(i - row * dv) << 3;
+    const long long b = row / rows_per_batch;
+    uint4 xv = ldg_v4(x + i * 8), yv = ldg_nc_v4(y + i * 8);
+    uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate + b * gate_stride + col));
+    uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = pack_bf16x2(rbf(bf16lo(xw[k]) + rbf(bf16lo(gw[k]) * bf16lo(yw[k]))),
+                         rbf(bf16hi(xw[k]) + rbf(bf16hi(gw[k]) * bf16hi(yw[k]))));
+    stg_v4(x + i * 8, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// Small-M linear ("GEMV"): y[m, n] = bf16( sum_k act(x[m,k]) * W[n,k] + bias[n] ), M <= 8 per pass.
+// HBM-bound on W (read exactly once).  Used for the timestep MLP (qwen_image_transformer.py:50-62),
+// all 2*L modulation projections img_mod/txt_mod (:552-557, batched into ONE launch over the
+// concatenated [L*2*6D, D] weight) and norm_out.linear (:797).  act = SiLU on the input when ACT_SILU.
+template <int MAXM>
+__global__ void __launch_bounds__(256) linear_small_m_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W,
+                                                             const bf16* __restrict__ bias, bf16* __restrict__ y, int M,
+                                                             long long N, int K, long long ldy, int act_silu) {
+  extern __shared__ uint8_t smem_raw[];
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);  // [M][K], activation applied, bf16-rounded like the reference
+  for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+    float v = __bfloat162float(x[i]);
+    if (act_silu) v = rbf(silu_f(v));
+    xs[i] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  const int kv = K >> 3;  // 16-byte vectors per row
+  for (long long n = (long long)blockIdx.x * (blockDim.x >> 5) + warp; n < N; n += warps_total) {
+    const bf16* wr = W + n * K;
+    float acc[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
+    for (int c = lane; c < kv; c += 32) {
+      uint4 wv = ldg_nc_v4(wr + c * 8);
+      uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int m = 0; m < MAXM; ++m) {
+        if (m < M) {
+          uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)m * K + c * 8);
+          uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            acc[m] = fmaf(bf16lo(ww[k]), bf16lo(xw[k]), acc[m]);
+            acc[m] = fmaf(bf16hi(ww[k]), bf16hi(xw[k]), acc[m]);
+          }
+        }
+      }
+    }
+    const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+      if (m < M) {
+        float s = warp_sum(acc[m]);
+        if (lane == 0) y[(size_t)m * ldy + n] = __float2bfloat16_rn(s + bv);
+      }
+    }
+  }
+}
+
+// Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0, scale=1000) -> bf16 [B,256] = [cos | sin]
+// (qwen_image_transformer.py:44,51-52; restated in-tree at pipeline_qwen_image.py:135-184)
+__global__ void timestep_sinusoid_kernel(const bf16* __restrict__ t, bf16* __restrict__ out, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 256) return;
+  const int b = i >> 8, j = i & 255;
+  const int f = j & 127;
+  const float freq = expf(-9.210340371976184f * (float)f / 128.0f);
+  const float arg = 1000.0f * (__bfloat162float(t[b]) * freq);
+  out[i] = __float2bfloat16_rn(j < 128 ? cosf(arg) : sinf(arg));
+}
+
+// Fused true-CFG combine + norm rescale + flow-match Euler update, one pass over the latents.
+//   comb = neg + s*(pos-neg); noise = comb * (||pos|| / ||comb||)   pipeline_qwen_image.py:580-583
+//   x    = bf16( float(x) + bf16(dt * noise) )                      FlowMatchEulerDiscreteScheduler.step (:585)
+// Rows have C = 64 channels (128 B): 8 lanes x 16 B per row, 4 rows per warp instruction.
+// neg == nullptr -> no CFG (noise = pos).
+__global__ void __launch_bounds__(256) cfg_euler_step_kernel(const bf16* __restrict__ pos, const bf16* __restrict__ neg,
+                                                             bf16* __restrict__ x, long long rows, float cfg_scale,
+                                                             float dt) {
+  const long long vec = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte vector per thread
+  const long long row = vec >> 3;
+  const bool active = row < rows;
+  uint32_t pw[4] = {0, 0, 0, 0}, nw[4] = {0, 0, 0, 0}, xw[4] = {0, 0, 0, 0};
+  if (active) {
+    uint4 pv = ldg_nc_v4(pos + vec * 8);
+    pw[0] = pv.x; pw[1] = pv.y; pw[2] = pv.z; pw[3] = pv.w;
+    uint4 xv = ldg_v4(x + vec * 8);
+    xw[0] = xv.x; xw[1] = xv.y; xw[2] = xv.z; xw[3] = xv.w;
+    if (neg) {
+      uint4 nv = ldg_nc_v4(neg + vec * 8);
+      nw[0] = nv.x; nw[1] = nv.y; nw[2] = nv.z; nw[3] = nv.w;
+    }
+  }
+  float noise[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    noise[2 * k] = bf16lo(pw[k]);
+    noise[2 * k + 1] = bf16hi(pw[k]);
+  }
+  if (neg) {  // uniform branch
+    float comb[8], pp = 0.f, cc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float n0 = bf16lo(nw[k]), n1 = bf16hi(nw[k]);
+      comb[2 * k] = rbf(n0 + rbf(cfg_scale * rbf(noise[2 * k] - n0)));
+      comb[2 * k + 1] = rbf(n1 + rbf(cfg_scale * rbf(noise[2 * k + 1] - n1)));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      pp += noise[k] * noise[k];
+      cc += comb[k] * comb[k];
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      pp += __shfl_xor_sync(0xffffffffu, pp, o);
+      cc += __shfl_xor_sync(0xffffffffu, cc, o);
+    }
+    const float ratio = rbf(rbf(sqrtf(pp)) / rbf(sqrtf(cc)));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) noise[k] = rbf(comb[k] * ratio);
+  }
+  if (active) {
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = pack_bf16x2(bf16lo(xw[k]) + rbf(dt * noise[2 * k]), bf16hi(xw[k]) + rbf(dt * noise[2 * k + 1]));
+    stg_v4(x + vec * 8, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+}  // namespace qimg

@@ -1,0 +1,293 @@
+// Joint (text + image) non-causal attention for the Qwen-Image MMDiT block, sm_100a.
+//
+// Replaces Attention.forward -> SDPAImpl.forward (reference attention/layer.py:54-70,
+// backends/sdpa.py:46-66) plus the torch.cat / permute / split copies around it
+// (qwen_image_transformer.py:414-416, 444-449): Q/K/V arrive head-major
+// [B, H, S = T + S_img, 128] (written directly by the QKV GEMM epilogue) and the output is
+// written straight into the two per-stream [rows, H*128] buffers the out-projections read.
+//
+// FA4-style structure, one CTA per (256 query rows, batch*head), 320 threads:
+//   warp 0    : TMA producer (Q once; K and V tiles through separate 2-stage mbarrier rings)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2-5 : softmax warpgroup for query tile 0 (one thread per query row)
+//   warps 6-9 : softmax warpgroup for query tile 1
+// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each.  P (bf16) overwrites the
+// first 64 columns of its S tile and feeds the P*V MMA as the TMEM A operand; V is consumed
+// in its natural [kv, hd] layout as an MN-major B operand.  The MMA issue order
+// QK0(j) PV1(j-1) QK1(j) PV0(j) keeps the tensor pipe busy while the other tile's softmax runs.
+// Online softmax with lazy (warp-uniform, threshold 2^8) rescaling of the O accumulator.
+#pragma once
+
+#include "qimg_common.cuh"
+
+namespace qimg {
+
+constexpr int FMHA_THREADS = 320;
+constexpr int FMHA_KS = 2;
+constexpr int FMHA_VS = 2;
+constexpr int FMHA_TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 64-column SW128 slabs of 16 KB
+constexpr int FMHA_SMEM_BYTES = (2 + FMHA_KS + FMHA_VS) * FMHA_TILE_BYTES + 1024 + 256;
+
+struct FmhaParams {
+  bf16* out_txt;  // [B*T, H*128]
+  bf16* out_img;  // [B*S_img, H*128]
+  int B, H, S, T;
+  float scale_log2;  // softmax_scale * log2(e)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(FMHA_THREADS, 1)
+fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // 2 tiles
+  uint8_t* sK = smem + 2 * FMHA_TILE_BYTES;             // KS tiles
+  uint8_t* sV = sK + FMHA_KS * FMHA_TILE_BYTES;         // VS tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FMHA_VS * FMHA_TILE_BYTES);
+  uint64_t* q_full = bars;              // [1]
+  uint64_t* k_full = bars + 1;          // [KS]
+  uint64_t* k_empty = k_full + FMHA_KS;
+  uint64_t* v_full = k_empty + FMHA_KS;
+  uint64_t* v_empty = v_full + FMHA_VS;
+  uint64_t* s_full = v_empty + FMHA_VS;  // [2]
+  uint64_t* p_ready = s_full + 2;        // [2]
+  uint64_t* o_full = p_ready + 2;        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int q_row0 = blockIdx.x * 256;
+  const int n_kv = (prm.S + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FMHA_KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < FMHA_VS; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * FMHA_TILE_BYTES);
+      for (int t = 0; t < 2; ++t)
+        for (int s = 0; s < 2; ++s)
+          tma_load_3d(sQ + t * FMHA_TILE_BYTES + s * 16384, &tmQ, q_full, s * 64, q_row0 + t * 128, bh);
+      for (int j = 0; j < n_kv; ++j) {
+        const int ks = j % FMHA_KS, vs = j % FMHA_VS;
+        mbar_wait(&k_empty[ks], ((j / FMHA_KS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[ks], FMHA_TILE_BYTES);
+        for (int s = 0; s < 2; ++s)
+          tma_load_3d(sK + ks * FMHA_TILE_BYTES + s * 16384, &tmK, &k_full[ks], s * 64, j * 128, bh);
+        mbar_wait(&v_empty[vs], ((j / FMHA_VS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[vs], FMHA_TILE_BYTES);
+        for (int s = 0; s < 2; ++s)
+          tma_load_3d(sV + vs * FMHA_TILE_BYTES + s * 16384, &tmV, &v_full[vs], s * 64, j * 128, bh);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
+      const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
+      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+      auto issue_qk = [&](int t, int ks) {
+        const uint32_t qa = smem_u32(sQ + t * FMHA_TILE_BYTES);
+        const uint32_t ka = smem_u32(sK + ks * FMHA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(tS[t], make_kmajor_sw128_desc(qa + off), make_kmajor_sw128_desc(ka + off), IDESC_QK, k != 0);
+        }
+      };
+      auto issue_pv = [&](int t, int vs, bool accumulate) {
+        const uint32_t va = smem_u32(sV + vs * FMHA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // A = P (bf16 pairs, 8 TMEM columns per K=16 step); B = V rows [16k, 16k+16) x 128 (MN-major)
+          umma_ts(tO[t], tS[t] + k * 8, make_mnmajor_sw128_desc(va + k * 2048, 16384), IDESC_PV,
+                  (accumulate || k != 0) ? 1u : 0u);
+        }
+      };
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int ks = j % FMHA_KS;
+        mbar_wait(&k_full[ks], (j / FMHA_KS) & 1);
+        tc_fence_after();
+        issue_qk(0, ks);
+        umma_commit(&s_full[0]);
+        if (j > 0) {
+          mbar_wait(&p_ready[1], (j - 1) & 1);
+          tc_fence_after();
+          issue_pv(1, (j - 1) % FMHA_VS, j - 1 > 0);
+          umma_commit(&v_empty[(j - 1) % FMHA_VS]);
+        }
+        issue_qk(1, ks);
+        umma_commit(&s_full[1]);
+        umma_commit(&k_empty[ks]);
+        const int vs = j % FMHA_VS;
+        mbar_wait(&v_full[vs], (j / FMHA_VS) & 1);
+        mbar_wait(&p_ready[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, vs, j > 0);
+      }
+      mbar_wait(&p_ready[1], (n_kv - 1) & 1);
+      tc_fence_after();
+      issue_pv(1, (n_kv - 1) % FMHA_VS, n_kv - 1 > 0);
+      umma_commit(&v_empty[(n_kv - 1) % FMHA_VS]);
+      umma_commit(&o_full[0]);
+      umma_commit(&o_full[1]);
+    }
+  } else {
+    // ===================== softmax / correction / output warps =====================
+    const int t = (warp - 2) >> 2;  // query tile handled by this warpgroup
+    const int q = warp & 3;         // TMEM lane quarter
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + t * 128;
+    const uint32_t tO = tmem_base + lane_off + 256 + t * 128;
+    const float c = prm.scale_log2;
+    float m_used = -INFINITY;  // row max (raw score units) the exponentials are referenced to
+    float l = 0.f;             // running row sum
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      const int kv_valid = prm.S - j * 128;  // < 128 only on a ragged last tile
+      // ---- pass 1: row max ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tS + cc * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(r[i]);
+          if (kv_valid < 128 && cc * 32 + i >= kv_valid) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const float m_new = fmaxf(m_used, mx);
+        const bool need = (m_new - m_used) * c > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // rescale O and l to the new reference max (PV(j-1) of this tile is complete: s_full(j)
+          // was committed after it in the in-order tensor pipe)
+          const float f = ex2_approx((m_used - m_new) * c);
+          l *= f;
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tO + cc * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            tmem_st_32x32b_x32(tO + cc * 32, r);
+          }
+          tmem_st_wait();
+          m_used = m_new;
+        }
+      }
+      // ---- pass 2: P = exp2(s*c - m*c), row sum, bf16 P -> TMEM (aliases S columns [0,64)) ----
+      const float mc = m_used * c;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tS + cc * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2_approx(__uint_as_float(r[2 * i]) * c - mc);
+          float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) * c - mc);
+          if (kv_valid < 128) {
+            if (cc * 32 + 2 * i >= kv_valid) p0 = 0.f;
+            if (cc * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
+          }
+          l += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x16(tS + cc * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[t]);
+    }
+    // ---- final: O / l -> bf16 -> smem (this tile's Q buffer is free now) -> coalesced stores ----
+    mbar_wait(&o_full[t], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    uint8_t* stg = sQ + t * FMHA_TILE_BYTES;  // 128 rows x 256 B
+    const int row = q * 32 + lane;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tO + cc * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+        v.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+        v.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+        v.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+        const int c16 = cc * 4 + g;  // 16-byte chunk index within the 256 B row
+        *reinterpret_cast<uint4*>(stg + row * 256 + ((c16 ^ (row & 7)) << 4)) = v;
+      }
+    }
+    __syncwarp();
+    const int b = bh / prm.H, h = bh - b * prm.H;
+    const int D = prm.H * 128;
+    const int S_img = prm.S - prm.T;
+#pragma unroll 1
+    for (int it = 0; it < 16; ++it) {
+      const int rr = q * 32 + it * 2 + (lane >> 4);
+      const int c16 = lane & 15;
+      const int pos = q_row0 + t * 128 + rr;
+      if (pos < prm.S) {
+        uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 256 + ((c16 ^ (rr & 7)) << 4));
+        bf16* dst = (pos < prm.T) ? prm.out_txt + ((size_t)b * prm.T + pos) * D
+                                  : prm.out_img + ((size_t)b * S_img + (pos - prm.T)) * D;
+        stg_v4(dst + h * 128 + c16 * 8, v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace qimg

@@ -1,0 +1,370 @@
+// tcgen05 (UMMA) persistent, warp-specialised bf16 GEMM for sm_100a with fused epilogues.
+//
+//   out[M,N] = A[M,K] * W[N,K]^T  (nn.Linear layout: both operands K-major) + epilogue
+//
+// Replaces (reference file:line, all cuBLAS + separate ATen kernels there):
+//   to_qkv / add_kv_proj + norm_q/k + rope + cat  qwen_image_transformer.py:380-416   -> EPI_QKV
+//   to_out[0] / to_add_out + gate*x + residual    :452-456, 586-587                   -> EPI_BIAS_GATE_RES
+//   img_mlp/txt_mlp net.0.proj + gelu(tanh)       :491,501,591,596                    -> EPI_BIAS_GELU
+//   net.2 + gate*x + residual                     :592,597                            -> EPI_BIAS_GATE_RES
+//   img_in / txt_in / proj_out                    :743,759,798                        -> EPI_BIAS
+// The image and text streams (different weights, M_txt << M_img) are GROUPED in one
+// launch so the small text GEMM fills the tail instead of starving 140 SMs.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage mbarrier ring)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
+//   warps 2-5: epilogue: tcgen05.ld accumulator rows -> fp32 math -> bf16 -> swizzled smem
+//              staging -> 128-byte coalesced global stores (residual / gate fused there)
+//   two TMEM accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the
+//   main loop of tile i+1.
+#pragma once
+
+#include "qimg_common.cuh"
+
+namespace qimg {
+
+enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_GATE_RES = 2, EPI_QKV = 3 };
+
+struct GemmProblem {
+  int M, N, K;
+  int rows_per_batch;  // rows of this stream per image (S_img or T)
+  const bf16* bias;    // [N]
+  bf16* out;           // EPI_BIAS / EPI_BIAS_GELU: output [M, ldo]; EPI_BIAS_GATE_RES: residual stream x (in/out)
+  int ldo;
+  const bf16* gate;  // EPI_BIAS_GATE_RES: gate[b * gate_stride + n]
+  long long gate_stride;
+  // EPI_QKV
+  bf16* q;  // joint [B, H, S_joint, 128]
+  bf16* k;
+  bf16* v;
+  const bf16* nq_w;  // RMSNorm weights [128]
+  const bf16* nk_w;
+  const bf16* cos;  // [rows_per_batch, 64]
+  const bf16* sin;
+  int S_joint, pos_off, H;
+  float eps;
+  // tile bookkeeping (filled by the host launcher)
+  int m_tiles, n_tiles, tile_begin;
+};
+
+struct GemmParams {
+  GemmProblem p[2];
+  int nprob;
+  int total_tiles;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_GROUP_M = 16;
+constexpr int GEMM_EPI_STAGE_BYTES = 4 * 32 * 128;  // 4 warps x 32 rows x 128 B
+
+template <int BN>
+constexpr int gemm_smem_bytes() {
+  return GEMM_STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + GEMM_EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+}
+
+struct TileCoord {
+  int pi, m_blk, n_blk;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& prm, int tile) {
+  TileCoord tc;
+  tc.pi = (prm.nprob > 1 && tile >= prm.p[1].tile_begin) ? 1 : 0;
+  const GemmProblem& P = prm.p[tc.pi];
+  int t = tile - P.tile_begin;
+  int per_band = GEMM_GROUP_M * P.n_tiles;
+  int band = t / per_band;
+  int within = t - band * per_band;
+  int m0 = band * GEMM_GROUP_M;
+  int gm = min(GEMM_GROUP_M, P.m_tiles - m0);
+  tc.m_blk = m0 + within % gm;
+  tc.n_blk = within / gm;
+  return tc;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ GemmParams prm) {
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  constexpr int B_BYTES = BN * GEMM_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages
+  constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_epi = smem + GEMM_STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + GEMM_EPI_STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + GEMM_STAGES;        // [STAGES]
+  uint64_t* tmem_full = bars + 2 * GEMM_STAGES;    // [2]
+  uint64_t* tmem_empty = bars + 2 * GEMM_STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (prm.nprob > 1) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int i = 0; i < GEMM_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        TileCoord tc = decode_tile(prm, tile);
+        const GemmProblem& P = prm.p[tc.pi];
+        const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
+        const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
+        const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sa, ta, &full_bar[stage], kb * GEMM_BK, tc.m_blk * GEMM_BM);
+          tma_load_2d(sb, tb, &full_bar[stage], kb * GEMM_BK, tc.n_blk * BN);
+          if (++stage == GEMM_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        TileCoord tc = decode_tile(prm, tile);
+        const GemmProblem& P = prm.p[tc.pi];
+        const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 B per K=16 step inside the 128 B swizzle row (descriptor start field is >>4)
+            umma_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs complete
+          if (++stage == GEMM_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int ew = warp - 2;      // staging slot
+    uint8_t* stg = smem_epi + ew * 4096;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      TileCoord tc = decode_tile(prm, tile);
+      const GemmProblem& P = prm.p[tc.pi];
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const int m_own = tc.m_blk * GEMM_BM + q * 32 + lane;  // this thread's accumulator row
+
+      // per-row constants for EPI_QKV
+      float rstd = 0.f;
+      const bf16* cos_row = nullptr;
+      const bf16* sin_row = nullptr;
+      if (EPI == EPI_QKV) {
+        int i_own = (m_own < P.M) ? (m_own % P.rows_per_batch) : 0;
+        cos_row = P.cos + (size_t)i_own * 64;
+        sin_row = P.sin + (size_t)i_own * 64;
+      }
+
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 64; ++chunk) {
+        const int n0 = tc.n_blk * BN + chunk * 64;
+        uint32_t r[64];
+        int which = 0, head = 0, half = 0;
+        if (EPI == EPI_QKV) {
+          const int D = P.N / 3;
+          which = n0 / D;                 // 0 = q, 1 = k, 2 = v
+          head = (n0 - which * D) >> 7;   // head index
+          half = (n0 >> 6) & 1;           // which 64-column half of the head
+          if (which < 2 && half == 0 && n0 < P.N) {
+            // pass 1 over the whole head (128 columns): sum of squares of bf16(acc + bias)
+            float ss = 0.f;
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint32_t t[32];
+              tmem_ld_32x32b_x32(t_row + chunk * 64 + c4 * 32, t);
+              tmem_ld_wait();
+              const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0 + c4 * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 bv = __ldg(bp + j);
+                uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float v0 = rbf(__uint_as_float(t[j * 8 + e * 2]) + bf16lo(bw[e]));
+                  float v1 = rbf(__uint_as_float(t[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
+                  ss += v0 * v0 + v1 * v1;
+                }
+              }
+            }
+            rstd = rsqrtf(ss * (1.0f / 128.0f) + P.eps);
+          }
+        }
+        tmem_ld_32x32b_x32(t_row + chunk * 64, r);
+        tmem_ld_32x32b_x32(t_row + chunk * 64 + 32, r + 32);
+        tmem_ld_wait();
+
+        // ---- math on this thread's 64 columns -> 32 packed bf16x2 words ----
+        uint32_t pk[32];
+        if (n0 < P.N) {
+          const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 bv = __ldg(bp + j);
+            uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+            uint32_t nw[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0}, sw[4] = {0, 0, 0, 0};
+            if (EPI == EPI_QKV && which < 2) {
+              const bf16* nwp = (which == 0 ? P.nq_w : P.nk_w) + half * 64 + j * 8;
+              uint4 nv = __ldg(reinterpret_cast<const uint4*>(nwp));
+              nw[0] = nv.x; nw[1] = nv.y; nw[2] = nv.z; nw[3] = nv.w;
+              if ((j & 1) == 0) {
+                // 8 columns = 4 pairs -> 4 cos / 4 sin values (8 B each); load 16 B every other j
+              }
+              const uint2 cv = __ldg(reinterpret_cast<const uint2*>(cos_row + half * 32 + j * 4));
+              const uint2 sv = __ldg(reinterpret_cast<const uint2*>(sin_row + half * 32 + j * 4));
+              cw[0] = cv.x; cw[1] = cv.y; sw[0] = sv.x; sw[1] = sv.y;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float v0 = rbf(__uint_as_float(r[j * 8 + e * 2]) + bf16lo(bw[e]));
+              float v1 = rbf(__uint_as_float(r[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
+              if (EPI == EPI_BIAS_GELU) {
+                v0 = gelu_tanh_f(v0);
+                v1 = gelu_tanh_f(v1);
+              }
+              if (EPI == EPI_QKV && which < 2) {
+                // RMSNorm: fp32 normalise -> bf16 -> * weight -> bf16   (vLLM rms_norm)
+                float x1 = rbf(rbf(v0 * rstd) * bf16lo(nw[e]));
+                float x2 = rbf(rbf(v1 * rstd) * bf16hi(nw[e]));
+                // interleaved RoPE with bf16 cos/sin: x*cos + rotate_half(x)*sin, every op rounded
+                uint32_t cpair = cw[e >> 1], spair = sw[e >> 1];
+                float c = (e & 1) ? bf16hi(cpair) : bf16lo(cpair);
+                float s = (e & 1) ? bf16hi(spair) : bf16lo(spair);
+                v0 = rbf(rbf(x1 * c) + rbf(-x2 * s));
+                v1 = rbf(rbf(x2 * c) + rbf(x1 * s));
+              }
+              pk[j * 4 + e] = pack_bf16x2(v0, v1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pk[j] = 0;
+        }
+
+        // ---- stage to smem (16 B chunk index XOR row&7 -> conflict-free), then coalesced stores ----
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v = make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+        }
+        __syncwarp();
+        const int c16 = lane & 7;
+        const int gn = n0 + c16 * 8;
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const int gm = tc.m_blk * GEMM_BM + q * 32 + rr;
+          uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+          if (gm < P.M && gn < P.N) {
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+              stg_v4(P.out + (size_t)gm * P.ldo + gn, v);
+            } else if (EPI == EPI_BIAS_GATE_RES) {
+              const int b = gm / P.rows_per_batch;
+              bf16* xp = P.out + (size_t)gm * P.ldo + gn;
+              uint4 xv = ldg_v4(xp);
+              uint4 gv = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)b * P.gate_stride + gn));
+              uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, yw[4] = {v.x, v.y, v.z, v.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float o0 = rbf(bf16lo(xw[e]) + rbf(bf16lo(gw[e]) * bf16lo(yw[e])));
+                float o1 = rbf(bf16hi(xw[e]) + rbf(bf16hi(gw[e]) * bf16hi(yw[e])));
+                ow[e] = pack_bf16x2(o0, o1);
+              }
+              stg_v4(xp, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+            } else {  // EPI_QKV: scatter into the joint [B,H,S,128] head-major layout
+              const int b = gm / P.rows_per_batch;
+              const int i = gm - b * P.rows_per_batch;
+              bf16* base = (which == 0) ? P.q : (which == 1 ? P.k : P.v);
+              size_t off = (((size_t)b * P.H + head) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
+              stg_v4(base + off, v);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace qimg

@@ -1,0 +1,239 @@
+"""ctypes binding of the C-ABI library `csrc/libqimg_b200.so` (include/qimg_b200.h).
+
+PyTorch is plumbing here: tensors own the device memory, `tensor.data_ptr()` and the
+current stream's handle cross the C ABI.  There is NO fallback path: if the library is
+missing or a call fails, a RuntimeError is raised (the reference's worker turns that
+into DiffusionOutput(error=...), diffusion/worker/gpu_worker.py:267-274).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libqimg_b200.so")
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_QKV = 0, 1, 2, 3
+
+# every symbol declared in include/qimg_b200.h (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = [
+    "qimg_abi_version", "qimg_last_error", "qimg_device_check", "qimg_launch_count", "qimg_reset_launch_count",
+    "qimg_ln_modulate", "qimg_gate_residual", "qimg_rms_norm", "qimg_linear_small_m", "qimg_timestep_sinusoid",
+    "qimg_cfg_euler_step", "qimg_gemm", "qimg_fmha_joint", "qimg_engine_create", "qimg_engine_destroy",
+    "qimg_engine_workspace_bytes", "qimg_engine_forward", "qimg_engine_ws_offset_img", "qimg_engine_ws_offset_txt",
+    "qimg_umma_probe",
+]
+
+
+class GemmProblem(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("rows_per_batch", C.c_int),
+        ("out", C.c_void_p), ("ldo", C.c_int), ("gate", C.c_void_p), ("gate_stride", C.c_longlong),
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("norm_q_w", C.c_void_p), ("norm_k_w", C.c_void_p), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("S_joint", C.c_int), ("pos_off", C.c_int), ("H", C.c_int), ("eps", C.c_float),
+    ]
+
+
+class Dims(C.Structure):
+    _fields_ = [("num_layers", C.c_int), ("num_heads", C.c_int), ("head_dim", C.c_int), ("in_channels", C.c_int),
+                ("out_dim", C.c_int), ("joint_dim", C.c_int), ("eps", C.c_float)]
+
+
+BLOCK_FIELDS = [
+    "img_mod_w", "img_mod_b", "txt_mod_w", "txt_mod_b", "to_qkv_w", "to_qkv_b", "add_kv_w", "add_kv_b",
+    "norm_q", "norm_k", "norm_added_q", "norm_added_k", "to_out_w", "to_out_b", "to_add_out_w", "to_add_out_b",
+    "img_mlp_w1", "img_mlp_b1", "img_mlp_w2", "img_mlp_b2", "txt_mlp_w1", "txt_mlp_b1", "txt_mlp_w2", "txt_mlp_b2",
+]
+GLOBAL_FIELDS = [
+    "t_lin1_w", "t_lin1_b", "t_lin2_w", "t_lin2_b", "txt_norm_w", "img_in_w", "img_in_b", "txt_in_w", "txt_in_b",
+    "norm_out_w", "norm_out_b", "proj_out_w", "proj_out_b", "mod_all_w", "mod_all_b",
+]
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in BLOCK_FIELDS]
+
+
+class GlobalWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in GLOBAL_FIELDS]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU/PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, ll, f, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+    lib.qimg_abi_version.restype = i
+    lib.qimg_last_error.restype = C.c_char_p
+    lib.qimg_device_check.argtypes = [C.POINTER(i)]
+    lib.qimg_launch_count.restype = ll
+    lib.qimg_reset_launch_count.restype = None
+    lib.qimg_ln_modulate.argtypes = [vp, vp, vp, vp, i, i, i, ll, f, vp]
+    lib.qimg_gate_residual.argtypes = [vp, vp, vp, i, i, i, ll, vp]
+    lib.qimg_rms_norm.argtypes = [vp, vp, vp, i, i, f, vp]
+    lib.qimg_linear_small_m.argtypes = [vp, vp, vp, vp, i, ll, i, ll, i, vp]
+    lib.qimg_timestep_sinusoid.argtypes = [vp, vp, i, vp]
+    lib.qimg_cfg_euler_step.argtypes = [vp, vp, vp, ll, i, f, f, f, vp]
+    lib.qimg_gemm.argtypes = [C.POINTER(GemmProblem), i, i, vp]
+    lib.qimg_fmha_joint.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, f, vp]
+    lib.qimg_engine_create.argtypes = [C.POINTER(Dims), C.POINTER(GlobalWeights), C.POINTER(BlockWeights), C.POINTER(vp)]
+    lib.qimg_engine_destroy.argtypes = [vp]
+    lib.qimg_engine_destroy.restype = None
+    lib.qimg_engine_workspace_bytes.argtypes = [vp, i, i, i]
+    lib.qimg_engine_workspace_bytes.restype = sz
+    lib.qimg_engine_ws_offset_img.argtypes = [vp, i, i, i]
+    lib.qimg_engine_ws_offset_img.restype = sz
+    lib.qimg_engine_ws_offset_txt.argtypes = [vp, i, i, i]
+    lib.qimg_engine_ws_offset_txt.restype = sz
+    lib.qimg_engine_forward.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp, sz, vp]
+    lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("qimg_abi_version",):
+            pass
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "qimg"):
+    if rc != 0:
+        msg = load().qimg_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "qimg_b200 ops take CUDA tensors only (no CPU fallback)"
+    return t.data_ptr()
+
+
+def _bf16c(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.bfloat16, f"expected bf16, got {t.dtype}"
+    assert t.is_contiguous(), "expected a contiguous tensor"
+    return t
+
+
+def device_check() -> int:
+    n = C.c_int(0)
+    check(load().qimg_device_check(C.byref(n)), "qimg_device_check")
+    return n.value
+
+
+def launch_count() -> int:
+    return int(load().qimg_launch_count())
+
+
+def reset_launch_count():
+    load().qimg_reset_launch_count()
+
+
+# ----------------------------------------------------------------------------------------
+# thin tensor-level wrappers
+# ----------------------------------------------------------------------------------------
+def ln_modulate(x, shift, scale, rows_per_batch: int, mod_stride: int, eps: float = 1e-6, out=None):
+    """x [rows, D]; shift/scale are (views into) modulation rows; see qimg_ln_modulate."""
+    _bf16c(x)
+    rows, D = x.shape
+    out = torch.empty_like(x) if out is None else out
+    check(load().qimg_ln_modulate(_p(x), _p(shift), _p(scale), _p(out), rows, D, rows_per_batch, mod_stride, eps,
+                                  stream_ptr()), "qimg_ln_modulate")
+    return out
+
+
+def gate_residual(x, y, gate, rows_per_batch: int, gate_stride: int):
+    _bf16c(x), _bf16c(y)
+    rows, D = x.shape
+    check(load().qimg_gate_residual(_p(x), _p(y), _p(gate), rows, D, rows_per_batch, gate_stride, stream_ptr()),
+          "qimg_gate_residual")
+    return x
+
+
+def rms_norm(x, w, eps: float = 1e-6):
+    _bf16c(x), _bf16c(w)
+    rows, D = x.shape
+    out = torch.empty_like(x)
+    check(load().qimg_rms_norm(_p(x), _p(w), _p(out), rows, D, eps, stream_ptr()), "qimg_rms_norm")
+    return out
+
+
+def linear_small_m(x, W, bias, act_silu: bool, out=None):
+    _bf16c(x), _bf16c(W)
+    M, K = x.shape
+    N = W.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device) if out is None else out
+    check(load().qimg_linear_small_m(_p(x), _p(W), _p(bias), _p(out), M, N, K, out.stride(0), int(act_silu), stream_ptr()),
+          "qimg_linear_small_m")
+    return out
+
+
+def timestep_sinusoid(t):
+    _bf16c(t)
+    out = torch.empty((t.numel(), 256), dtype=torch.bfloat16, device=t.device)
+    check(load().qimg_timestep_sinusoid(_p(t), _p(out), t.numel(), stream_ptr()), "qimg_timestep_sinusoid")
+    return out
+
+
+def cfg_euler_step(pos, neg, latents, cfg_scale: float, sigma: float, sigma_next: float):
+    """In-place on `latents` [.., 64]."""
+    _bf16c(pos), _bf16c(latents)
+    if neg is not None:
+        _bf16c(neg)
+    rows = latents.numel() // latents.shape[-1]
+    check(load().qimg_cfg_euler_step(_p(pos), _p(neg), _p(latents), rows, latents.shape[-1], cfg_scale, sigma, sigma_next,
+                                     stream_ptr()), "qimg_cfg_euler_step")
+    return latents
+
+
+def gemm(problems: list[GemmProblem], epilogue: int):
+    arr = (GemmProblem * len(problems))(*problems)
+    check(load().qimg_gemm(arr, len(problems), epilogue, stream_ptr()), "qimg_gemm")
+
+
+def linear(x, W, bias, epilogue: int = EPI_BIAS, out=None):
+    """Single-problem convenience: out[M,N] = x[M,K] @ W[N,K]^T + bias (optionally GELU)."""
+    _bf16c(x), _bf16c(W), _bf16c(bias)
+    M, K = x.shape
+    N = W.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device) if out is None else out
+    p = GemmProblem(A=_p(x), W=_p(W), bias=_p(bias), M=M, N=N, K=K, rows_per_batch=max(M, 1), out=_p(out), ldo=out.stride(0))
+    gemm([p], epilogue)
+    return out
+
+
+def fmha_joint(q, k, v, T: int, softmax_scale: float, out_txt=None, out_img=None):
+    """q,k,v [B,H,S,128] head-major -> (out_txt [B*T, H*128], out_img [B*(S-T), H*128])."""
+    for t in (q, k, v):
+        _bf16c(t)
+    B, H, S, hd = q.shape
+    assert hd == 128
+    if out_txt is None:
+        out_txt = torch.empty((B * T, H * 128), dtype=torch.bfloat16, device=q.device)
+    if out_img is None:
+        out_img = torch.empty((B * (S - T), H * 128), dtype=torch.bfloat16, device=q.device)
+    check(load().qimg_fmha_joint(_p(q), _p(k), _p(v), _p(out_txt), _p(out_img), B, H, S, T, softmax_scale, stream_ptr()),
+          "qimg_fmha_joint")
+    return out_txt, out_img
+
+
+def umma_probe(A, Bm, mode: int):
+    D = torch.empty((128, 128), dtype=torch.float32, device=A.device)
+    check(load().qimg_umma_probe(_p(A), _p(Bm), _p(D), 128, 128, mode, stream_ptr()), "qimg_umma_probe")
+    return D
