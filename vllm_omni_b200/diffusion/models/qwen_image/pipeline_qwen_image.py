@@ -1,0 +1,299 @@
+"""B200-native Qwen-Image denoise pipeline — host-side mirror of the reference
+`QwenImagePipeline` (vllm_omni/diffusion/models/qwen_image/pipeline_qwen_image.py:235-754)
+for the part SURVEY.md §8 puts on the hot path: `prepare_latents`, `prepare_timesteps`,
+the 50-step `diffuse()` loop with true-CFG + norm rescale + flow-match Euler step.
+
+Prompt encoding (Qwen2.5-VL) and VAE decode run once per image, are unchanged reference
+code and out of scope (§8f N1): this class takes pre-computed `prompt_embeds` and returns
+latents (`output_type="latent"`) unless a text encoder / VAE object is injected.
+
+Every arithmetic op runs in the C-ABI sm_100a library; the loop issues no host<->device
+synchronisation (timesteps live on the device, sigmas are host floats).
+"""
+from __future__ import annotations
+
+import math
+from collections.abc import Iterable
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from vllm_omni_b200 import lib as qlib
+from vllm_omni_b200.diffusion.data import DiffusionOutput, OmniDiffusionConfig
+from vllm_omni_b200.diffusion.models.qwen_image.qwen_image_transformer import QwenImageTransformer2DModel
+from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+
+
+def calculate_shift(image_seq_len, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
+                    max_shift: float = 1.15):
+    """reference pipeline_qwen_image.py:63-73"""
+    m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    b = base_shift - m * base_seq_len
+    return image_seq_len * m + b
+
+
+class FlowMatchEulerDiscreteScheduler:
+    """Restatement of the diffusers scheduler the reference pipeline drives
+    (pipeline_qwen_image.py:18-20,116-131,545,585): dynamic exponential time shift, terminal
+    stretch, Euler step.  The config defaults are the Qwen-Image scheduler_config.json values
+    recalled in SURVEY.md §8c (assumptions; callers may pass explicit sigmas)."""
+
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, shift: float = 1.0, use_dynamic_shifting: bool = True,
+                 base_shift: float = 0.5, max_shift: float = 0.9, base_image_seq_len: int = 256,
+                 max_image_seq_len: int = 8192, shift_terminal: float | None = 0.02,
+                 time_shift_type: str = "exponential"):
+        self.config = dict(num_train_timesteps=num_train_timesteps, shift=shift, use_dynamic_shifting=use_dynamic_shifting,
+                           base_shift=base_shift, max_shift=max_shift, base_image_seq_len=base_image_seq_len,
+                           max_image_seq_len=max_image_seq_len, shift_terminal=shift_terminal,
+                           time_shift_type=time_shift_type)
+        self.sigmas: torch.Tensor | None = None      # fp32 [N+1] (host)
+        self.timesteps: torch.Tensor | None = None   # fp32 [N]   (host)
+        self._step_index: int | None = None
+        self._begin_index: int | None = None
+
+    def set_begin_index(self, begin_index: int = 0):
+        self._begin_index = begin_index
+
+    def time_shift(self, mu: float, sigma: float, t: np.ndarray):
+        if self.config["time_shift_type"] == "exponential":
+            return math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** sigma)
+        return mu / (mu + (1 / t - 1) ** sigma)  # "linear"
+
+    def stretch_shift_to_terminal(self, t: np.ndarray) -> np.ndarray:
+        one_minus_z = 1 - t
+        scale_factor = one_minus_z[-1] / (1 - self.config["shift_terminal"])
+        return 1 - (one_minus_z / scale_factor)
+
+    def set_timesteps(self, num_inference_steps: int | None = None, device=None, sigmas=None, mu: float | None = None):
+        n_train = self.config["num_train_timesteps"]
+        if sigmas is None:
+            ts = np.linspace(n_train, 1, num_inference_steps)
+            sigmas = ts / n_train
+        sigmas = np.array(sigmas).astype(np.float32)
+        if self.config["use_dynamic_shifting"]:
+            if mu is None:
+                raise ValueError("`mu` must be passed when `use_dynamic_shifting` is True")
+            sigmas = self.time_shift(mu, 1.0, sigmas)
+        else:
+            s = self.config["shift"]
+            sigmas = s * sigmas / (1 + (s - 1) * sigmas)
+        if self.config["shift_terminal"]:
+            sigmas = self.stretch_shift_to_terminal(sigmas)
+        sig = torch.from_numpy(np.asarray(sigmas, dtype=np.float32))
+        self.timesteps = sig * n_train
+        self.sigmas = torch.cat([sig, torch.zeros(1)])
+        self.num_inference_steps = len(sig)
+        self._step_index = None
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = False):
+        """x_{t-1} = bf16(float(x) + bf16(dt * v)) on the device (qimg_cfg_euler_step, no CFG)."""
+        if self._step_index is None:
+            self._step_index = self._begin_index or 0
+        sigma, sigma_next = float(self.sigmas[self._step_index]), float(self.sigmas[self._step_index + 1])
+        prev = sample.clone()
+        qlib.cfg_euler_step(model_output.contiguous(), None, prev, 1.0, sigma, sigma_next)
+        self._step_index += 1
+        return (prev,)
+
+
+@dataclass
+class ComponentSource:
+    """Same fields as DiffusersPipelineLoader.ComponentSource (reference diffusers_loader.py:40-60)."""
+
+    model_or_path: str
+    subfolder: str | None
+    revision: str | None
+    prefix: str = ""
+    fall_back_to_pt: bool = True
+
+
+class QwenImagePipeline(nn.Module):
+    def __init__(self, *, od_config: OmniDiffusionConfig, prefix: str = "", text_encoder=None, vae=None,
+                 transformer_kwargs: dict | None = None):
+        super().__init__()
+        self.od_config = od_config
+        self.weights_sources = [ComponentSource(model_or_path=od_config.model, subfolder="transformer", revision=None,
+                                                prefix="transformer.", fall_back_to_pt=True)]
+        self.scheduler = FlowMatchEulerDiscreteScheduler()
+        self.text_encoder = text_encoder
+        self.vae = vae
+        self.transformer = QwenImageTransformer2DModel(od_config=od_config, **(transformer_kwargs or {}))
+        self.vae_scale_factor = 8
+        self.default_sample_size = 128
+        self._interrupt = False
+        self._attention_kwargs = None
+        self._current_timestep = None
+        self._num_timesteps = 0
+
+    @property
+    def device(self):
+        return self.transformer.img_in.weight.device
+
+    @property
+    def interrupt(self):
+        return self._interrupt
+
+    @property
+    def attention_kwargs(self):
+        return self._attention_kwargs
+
+    def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
+        """(name, tensor) stream with the `transformer.` prefix of weights_sources (reference :752-754)."""
+        def strip(ws):
+            for n, t in ws:
+                if n.startswith("transformer."):
+                    yield n[len("transformer."):], t
+        return {"transformer." + n for n in self.transformer.load_weights(strip(weights))}
+
+    # ---- reference :435-488 ---------------------------------------------------------------------
+    @staticmethod
+    def _pack_latents(latents, batch_size, num_channels_latents, height, width):
+        latents = latents.view(batch_size, num_channels_latents, height // 2, 2, width // 2, 2)
+        latents = latents.permute(0, 2, 4, 1, 3, 5)
+        return latents.reshape(batch_size, (height // 2) * (width // 2), num_channels_latents * 4)
+
+    @staticmethod
+    def _unpack_latents(latents, height, width, vae_scale_factor):
+        batch_size, num_patches, channels = latents.shape
+        height = 2 * (int(height) // (vae_scale_factor * 2))
+        width = 2 * (int(width) // (vae_scale_factor * 2))
+        latents = latents.view(batch_size, height // 2, width // 2, channels // 4, 2, 2)
+        latents = latents.permute(0, 3, 1, 4, 2, 5)
+        return latents.reshape(batch_size, channels // (2 * 2), 1, height, width)
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
+        height = 2 * (int(height) // (self.vae_scale_factor * 2))
+        width = 2 * (int(width) // (self.vae_scale_factor * 2))
+        if latents is not None:
+            return latents.to(device=device, dtype=dtype)
+        shape = (batch_size, 1, num_channels_latents, height, width)
+        gdev = generator.device if isinstance(generator, torch.Generator) else "cpu"
+        noise = torch.randn(shape, generator=generator if isinstance(generator, torch.Generator) else None,
+                            device=gdev, dtype=dtype).to(device)
+        return self._pack_latents(noise, batch_size, num_channels_latents, height, width)
+
+    def prepare_timesteps(self, num_inference_steps, sigmas, image_seq_len):
+        """reference :492-509"""
+        sigmas = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps) if sigmas is None else sigmas
+        cfg = self.scheduler.config
+        mu = calculate_shift(image_seq_len, cfg.get("base_image_seq_len", 256), cfg.get("max_image_seq_len", 4096),
+                             cfg.get("base_shift", 0.5), cfg.get("max_shift", 1.15))
+        self.scheduler.set_timesteps(sigmas=sigmas, mu=mu)
+        return self.scheduler.timesteps, len(self.scheduler.timesteps)
+
+    # ---- the hot loop: reference :530-586 ---------------------------------------------------------
+    def diffuse(self, prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents,
+                img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale):
+        self.scheduler.set_begin_index(0)
+        dev = latents.device
+        latents = latents.to(torch.bfloat16).contiguous().clone()
+        sig = self.scheduler.sigmas  # host fp32 [N+1]
+        # `timestep = t.expand(B).to(latents.dtype)` then `/ 1000` (reference :552,558): same two bf16 roundings,
+        # computed once for all steps; one row per step, shared by the whole batch.
+        t_dev = (timesteps.to(torch.bfloat16) / 1000).to(dev).contiguous()
+        self.transformer.do_true_cfg = do_true_cfg
+        for i in range(len(timesteps)):
+            if self.interrupt:
+                continue
+            self._current_timestep = timesteps[i]
+            noise_pred = self.transformer(
+                hidden_states=latents, timestep=t_dev[i:i + 1], guidance=guidance,
+                encoder_hidden_states_mask=prompt_embeds_mask, encoder_hidden_states=prompt_embeds, img_shapes=img_shapes,
+                txt_seq_lens=txt_seq_lens, attention_kwargs=self.attention_kwargs, return_dict=False, uniform_timestep=True)[0]
+            neg_noise_pred = None
+            if do_true_cfg:
+                neg_noise_pred = self.transformer(
+                    hidden_states=latents, timestep=t_dev[i:i + 1], guidance=guidance,
+                    encoder_hidden_states_mask=negative_prompt_embeds_mask, encoder_hidden_states=negative_prompt_embeds,
+                    img_shapes=img_shapes, txt_seq_lens=negative_txt_seq_lens, attention_kwargs=self.attention_kwargs,
+                    return_dict=False, uniform_timestep=True)[0]
+            # fused: comb = neg + s (pos - neg); rescale by ||pos|| / ||comb||; x += (sigma_{i+1} - sigma_i) v
+            qlib.cfg_euler_step(noise_pred, neg_noise_pred, latents, float(true_cfg_scale), float(sig[i]), float(sig[i + 1]))
+        return latents
+
+    # ---- request entry point: reference :588-750 ----------------------------------------------------
+    @torch.inference_mode()
+    def forward(self, req: OmniDiffusionRequest, prompt=None, negative_prompt=None, true_cfg_scale: float = 4.0,
+                height: int | None = None, width: int | None = None, num_inference_steps: int = 50,
+                sigmas: list[float] | None = None, guidance_scale: float = 1.0, num_images_per_prompt: int = 1,
+                generator=None, latents=None, prompt_embeds=None, prompt_embeds_mask=None, negative_prompt_embeds=None,
+                negative_prompt_embeds_mask=None, output_type: str | None = "latent",
+                attention_kwargs: dict[str, Any] | None = None, max_sequence_length: int = 512) -> DiffusionOutput:
+        height = req.height or height or self.default_sample_size * self.vae_scale_factor
+        width = req.width or width or self.default_sample_size * self.vae_scale_factor
+        num_inference_steps = req.num_inference_steps or num_inference_steps
+        generator = req.generator or generator
+        if generator is None and req.seed is not None:
+            generator = torch.Generator().manual_seed(req.seed)
+        true_cfg_scale = req.true_cfg_scale or true_cfg_scale
+        sigmas = req.sigmas if req.sigmas is not None else sigmas
+        latents = req.latents if req.latents is not None else latents
+        output_type = req.output_type or output_type
+        if req.num_outputs_per_prompt and req.num_outputs_per_prompt > 0:
+            num_images_per_prompt = req.num_outputs_per_prompt
+        prompt_embeds = req.prompt_embeds if req.prompt_embeds is not None else prompt_embeds
+        negative_prompt_embeds = req.negative_prompt_embeds if req.negative_prompt_embeds is not None else negative_prompt_embeds
+        prompt_embeds_mask = req.prompt_attention_mask if req.prompt_attention_mask is not None else prompt_embeds_mask
+        negative_prompt_embeds_mask = (req.negative_attention_mask if req.negative_attention_mask is not None
+                                       else negative_prompt_embeds_mask)
+        if height % (self.vae_scale_factor * 2) or width % (self.vae_scale_factor * 2):
+            raise ValueError(f"height and width must be divisible by {self.vae_scale_factor * 2}")
+        if prompt_embeds is None:
+            if self.text_encoder is None:
+                raise ValueError("prompt_embeds are required: the Qwen2.5-VL prompt encoder is outside the native "
+                                 "DiT engine's scope (inject `text_encoder` or pass embeddings)")
+            prompt_embeds, prompt_embeds_mask = self.text_encoder(req.prompt if req.prompt is not None else prompt)
+            neg = req.negative_prompt if req.negative_prompt is not None else negative_prompt
+            if neg is not None and true_cfg_scale > 1:
+                negative_prompt_embeds, negative_prompt_embeds_mask = self.text_encoder(neg)
+        dev = self.device
+
+        def rep(e, m):
+            e = e.to(dev, torch.bfloat16)
+            if m is None:
+                m = torch.ones(e.shape[:2], dtype=torch.long)
+            b, s, _ = e.shape
+            e = e.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, s, -1)
+            m = m.repeat(1, num_images_per_prompt).view(b * num_images_per_prompt, s)
+            return e.contiguous(), m
+
+        self._attention_kwargs = attention_kwargs or {}
+        self._interrupt = False
+        batch_size = prompt_embeds.shape[0]
+        do_true_cfg = true_cfg_scale > 1 and negative_prompt_embeds is not None
+        prompt_embeds, prompt_embeds_mask = rep(prompt_embeds, prompt_embeds_mask)
+        if do_true_cfg:
+            negative_prompt_embeds, negative_prompt_embeds_mask = rep(negative_prompt_embeds, negative_prompt_embeds_mask)
+        latents = self.prepare_latents(batch_size * num_images_per_prompt, self.transformer.in_channels // 4, height, width,
+                                       torch.bfloat16, dev, generator, latents)
+        img_shapes = [[(1, height // self.vae_scale_factor // 2, width // self.vae_scale_factor // 2)]] * (
+            batch_size * num_images_per_prompt)
+        timesteps, num_inference_steps = self.prepare_timesteps(num_inference_steps, sigmas, latents.shape[1])
+        self._num_timesteps = len(timesteps)
+        txt_seq_lens = prompt_embeds_mask.sum(dim=1).tolist()
+        negative_txt_seq_lens = negative_prompt_embeds_mask.sum(dim=1).tolist() if do_true_cfg else None
+        latents = self.diffuse(prompt_embeds, prompt_embeds_mask, negative_prompt_embeds if do_true_cfg else None,
+                               negative_prompt_embeds_mask if do_true_cfg else None, latents, img_shapes, txt_seq_lens,
+                               negative_txt_seq_lens, timesteps, do_true_cfg, None, true_cfg_scale)
+        self._current_timestep = None
+        if output_type == "latent" or self.vae is None:
+            return DiffusionOutput(output=latents)
+        lat = self._unpack_latents(latents, height, width, self.vae_scale_factor).to(self.vae.dtype)
+        z = self.vae.config.z_dim
+        mean = torch.tensor(self.vae.config.latents_mean).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
+        std = 1.0 / torch.tensor(self.vae.config.latents_std).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
+        image = self.vae.decode(lat / std + mean, return_dict=False)[0][:, :, 0]
+        return DiffusionOutput(output=image)
+
+
+def get_qwen_image_post_process_func(od_config: OmniDiffusionConfig):
+    """Looked up by name by the registry (reference registry.py:97-139, pipeline :40-60).  With no VAE in
+    scope the native pipeline returns latents; the post-process is the identity."""
+    def post_process_func(images: torch.Tensor):
+        return images
+    return post_process_func
