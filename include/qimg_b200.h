@@ -31,6 +31,12 @@ int qimg_device_check(int* sm_count);
 long long qimg_launch_count(void);
 void qimg_reset_launch_count(void);
 
+/* Per-launch CUDA-event timing of the tensor-core kernels (kind 0 = tcgen05 GEMM, 1 = FMHA): while
+ * enabled every launch is bracketed by events on its stream; collect() synchronises them and returns the
+ * summed device time, launch count and algorithmic FLOPs since the previous collect (bench.py roofline). */
+void qimg_prof_enable(int on);
+int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* flops_total);
+
 /* ---- bandwidth-bound fused ops ------------------------------------------------------ */
 /* y[r,:] = LN(x[r,:]; eps, no affine) * (1 + scale[b,:]) + shift[b,:],  b = r / rows_per_batch.
  * Replaces AdaLayerNorm.forward_cuda/forward_native, vllm_omni/diffusion/layers/adalayernorm.py:62-68,94-102
@@ -59,7 +65,8 @@ int qimg_timestep_sinusoid(const void* t, void* out, int B, qimg_stream_t stream
 
 /* Fused true-CFG combine + norm rescale + flow-match Euler step on latents [rows, 64]:
  *   pipeline_qwen_image.py:580-583 and FlowMatchEulerDiscreteScheduler.step at :585.
- * neg == NULL => no CFG.  latents updated in place: x = bf16(float(x) + bf16((sigma_next - sigma) * noise)). */
+ * neg == NULL => no CFG.  latents updated in place: x = bf16(float(x) + bf16(bf16(sigma_next - sigma) * noise))
+ * (torch promotes the 0-dim fp32 dt to the bf16 operand dtype). */
 int qimg_cfg_euler_step(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale,
                         float sigma, float sigma_next, qimg_stream_t stream);
 
@@ -141,8 +148,7 @@ size_t qimg_engine_workspace_bytes(const qimg_engine* e, int B, int S_img, int T
  *   hidden [B,S_img,64], enc [B,T,joint], timestep bf16 [n_t] (already /1000; n_t = B, or 1 when the
  *   whole batch shares one timestep as in QwenImagePipeline.diffuse, pipeline_qwen_image.py:552),
  *   RoPE tables bf16 img [S_img,64] x2, txt [T,64] x2  ->  out [B,S_img,64].
- * layer_begin/layer_end select a block range (0, num_layers for the full model); prologue/epilogue
- * run only when the range starts at 0 / ends at num_layers. */
+ * workspace: >= qimg_engine_workspace_bytes(), 1024-byte aligned, caller-owned. */
 int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, const void* timestep, int n_t,
                         const void* img_cos, const void* img_sin, const void* txt_cos, const void* txt_sin, int B,
                         int S_img, int T, void* out, void* workspace, size_t workspace_bytes, qimg_stream_t stream);

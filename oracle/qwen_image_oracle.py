@@ -277,8 +277,9 @@ def cfg_combine(pos: torch.Tensor, neg: torch.Tensor, true_cfg_scale: float) -> 
 def euler_step(noise_pred: torch.Tensor, latents: torch.Tensor, sigma: torch.Tensor, sigma_next: torch.Tensor):
     """FlowMatchEulerDiscreteScheduler.step (called at pipeline_qwen_image.py:585):
     sample upcast to fp32; dt = sigma_next - sigma is a 0-dim fp32 tensor, so under torch
-    type promotion `dt * model_output` stays in model_output.dtype; the sum is fp32 and is
-    cast back to model_output.dtype."""
+    type promotion `dt * model_output` is computed in model_output.dtype (dt itself is rounded
+    to bf16 first when the model runs in bf16); the sum is fp32 and is cast back to
+    model_output.dtype."""
     sample = latents.to(torch.float32)
     dt = sigma_next - sigma
     prev = sample + dt * noise_pred

@@ -1,0 +1,47 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of the data-parallel path (shard -> local work -> gather)."""
+import os
+
+import torch
+import torch.multiprocessing as mp
+
+from vllm_omni_b200.diffusion.distributed import parallel_state as ps
+
+
+def _worker(rank, world, port, tp, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    ps.init_distributed_environment(world_size=world, rank=rank, backend="gloo")
+    ps.initialize_model_parallel(data_parallel_size=world // tp, tensor_parallel_size=tp, backend="gloo")
+    dp, dpr = ps.get_data_parallel_world_size(), ps.get_data_parallel_rank()
+    total = 5
+    counts = [ps.shard_range(total, r, dp)[1] - ps.shard_range(total, r, dp)[0] for r in range(dp)]
+    lo, hi = ps.shard_range(total, dpr, dp)
+    local = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1).expand(-1, 3, 4).contiguous() * 10
+    out = ps.gather_to_rank0(local, counts) if ps.get_tensor_model_parallel_rank() == 0 or tp == 1 else None
+    if tp > 1:
+        t = torch.full((4,), float(rank))
+        torch.distributed.all_reduce(t, group=ps.get_tp_group())
+        q.put(("tp", rank, t.tolist()))
+    if out is not None and dpr == 0:
+        q.put(("gather", rank, out[:, 0, 0].tolist()))
+    ps.destroy_distributed_env()
+
+
+def _run(world, tp, port):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, tp, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(1 if tp == 1 else world)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    return res
+
+
+def test_dp2_gather_gloo():
+    res = _run(2, 1, 29631)
+    assert res == [("gather", 0, [0.0, 10.0, 20.0, 30.0, 40.0])]
+
+
+def test_tp2_allreduce_group_gloo():
+    res = sorted(_run(2, 2, 29632))
+    assert res[0][2] == [1.0] * 4 and res[1][2] == [1.0] * 4

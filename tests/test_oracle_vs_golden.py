@@ -1,0 +1,69 @@
+"""CPU: pins the oracle restatement against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/*.pt, generator: oracle/make_golden.py).  bf16 must be bit-exact (same torch build, same
+op order), fp32 within float rounding."""
+import os
+
+import pytest
+import torch
+
+from oracle import qwen_image_oracle as O
+from vllm_omni_b200 import synthetic
+
+CASES = ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1"]
+
+
+def _weights(c):
+    return dict(synthetic.synthetic_weights(c["L"], seed=c["seed"], dtype=torch.bfloat16, norm_jitter=0.1,
+                                            num_heads=c["H"], joint_dim=c["joint"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(golden_dir, name):
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"))
+    c = fx["case"]
+    w = _weights(c)
+    chk = sum(float(w[k].double().abs().sum()) for k in sorted(w))
+    assert abs(chk - fx["weights_checksum"]) <= 1e-9 * abs(fx["weights_checksum"]), "synthetic weight RNG drifted"
+    dims = O.DiTDims(num_layers=c["L"], num_heads=c["H"], joint_dim=c["joint"])
+    grid = (1,) + tuple(c["grid"])
+    out = O.model_forward(w, dims, fx["hidden_states"], fx["encoder_hidden_states"], fx["timestep"], grid)
+    assert out.dtype == torch.bfloat16
+    assert O.rel_fro(out, fx["ref_bf16"]) <= 1e-6, "bf16 restatement must reproduce the reference bit-for-bit"
+    out32 = O.model_forward(O.cast_weights(w, torch.float32), dims, fx["hidden_states"].float(),
+                            fx["encoder_hidden_states"].float(), fx["timestep"].float(), grid)
+    assert O.rel_fro(out32, fx["ref_fp32"]) <= 1e-5
+    # the reference's own bf16 path sits this far from fp32: sanity bound
+    assert 1e-3 < O.rel_fro(fx["ref_bf16"], fx["ref_fp32"]) < 2e-2
+
+
+def test_scheduler_tables_and_step():
+    sig = O.flow_match_sigmas(50, 4096)
+    assert sig.shape == (51,) and sig[-1] == 0.0
+    assert abs(float(sig[0]) - 1.0) < 1e-6 and abs(float(sig[-2]) - 0.02) < 1e-6  # terminal stretch
+    assert all(sig[i] > sig[i + 1] for i in range(50))
+    mu = O.calculate_shift(4096, 256, 8192, 0.5, 0.9)
+    assert abs(mu - 0.6935) < 1e-3
+    x = torch.randn(2, 16, 64).bfloat16()
+    v = torch.randn(2, 16, 64).bfloat16()
+    s0, s1 = torch.tensor(float(sig[3])), torch.tensor(float(sig[4]))
+    y = O.euler_step(v, x, s0, s1)
+    ref = (x.float() + ((s1 - s0).bfloat16().float() * v.float()).bfloat16().float()).bfloat16()
+    assert torch.equal(y, ref)
+
+
+def test_cfg_combine_norm_preserving():
+    pos, neg = torch.randn(3, 8, 64), torch.randn(3, 8, 64)
+    out = O.cfg_combine(pos, neg, 4.0)
+    assert torch.allclose(out.norm(dim=-1), pos.norm(dim=-1), rtol=1e-5)
+    assert torch.allclose(O.cfg_combine(pos, pos, 4.0), pos, rtol=1e-5, atol=1e-6)
+
+
+def test_rope_tables_shape_and_text_offset():
+    ic, isn, tc, tsn = O.rope_tables(1, 6, 4, 5)
+    assert ic.shape == (24, 64) and tc.shape == (5, 64)
+    assert torch.allclose(ic ** 2 + isn ** 2, torch.ones_like(ic), atol=1e-6)
+    # centre-scaled grid: frame index 0 -> first 8 pair angles are 0
+    assert torch.allclose(ic[:, :8], torch.ones(24, 8))
+    # text positions start at max(h//2, w//2) on every axis (reference :251-257)
+    ang = torch.atan2(tsn[0, 0], tc[0, 0])
+    assert abs(float(ang) - 3.0) < 1e-5

@@ -25,6 +25,48 @@ int device_sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------
+// per-launch CUDA-event profiling of the two tensor-core kernels (bench.py roofline numbers)
+// ------------------------------------------------------------------------------------------
+struct ProfRec {
+  cudaEvent_t a, b;
+  double flops;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof[2];            // 0 = gemm, 1 = fmha
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  int kind;
+  cudaStream_t st;
+  ProfRec rec;
+  bool on;
+  ProfScope(int kind_, double flops, cudaStream_t st_) : kind(kind_), st(st_), on(g_prof_on) {
+    if (on) {
+      rec.a = prof_event();
+      rec.b = prof_event();
+      rec.flops = flops;
+      cudaEventRecord(rec.a, st);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(rec.b, st);
+      g_prof[kind].push_back(rec);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // TMA descriptor cache
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -174,6 +216,9 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
     tB[1] = tB[0];
   }
   prm.total_tiles = tiles;
+  double flops = 0;
+  for (int i = 0; i < nprob; ++i) flops += 2.0 * pr[i].M * (double)pr[i].N * pr[i].K;
+  ProfScope prof(0, flops, st);
   if (BN == 64) return launch_gemm_inst<64, EPI_BIAS>(tA, tB, prm, st);
   switch (epi) {
     case QIMG_EPI_BIAS: return launch_gemm_inst<256, EPI_BIAS>(tA, tB, prm, st);
@@ -282,6 +327,27 @@ int qimg_abi_version(void) { return 1; }
 const char* qimg_last_error(void) { return g_last_error.c_str(); }
 long long qimg_launch_count(void) { return g_launch_count.load(); }
 void qimg_reset_launch_count(void) { g_launch_count.store(0); }
+
+void qimg_prof_enable(int on) { g_prof_on = on != 0; }
+
+int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* flops_total) {
+  if (kind < 0 || kind > 1) return fail("qimg_prof_collect: kind");
+  double ms = 0, fl = 0;
+  for (ProfRec& r : g_prof[kind]) {
+    QIMG_CUDA_CHECK(cudaEventSynchronize(r.b));
+    float t = 0;
+    QIMG_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    fl += r.flops;
+    g_event_pool.push_back(r.a);
+    g_event_pool.push_back(r.b);
+  }
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = (long long)g_prof[kind].size();
+  if (flops_total) *flops_total = fl;
+  g_prof[kind].clear();
+  return 0;
+}
 
 int qimg_device_check(int* sm_count) {
   int dev = 0, major = 0, minor = 0, n = 0;
@@ -397,6 +463,7 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   prm.B = B; prm.H = H; prm.S = S; prm.T = T;
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
   dim3 grid((S + 255) / 256, B * H);
+  ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
   fmha_joint_kernel<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, (cudaStream_t)stream>>>(*tq, *tk, *tv, prm);
   QIMG_LAUNCH_CHECK("fmha_joint_kernel");
   return 0;

@@ -195,7 +195,9 @@ __global__ void timestep_sinusoid_kernel(const bf16* __restrict__ t, bf16* __res
 
 // Fused true-CFG combine + norm rescale + flow-match Euler update, one pass over the latents.
 //   comb = neg + s*(pos-neg); noise = comb * (||pos|| / ||comb||)   pipeline_qwen_image.py:580-583
-//   x    = bf16( float(x) + bf16(dt * noise) )                      FlowMatchEulerDiscreteScheduler.step (:585)
+//   x    = bf16( float(x) + bf16(bf16(dt) * noise) )                FlowMatchEulerDiscreteScheduler.step (:585)
+//          (dt is a 0-dim fp32 tensor: under torch type promotion `dt * model_output` is computed in
+//           model_output's dtype, i.e. dt is first rounded to bf16 — verified against torch on CPU)
 // Rows have C = 64 channels (128 B): 8 lanes x 16 B per row, 4 rows per warp instruction.
 // neg == nullptr -> no CFG (noise = pos).
 __global__ void __launch_bounds__(256) cfg_euler_step_kernel(const bf16* __restrict__ pos, const bf16* __restrict__ neg,
@@ -245,9 +247,10 @@ __global__ void __launch_bounds__(256) cfg_euler_step_kernel(const bf16* __restr
   }
   if (active) {
     uint32_t o[4];
+    const float dtb = rbf(dt);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      o[k] = pack_bf16x2(bf16lo(xw[k]) + rbf(dt * noise[2 * k]), bf16hi(xw[k]) + rbf(dt * noise[2 * k + 1]));
+      o[k] = pack_bf16x2(bf16lo(xw[k]) + rbf(dtb * noise[2 * k]), bf16hi(xw[k]) + rbf(dtb * noise[2 * k + 1]));
     stg_v4(x + vec * 8, make_uint4(o[0], o[1], o[2], o[3]));
   }
 }

@@ -1,0 +1,129 @@
+"""Process-group bookkeeping for the native runner — the part of the reference's
+`vllm_omni/diffusion/distributed/parallel_state.py` (:391-713) the Qwen-Image DiT path needs.
+
+One process per GPU, `torch.distributed` (NCCL on GPUs, gloo in CPU tests).  Rank order follows the
+reference's "tp-sp-pp-cfg-dp" string (:659): TP ranks are adjacent, DP is the outermost dimension.
+  * DP (data parallel over images): independent units, NO collective on the data path; only the final
+    gather of the [B/P, S_img, 64] latents to rank 0.  Not wired in the reference (groups only, :661-668).
+  * TP group: kept for the tensor-parallel engine mode (all-reduce of row-parallel partial sums).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class _State:
+    world_size: int = 1
+    rank: int = 0
+    dp_size: int = 1
+    tp_size: int = 1
+    dp_group: "dist.ProcessGroup | None" = None
+    tp_group: "dist.ProcessGroup | None" = None
+
+
+_STATE = _State()
+
+
+def get_torch_distributed_backend() -> str:
+    """reference envs.py:113-115 -> "nccl" on CUDA; gloo when no GPU is visible (CPU tests)."""
+    return "nccl" if torch.cuda.is_available() else "gloo"
+
+
+def init_distributed_environment(world_size: int = -1, rank: int = -1, backend: str | None = None,
+                                 distributed_init_method: str = "env://"):
+    """reference parallel_state.py:391-430."""
+    backend = backend or get_torch_distributed_backend()
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        kw = {}
+        if world_size > 0:
+            kw.update(world_size=world_size, rank=rank)
+        dist.init_process_group(backend=backend, init_method=distributed_init_method, **kw)
+    _STATE.world_size, _STATE.rank = dist.get_world_size(), dist.get_rank()
+
+
+def initialize_model_parallel(data_parallel_size: int = 1, tensor_parallel_size: int = 1, backend: str | None = None,
+                              **unused_reference_kwargs):
+    """reference parallel_state.py:563-713 (only the DP and TP groups are created; PP/CFG/SP groups are dead
+    scaffolding for this model — SURVEY §2b)."""
+    ws = dist.get_world_size() if dist.is_initialized() else 1
+    if data_parallel_size * tensor_parallel_size != ws:
+        raise ValueError(f"dp({data_parallel_size}) * tp({tensor_parallel_size}) != world_size({ws})")
+    _STATE.dp_size, _STATE.tp_size = data_parallel_size, tensor_parallel_size
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if ws == 1:
+        return
+    for d in range(data_parallel_size):  # TP groups: adjacent ranks
+        ranks = list(range(d * tensor_parallel_size, (d + 1) * tensor_parallel_size))
+        g = dist.new_group(ranks, backend=backend)
+        if rank in ranks:
+            _STATE.tp_group = g
+    for t in range(tensor_parallel_size):  # DP groups: stride tp
+        ranks = list(range(t, ws, tensor_parallel_size))
+        g = dist.new_group(ranks, backend=backend)
+        if rank in ranks:
+            _STATE.dp_group = g
+
+
+def get_world_size() -> int:
+    return _STATE.world_size
+
+
+def get_data_parallel_world_size() -> int:
+    return _STATE.dp_size
+
+
+def get_data_parallel_rank() -> int:
+    return _STATE.rank // _STATE.tp_size
+
+
+def get_tensor_model_parallel_world_size() -> int:
+    return _STATE.tp_size
+
+
+def get_tensor_model_parallel_rank() -> int:
+    return _STATE.rank % _STATE.tp_size
+
+
+def get_dp_group():
+    return _STATE.dp_group
+
+
+def get_tp_group():
+    return _STATE.tp_group
+
+
+def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced split of n_items units over `world` ranks (first n%world ranks get one extra)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_to_rank0(local: torch.Tensor, counts: list[int]) -> torch.Tensor | None:
+    """Gather per-rank [n_i, ...] tensors along dim 0 on DP-rank 0 (the only exchange of the DP path)."""
+    if _STATE.dp_size == 1:
+        return local
+    group = _STATE.dp_group
+    dp_rank = get_data_parallel_rank()
+    mx = max(counts)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(_STATE.dp_size)] if dp_rank == 0 else None
+    dst = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if dp_rank != 0:
+        return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def destroy_distributed_env():
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    global _STATE
+    _STATE = _State()

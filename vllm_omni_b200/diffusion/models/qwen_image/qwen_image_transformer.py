@@ -268,10 +268,11 @@ class QwenImageTransformer2DModel(nn.Module):
     # ------------------------------------------------------------------ weights
     def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
         """Same contract as the reference (:804-839): q/k/v checkpoint shards are stacked into
-        to_qkv / add_kv_proj in (q, k, v) order; everything else is copied by name."""
+        to_qkv / add_kv_proj in (q, k, v) order; everything else is copied by name (already-stacked
+        `to_qkv` / `add_kv_proj` names are accepted too)."""
         stacked = [
-            (".to_qkv", ".to_q", 0), (".to_qkv", ".to_k", 1), (".to_qkv", ".to_v", 2),
-            (".add_kv_proj", ".add_q_proj", 0), (".add_kv_proj", ".add_k_proj", 1), (".add_kv_proj", ".add_v_proj", 2),
+            (".to_qkv.", ".to_q.", 0), (".to_qkv.", ".to_k.", 1), (".to_qkv.", ".to_v.", 2),
+            (".add_kv_proj.", ".add_q_proj.", 0), (".add_kv_proj.", ".add_k_proj.", 1), (".add_kv_proj.", ".add_v_proj.", 2),
         ]
         params = dict(self.named_parameters())
         loaded: set[str] = set()

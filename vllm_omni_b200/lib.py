@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "qimg_ln_modulate", "qimg_gate_residual", "qimg_rms_norm", "qimg_linear_small_m", "qimg_timestep_sinusoid",
     "qimg_cfg_euler_step", "qimg_gemm", "qimg_fmha_joint", "qimg_engine_create", "qimg_engine_destroy",
     "qimg_engine_workspace_bytes", "qimg_engine_forward", "qimg_engine_ws_offset_img", "qimg_engine_ws_offset_txt",
-    "qimg_umma_probe",
+    "qimg_umma_probe", "qimg_prof_enable", "qimg_prof_collect",
 ]
 
 
@@ -100,6 +100,9 @@ def load():
     lib.qimg_engine_ws_offset_txt.restype = sz
     lib.qimg_engine_forward.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp, sz, vp]
     lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
+    lib.qimg_prof_enable.argtypes = [i]
+    lib.qimg_prof_enable.restype = None
+    lib.qimg_prof_collect.argtypes = [i, C.POINTER(C.c_double), C.POINTER(ll), C.POINTER(C.c_double)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("qimg_abi_version",):
@@ -143,6 +146,17 @@ def launch_count() -> int:
 
 def reset_launch_count():
     load().qimg_reset_launch_count()
+
+
+def prof_enable(on: bool):
+    load().qimg_prof_enable(int(on))
+
+
+def prof_collect(kind: int) -> dict:
+    """kind 0 = tcgen05 GEMM, 1 = FMHA -> {ms, launches, flops} since the previous collect."""
+    ms, n, fl = C.c_double(0), C.c_longlong(0), C.c_double(0)
+    check(load().qimg_prof_collect(kind, C.byref(ms), C.byref(n), C.byref(fl)), "qimg_prof_collect")
+    return dict(ms=ms.value, launches=n.value, flops=fl.value)
 
 
 # ----------------------------------------------------------------------------------------
