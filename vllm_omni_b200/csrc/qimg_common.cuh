@@ -26,6 +26,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// packed bf16x2 arithmetic: one HMUL2/HADD2.BF16 rounds each lane to bf16 exactly like the reference's
+// per-op bf16 tensors do (the fp32 product of two bf16 values is exact, so rounding once is identical)
+__device__ __forceinline__ __nv_bfloat162 u2bf2(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+__device__ __forceinline__ uint32_t bf22u(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) { return bf22u(__hmul2(u2bf2(a), u2bf2(b))); }
+__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) { return bf22u(__hadd2(u2bf2(a), u2bf2(b))); }
+__device__ __forceinline__ uint32_t bsub2(uint32_t a, uint32_t b) { return bf22u(__hsub2(u2bf2(a), u2bf2(b))); }
+__device__ __forceinline__ uint32_t dup_lo(uint32_t v) { return __byte_perm(v, v, 0x1010); }  // (lo, lo)
+__device__ __forceinline__ uint32_t dup_hi(uint32_t v) { return __byte_perm(v, v, 0x3232); }  // (hi, hi)
+__device__ __forceinline__ uint32_t swap_halves(uint32_t v) { return __byte_perm(v, v, 0x1032); }
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * x * fmaf(k1, x * x, 1.0f);
+  return 0.5f * x * (1.0f + tanh_approx(u));
+}
+
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   // F.gelu(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

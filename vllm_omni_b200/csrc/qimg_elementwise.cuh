@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+  const float nmr = -mean * rstd;
   const int b = row / rows_per_batch;
   const bf16* sh = shift + (size_t)b * mod_stride;
   const bf16* sc = scale + (size_t)b * mod_stride;
@@ -62,10 +63,9 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
       uint32_t s1[4] = {shv.x, shv.y, shv.z, shv.w}, s2[4] = {scv.x, scv.y, scv.z, scv.w}, o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float n0 = rbf((bf16lo(w[k]) - mean) * rstd), n1 = rbf((bf16hi(w[k]) - mean) * rstd);
-        float g0 = rbf(1.0f + bf16lo(s2[k])), g1 = rbf(1.0f + bf16hi(s2[k]));
-        float o0 = rbf(rbf(n0 * g0) + bf16lo(s1[k])), o1 = rbf(rbf(n1 * g1) + bf16hi(s1[k]));
-        o[k] = pack_bf16x2(o0, o1);
+        // bf16(LN(x)) -> * bf16(1 + scale) -> + shift, each op rounded to bf16 (packed HMUL2/HADD2.BF16)
+        const uint32_t n = pack_bf16x2(fmaf(bf16lo(w[k]), rstd, nmr), fmaf(bf16hi(w[k]), rstd, nmr));
+        o[k] = badd2(bmul2(n, badd2(0x3F803F80u, s2[k])), s1[k]);
       }
       stg_v4(yr + e, make_uint4(o[0], o[1], o[2], o[3]));
     }

@@ -179,20 +179,25 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       const int kv_valid = prm.S - j * 128;  // < 128 only on a ragged last tile
-      // ---- pass 1: row max ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tS + cc * 32, r);
-        tmem_ld_wait();
+      // ---- one TMEM round trip: the whole 128-wide score row lives in registers ----
+      uint32_t r[128];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]);
-          if (kv_valid < 128 && cc * 32 + i >= kv_valid) s = -INFINITY;
-          mx = fmaxf(mx, s);
-        }
+      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(tS + cc * 32, r + cc * 32);
+      tmem_ld_wait();
+      if (kv_valid < 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_valid) r[i] = 0xff800000u;  // -inf
       }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       if (j == 0) {
         m_used = mx;
       } else {
@@ -205,38 +210,36 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           l *= f;
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tO + cc * 32, r);
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tO + cc * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-            tmem_st_32x32b_x32(tO + cc * 32, r);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x32b_x32(tO + cc * 32, o);
           }
           tmem_st_wait();
           m_used = m_new;
         }
       }
-      // ---- pass 2: P = exp2(s*c - m*c), row sum, bf16 P -> TMEM (aliases S columns [0,64)) ----
+      // ---- P = exp2(s*c - m*c) (masked columns give exp2(-inf) = 0), row sum, bf16 P -> TMEM ----
       const float mc = m_used * c;
-#pragma unroll 1
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tS + cc * 32, r);
-        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2_approx(__uint_as_float(r[2 * i]) * c - mc);
-          float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) * c - mc);
-          if (kv_valid < 128) {
-            if (cc * 32 + 2 * i >= kv_valid) p0 = 0.f;
-            if (cc * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
-          }
-          l += p0 + p1;
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[cc * 32 + 2 * i]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 1]), c, -mc));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 2]), c, -mc));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), c, -mc));
+          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
           pk[i] = pack_bf16x2(p0, p1);
+          pk[i + 1] = pack_bf16x2(p2, p3);
         }
         tmem_st_32x32b_x16(tS + cc * 16, pk);
       }
+      l += (l0 + l1) + (l2 + l3);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

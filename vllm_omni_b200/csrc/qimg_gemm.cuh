@@ -11,11 +11,13 @@
 // The image and text streams (different weights, M_txt << M_img) are GROUPED in one
 // launch so the small text GEMM fills the tail instead of starving 140 SMs.
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage mbarrier ring)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
-//   warps 2-5: epilogue: tcgen05.ld accumulator rows -> fp32 math -> bf16 -> swizzled smem
-//              staging -> 128-byte coalesced global stores (residual / gate fused there)
+//   warps 2-9: epilogue, two warps per scheduler (warps 2-5 take the first BN/2 columns, 6-9 the
+//              second): tcgen05.ld accumulator rows -> math (packed bf16x2 where the reference rounds
+//              per op) -> swizzled smem staging -> 128-byte coalesced global stores (residual / gate
+//              fused there)
 //   two TMEM accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the
 //   main loop of tile i+1.
 #pragma once
@@ -57,9 +59,9 @@ struct GemmParams {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_GROUP_M = 16;
-constexpr int GEMM_EPI_STAGE_BYTES = 4 * 32 * 128;  // 4 warps x 32 rows x 128 B
+constexpr int GEMM_EPI_STAGE_BYTES = 8 * 32 * 128;  // 8 warps x 32 rows x 128 B
 
 template <int BN>
 constexpr int gemm_smem_bytes() {
@@ -123,7 +125,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -198,8 +200,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;       // TMEM lane quarter this warp may access
-    const int ew = warp - 2;      // staging slot
+    constexpr int CHUNKS = BN / 64;                   // 64-column chunks per tile
+    constexpr int CH_PER_HALF = (CHUNKS + 1) / 2;     // BN=256: each warpgroup owns one 128-column head
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int ew = warp - 2;                          // staging slot 0..7
+    const int chunk_lo = (ew >> 2) * CH_PER_HALF;
+    const int chunk_hi = (chunk_lo + CH_PER_HALF < CHUNKS) ? chunk_lo + CH_PER_HALF : CHUNKS;
     uint8_t* stg = smem_epi + ew * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -211,94 +217,107 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const int m_own = tc.m_blk * GEMM_BM + q * 32 + lane;  // this thread's accumulator row
 
-      // per-row constants for EPI_QKV
       float rstd = 0.f;
       const bf16* cos_row = nullptr;
       const bf16* sin_row = nullptr;
       if (EPI == EPI_QKV) {
-        int i_own = (m_own < P.M) ? (m_own % P.rows_per_batch) : 0;
+        const int i_own = (m_own < P.M) ? (m_own % P.rows_per_batch) : 0;
         cos_row = P.cos + (size_t)i_own * 64;
         sin_row = P.sin + (size_t)i_own * 64;
       }
 
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 64; ++chunk) {
+      for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
         const int n0 = tc.n_blk * BN + chunk * 64;
-        uint32_t r[64];
         int which = 0, head = 0, half = 0;
         if (EPI == EPI_QKV) {
           const int D = P.N / 3;
-          which = n0 / D;                 // 0 = q, 1 = k, 2 = v
-          head = (n0 - which * D) >> 7;   // head index
-          half = (n0 >> 6) & 1;           // which 64-column half of the head
+          which = n0 / D;                // 0 = q, 1 = k, 2 = v
+          head = (n0 - which * D) >> 7;  // head index
+          half = (n0 >> 6) & 1;          // which 64-column half of the head
           if (which < 2 && half == 0 && n0 < P.N) {
             // pass 1 over the whole head (128 columns): sum of squares of bf16(acc + bias)
-            float ss = 0.f;
+            float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll 1
             for (int c4 = 0; c4 < 4; ++c4) {
               uint32_t t[32];
               tmem_ld_32x32b_x32(t_row + chunk * 64 + c4 * 32, t);
-              tmem_ld_wait();
               const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0 + c4 * 32);
+              uint4 bv[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) bv[j] = __ldg(bp + j);
+              tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                uint4 bv = __ldg(bp + j);
-                uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                const uint32_t bw[4] = {bv[j].x, bv[j].y, bv[j].z, bv[j].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  float v0 = rbf(__uint_as_float(t[j * 8 + e * 2]) + bf16lo(bw[e]));
-                  float v1 = rbf(__uint_as_float(t[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
-                  ss += v0 * v0 + v1 * v1;
+                  const uint32_t v = pack_bf16x2(__uint_as_float(t[j * 8 + e * 2]) + bf16lo(bw[e]),
+                                                 __uint_as_float(t[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
+                  ss0 = fmaf(bf16lo(v), bf16lo(v), ss0);
+                  ss1 = fmaf(bf16hi(v), bf16hi(v), ss1);
                 }
               }
             }
-            rstd = rsqrtf(ss * (1.0f / 128.0f) + P.eps);
+            rstd = rsqrtf((ss0 + ss1) * (1.0f / 128.0f) + P.eps);
           }
         }
+        uint32_t r[64];
         tmem_ld_32x32b_x32(t_row + chunk * 64, r);
         tmem_ld_32x32b_x32(t_row + chunk * 64 + 32, r + 32);
+        // operand loads overlap the TMEM read latency
+        uint4 bv[8];
+        uint4 nv[8];
+        uint4 cv[4], sv[4];
+        if (n0 < P.N) {
+          const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+          if (EPI == EPI_QKV && which < 2) {
+            const uint4* np = reinterpret_cast<const uint4*>((which == 0 ? P.nq_w : P.nk_w) + half * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nv[j] = __ldg(np + j);
+            const uint4* cp = reinterpret_cast<const uint4*>(cos_row + half * 32);
+            const uint4* sp = reinterpret_cast<const uint4*>(sin_row + half * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              cv[j] = __ldg(cp + j);
+              sv[j] = __ldg(sp + j);
+            }
+          }
+        }
         tmem_ld_wait();
 
         // ---- math on this thread's 64 columns -> 32 packed bf16x2 words ----
         uint32_t pk[32];
         if (n0 < P.N) {
-          const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            uint4 bv = __ldg(bp + j);
-            uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-            uint32_t nw[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0}, sw[4] = {0, 0, 0, 0};
-            if (EPI == EPI_QKV && which < 2) {
-              const bf16* nwp = (which == 0 ? P.nq_w : P.nk_w) + half * 64 + j * 8;
-              uint4 nv = __ldg(reinterpret_cast<const uint4*>(nwp));
-              nw[0] = nv.x; nw[1] = nv.y; nw[2] = nv.z; nw[3] = nv.w;
-              if ((j & 1) == 0) {
-                // 8 columns = 4 pairs -> 4 cos / 4 sin values (8 B each); load 16 B every other j
-              }
-              const uint2 cv = __ldg(reinterpret_cast<const uint2*>(cos_row + half * 32 + j * 4));
-              const uint2 sv = __ldg(reinterpret_cast<const uint2*>(sin_row + half * 32 + j * 4));
-              cw[0] = cv.x; cw[1] = cv.y; sw[0] = sv.x; sw[1] = sv.y;
-            }
+            const uint32_t bw[4] = {bv[j].x, bv[j].y, bv[j].z, bv[j].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float v0 = rbf(__uint_as_float(r[j * 8 + e * 2]) + bf16lo(bw[e]));
-              float v1 = rbf(__uint_as_float(r[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
+              // v = bf16(acc + bias): the Linear's bf16 output
+              uint32_t v = pack_bf16x2(__uint_as_float(r[j * 8 + e * 2]) + bf16lo(bw[e]),
+                                       __uint_as_float(r[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
               if (EPI == EPI_BIAS_GELU) {
-                v0 = gelu_tanh_f(v0);
-                v1 = gelu_tanh_f(v1);
+                v = pack_bf16x2(gelu_tanh_fast(bf16lo(v)), gelu_tanh_fast(bf16hi(v)));
               }
               if (EPI == EPI_QKV && which < 2) {
+                const uint32_t nw4[4] = {nv[j].x, nv[j].y, nv[j].z, nv[j].w};
                 // RMSNorm: fp32 normalise -> bf16 -> * weight -> bf16   (vLLM rms_norm)
-                float x1 = rbf(rbf(v0 * rstd) * bf16lo(nw[e]));
-                float x2 = rbf(rbf(v1 * rstd) * bf16hi(nw[e]));
-                // interleaved RoPE with bf16 cos/sin: x*cos + rotate_half(x)*sin, every op rounded
-                uint32_t cpair = cw[e >> 1], spair = sw[e >> 1];
-                float c = (e & 1) ? bf16hi(cpair) : bf16lo(cpair);
-                float s = (e & 1) ? bf16hi(spair) : bf16lo(spair);
-                v0 = rbf(rbf(x1 * c) + rbf(-x2 * s));
-                v1 = rbf(rbf(x2 * c) + rbf(x1 * s));
+                uint32_t x = bmul2(pack_bf16x2(bf16lo(v) * rstd, bf16hi(v) * rstd), nw4[e]);
+                // interleaved RoPE, every op rounded to bf16: x*cos + rotate_half(x)*sin with
+                // rotate_half(x) = (-x[2i+1], x[2i]); pair index within this 64-col chunk = j*4 + e
+                const int pi = j * 4 + e;  // 0..31 -> 16-byte vector pi/8, word (pi%8)/2, half pi&1
+                const uint4 c4 = cv[pi >> 3], s4 = sv[pi >> 3];
+                const uint32_t cw4[4] = {c4.x, c4.y, c4.z, c4.w}, sw4[4] = {s4.x, s4.y, s4.z, s4.w};
+                const uint32_t cw = cw4[(pi & 7) >> 1], sw = sw4[(pi & 7) >> 1];
+                const uint32_t cc = (pi & 1) ? dup_hi(cw) : dup_lo(cw);
+                const uint32_t ssn = (pi & 1) ? dup_hi(sw) : dup_lo(sw);
+                const uint32_t rot = swap_halves(x) ^ 0x00008000u;  // (-x_hi, x_lo)
+                v = badd2(bmul2(x, cc), bmul2(rot, ssn));
               }
-              pk[j * 4 + e] = pack_bf16x2(v0, v1);
+              pk[j * 4 + e] = v;
             }
           }
         } else {
@@ -315,34 +334,52 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         __syncwarp();
         const int c16 = lane & 7;
         const int gn = n0 + c16 * 8;
-#pragma unroll 2
+        const int gm0 = tc.m_blk * GEMM_BM + q * 32 + (lane >> 3);
+        uint4 yv[8];
+#pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + (lane >> 3);
-          const int gm = tc.m_blk * GEMM_BM + q * 32 + rr;
-          uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
-          if (gm < P.M && gn < P.N) {
-            if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
-              stg_v4(P.out + (size_t)gm * P.ldo + gn, v);
-            } else if (EPI == EPI_BIAS_GATE_RES) {
-              const int b = gm / P.rows_per_batch;
-              bf16* xp = P.out + (size_t)gm * P.ldo + gn;
-              uint4 xv = ldg_v4(xp);
-              uint4 gv = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)b * P.gate_stride + gn));
-              uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, yw[4] = {v.x, v.y, v.z, v.w};
-              uint32_t ow[4];
+          yv[it] = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+        }
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float o0 = rbf(bf16lo(xw[e]) + rbf(bf16lo(gw[e]) * bf16lo(yw[e])));
-                float o1 = rbf(bf16hi(xw[e]) + rbf(bf16hi(gw[e]) * bf16hi(yw[e])));
-                ow[e] = pack_bf16x2(o0, o1);
-              }
-              stg_v4(xp, make_uint4(ow[0], ow[1], ow[2], ow[3]));
-            } else {  // EPI_QKV: scatter into the joint [B,H,S,128] head-major layout
+          for (int it = 0; it < 8; ++it) {
+            const int gm = gm0 + it * 4;
+            if (gm < P.M && gn < P.N) stg_v4(P.out + (size_t)gm * P.ldo + gn, yv[it]);
+          }
+        } else if (EPI == EPI_BIAS_GATE_RES) {
+          uint4 xv[8], gv[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int gm = gm0 + it * 4;
+            if (gm < P.M && gn < P.N) {
+              xv[it] = ldg_v4(P.out + (size_t)gm * P.ldo + gn);
+              gv[it] = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)(gm / P.rows_per_batch) * P.gate_stride + gn));
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int gm = gm0 + it * 4;
+            if (gm < P.M && gn < P.N) {
+              // x = bf16(x + bf16(gate * y))
+              uint4 o;
+              o.x = badd2(xv[it].x, bmul2(gv[it].x, yv[it].x));
+              o.y = badd2(xv[it].y, bmul2(gv[it].y, yv[it].y));
+              o.z = badd2(xv[it].z, bmul2(gv[it].z, yv[it].z));
+              o.w = badd2(xv[it].w, bmul2(gv[it].w, yv[it].w));
+              stg_v4(P.out + (size_t)gm * P.ldo + gn, o);
+            }
+          }
+        } else {  // EPI_QKV: scatter into the joint [B,H,S,128] head-major layout
+          bf16* base = (which == 0) ? P.q : (which == 1 ? P.k : P.v);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int gm = gm0 + it * 4;
+            if (gm < P.M && gn < P.N) {
               const int b = gm / P.rows_per_batch;
               const int i = gm - b * P.rows_per_batch;
-              bf16* base = (which == 0) ? P.q : (which == 1 ? P.k : P.v);
-              size_t off = (((size_t)b * P.H + head) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
-              stg_v4(base + off, v);
+              const size_t off = (((size_t)b * P.H + head) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
+              stg_v4(base + off, yv[it]);
             }
           }
         }
