@@ -51,17 +51,22 @@ def gemm_case(name, N, K, epi):
     return keep
 
 print("device", torch.cuda.get_device_name(0), "B", B)
+ONLY = set(filter(None, os.environ.get("KB_ONLY", "").split(",")))
+want = lambda k: (not ONLY) or k in ONLY
 # cuBLAS reference point for the same shapes
-for (N, K) in ((3 * D, D), (D, D), (FF, D), (D, FF)):
-    a, w = rn(Mi, K), rn(N, K)
-    timeit(f"cuBLAS (torch) {Mi}x{N}x{K}", lambda: torch.nn.functional.linear(a, w), flops=2.0 * Mi * N * K)
-gemm_case("gemm QKV+norm+rope  N=9216 K=3072", 3 * D, D, q.EPI_QKV)
-gemm_case("gemm out-proj+gate-res N=3072 K=3072", D, D, q.EPI_BIAS_GATE_RES)
-gemm_case("gemm MLP up + GELU  N=12288 K=3072", FF, D, q.EPI_BIAS_GELU)
-gemm_case("gemm MLP down+gate-res N=3072 K=12288", D, FF, q.EPI_BIAS_GATE_RES)
+if want("cublas"):
+    for (N, K) in ((3 * D, D), (D, D), (FF, D), (D, FF)):
+        a, w = rn(Mi, K), rn(N, K)
+        timeit(f"cuBLAS (torch) {Mi}x{N}x{K}", lambda: torch.nn.functional.linear(a, w), flops=2.0 * Mi * N * K)
+if want("qkv"): gemm_case("gemm QKV+norm+rope  N=9216 K=3072", 3 * D, D, q.EPI_QKV)
+if want("outproj"): gemm_case("gemm out-proj+gate-res N=3072 K=3072", D, D, q.EPI_BIAS_GATE_RES)
+if want("mlpup"): gemm_case("gemm MLP up + GELU  N=12288 K=3072", FF, D, q.EPI_BIAS_GELU)
+if want("mlpdown"): gemm_case("gemm MLP down+gate-res N=3072 K=12288", D, FF, q.EPI_BIAS_GATE_RES)
+if not (want("fmha") or want("ew")): sys.exit(0)
 qq, kk, vv = rn(B, H, S, 128), rn(B, H, S, 128), rn(B, H, S, 128)
 ot, oi = torch.empty(Mt, D, dtype=bf, device=dev), torch.empty(Mi, D, dtype=bf, device=dev)
 timeit("fmha joint S=4224", lambda: q.fmha_joint(qq, kk, vv, T, 128 ** -0.5, ot, oi), flops=4.0 * B * H * S * S * 128)
+if not want("ew"): sys.exit(0)
 try:
     qs, ks, vs = (t.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3) for t in (qq, kk, vv))
     timeit("torch SDPA (library) same shape", lambda: torch.nn.functional.scaled_dot_product_attention(qq, kk, vv), flops=4.0 * B * H * S * S * 128)

@@ -27,12 +27,14 @@ __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v <
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 // packed bf16x2 arithmetic: one HMUL2/HADD2.BF16 rounds each lane to bf16 exactly like the reference's
-// per-op bf16 tensors do (the fp32 product of two bf16 values is exact, so rounding once is identical)
+// per-op bf16 tensors do (the fp32 product of two bf16 values is exact, so rounding once is identical).
+// The *_rn intrinsics are used because plain __hmul2/__hadd2 may be contracted into one HFMA2 (single
+// rounding), which is NOT what a chain of separate bf16 torch ops computes.
 __device__ __forceinline__ __nv_bfloat162 u2bf2(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
 __device__ __forceinline__ uint32_t bf22u(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
-__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) { return bf22u(__hmul2(u2bf2(a), u2bf2(b))); }
-__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) { return bf22u(__hadd2(u2bf2(a), u2bf2(b))); }
-__device__ __forceinline__ uint32_t bsub2(uint32_t a, uint32_t b) { return bf22u(__hsub2(u2bf2(a), u2bf2(b))); }
+__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) { return bf22u(__hmul2_rn(u2bf2(a), u2bf2(b))); }
+__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) { return bf22u(__hadd2_rn(u2bf2(a), u2bf2(b))); }
+__device__ __forceinline__ uint32_t bsub2(uint32_t a, uint32_t b) { return bf22u(__hsub2_rn(u2bf2(a), u2bf2(b))); }
 __device__ __forceinline__ uint32_t dup_lo(uint32_t v) { return __byte_perm(v, v, 0x1010); }  // (lo, lo)
 __device__ __forceinline__ uint32_t dup_hi(uint32_t v) { return __byte_perm(v, v, 0x3232); }  // (hi, hi)
 __device__ __forceinline__ uint32_t swap_halves(uint32_t v) { return __byte_perm(v, v, 0x1032); }
