@@ -75,6 +75,16 @@ __device__ __forceinline__ uint4 ldg_v4(const void* p) { return *reinterpret_cas
 __device__ __forceinline__ void stg_v4(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// explicit shared-space 128-bit accesses (pointer arithmetic through uintptr_t loses the address space and
+// the compiler falls back to generic LD/ST)
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
 
 // ---------------------------------------------------------------------------------------
 // mbarrier

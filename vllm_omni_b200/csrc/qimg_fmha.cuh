@@ -41,6 +41,59 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// ---- packed fp32x2 helpers (Blackwell FFMA2 / FADD2 / FMNMX3): halve the issue slots of the softmax ----
+__device__ __forceinline__ uint64_t pack_f32x2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3_f32(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t splat_f32x2(float v) { return pack_f32x2(__float_as_uint(v), __float_as_uint(v)); }
+
+// 2^x for a pair on the FMA pipe (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3
+// minimax polynomial for 2^f (max rel. error 7.5e-5, far below the bf16 rounding of P), exponent add.
+// Softmax exponentials are XU (MUFU.EX2, 16/clk/SM) bound at head_dim 128; FMHA_POLY_MASK routes a
+// fraction of the pairs here so XU and FMA pipes share the load (FlashAttention-4's trick).
+__device__ __forceinline__ uint64_t exp2_poly_f32x2(uint64_t x) {
+  uint32_t xl, xh;
+  unpack_f32x2(x, xl, xh);
+  xl = __float_as_uint(fmaxf(__uint_as_float(xl), -125.0f));
+  xh = __float_as_uint(fmaxf(__uint_as_float(xh), -125.0f));
+  x = pack_f32x2(xl, xh);
+  const uint64_t magic = splat_f32x2(12582912.0f);  // 1.5 * 2^23: low mantissa bits of t hold round(x)
+  const uint64_t t = add_f32x2(x, magic);
+  const uint64_t n = add_f32x2(t, splat_f32x2(-12582912.0f));
+  const uint64_t f = fma_f32x2(n, splat_f32x2(-1.0f), x);
+  uint64_t p = fma_f32x2(f, splat_f32x2(0.05517164617776871f), splat_f32x2(0.2426111251115799f));
+  p = fma_f32x2(p, f, splat_f32x2(0.6932609677314758f));
+  p = fma_f32x2(p, f, splat_f32x2(0.9999280571937561f));
+  uint32_t pl, ph, tl, th;
+  unpack_f32x2(p, pl, ph);
+  unpack_f32x2(t, tl, th);
+  return pack_f32x2(pl + (tl << 23), ph + (th << 23));
+}
+
+#ifndef FMHA_POLY_MASK
+#define FMHA_POLY_MASK 0x52u  // of every 8 pairs, pairs {1,4,6} use the polynomial (37.5 %)
+#endif
+
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
@@ -191,11 +244,11 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(r[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+      for (int i = 0; i < 128; i += 8) {
+        mx0 = max3_f32(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        mx1 = max3_f32(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        mx2 = max3_f32(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+        mx3 = max3_f32(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       if (j == 0) {
@@ -222,24 +275,36 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
       // ---- P = exp2(s*c - m*c) (masked columns give exp2(-inf) = 0), row sum, bf16 P -> TMEM ----
-      const float mc = m_used * c;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_used * c);
+      uint64_t la = 0, lb = 0;  // two packed partial row sums (bit pattern 0 = +0.0f pairs)
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(r[cc * 32 + 2 * i]), c, -mc));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 1]), c, -mc));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 2]), c, -mc));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(r[cc * 32 + 2 * i + 3]), c, -mc));
-          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-          pk[i] = pack_bf16x2(p0, p1);
-          pk[i + 1] = pack_bf16x2(p2, p3);
+        for (int i = 0; i < 16; ++i) {
+          const int k = cc * 16 + i;  // pair index 0..63
+          const uint64_t x = fma_f32x2(pack_f32x2(r[2 * k], r[2 * k + 1]), c2, nmc2);
+          uint64_t p;
+          if ((FMHA_POLY_MASK >> (k & 7)) & 1u) {
+            p = exp2_poly_f32x2(x);
+          } else {
+            uint32_t xl, xh;
+            unpack_f32x2(x, xl, xh);
+            p = pack_f32x2(__float_as_uint(ex2_approx(__uint_as_float(xl))), __float_as_uint(ex2_approx(__uint_as_float(xh))));
+          }
+          if (i & 1) lb = add_f32x2(lb, p); else la = add_f32x2(la, p);
+          uint32_t pl, ph;
+          unpack_f32x2(p, pl, ph);
+          pk[i] = pack_bf16x2(__uint_as_float(pl), __uint_as_float(ph));
         }
         tmem_st_32x32b_x16(tS + cc * 16, pk);
       }
-      l += (l0 + l1) + (l2 + l3);
+      {
+        uint32_t a0, a1, b0, b1;
+        unpack_f32x2(la, a0, a1);
+        unpack_f32x2(lb, b0, b1);
+        l += (__uint_as_float(a0) + __uint_as_float(a1)) + (__uint_as_float(b0) + __uint_as_float(b1));
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

@@ -206,7 +206,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int ew = warp - 2;                          // staging slot 0..7
     const int chunk_lo = (ew >> 2) * CH_PER_HALF;
     const int chunk_hi = (chunk_lo + CH_PER_HALF < CHUNKS) ? chunk_lo + CH_PER_HALF : CHUNKS;
-    uint8_t* stg = smem_epi + ew * 4096;
+    const uint32_t stg = smem_u32(smem_epi + ew * 4096);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
@@ -265,25 +265,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         uint32_t r[64];
         tmem_ld_32x32b_x32(t_row + chunk * 64, r);
         tmem_ld_32x32b_x32(t_row + chunk * 64 + 32, r + 32);
-        // operand loads overlap the TMEM read latency
-        uint4 bv[8];
-        uint4 nv[8];
+        // this row's cos/sin (per-thread addresses) are fetched while the TMEM read is in flight;
+        // bias / norm weights are warp-uniform broadcast loads issued just in time (keeps registers < 168)
         uint4 cv[4], sv[4];
-        if (n0 < P.N) {
-          const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0);
+        if (EPI == EPI_QKV && which < 2 && n0 < P.N) {
+          const uint4* cp = reinterpret_cast<const uint4*>(cos_row + half * 32);
+          const uint4* sp = reinterpret_cast<const uint4*>(sin_row + half * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
-          if (EPI == EPI_QKV && which < 2) {
-            const uint4* np = reinterpret_cast<const uint4*>((which == 0 ? P.nq_w : P.nk_w) + half * 64);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) nv[j] = __ldg(np + j);
-            const uint4* cp = reinterpret_cast<const uint4*>(cos_row + half * 32);
-            const uint4* sp = reinterpret_cast<const uint4*>(sin_row + half * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              cv[j] = __ldg(cp + j);
-              sv[j] = __ldg(sp + j);
-            }
+          for (int j = 0; j < 4; ++j) {
+            cv[j] = __ldg(cp + j);
+            sv[j] = __ldg(sp + j);
           }
         }
         tmem_ld_wait();
@@ -291,9 +282,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ---- math on this thread's 64 columns -> 32 packed bf16x2 words ----
         uint32_t pk[32];
         if (n0 < P.N) {
+          const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0);
+          const uint4* np = reinterpret_cast<const uint4*>((which == 0 ? P.nq_w : P.nk_w) + half * 64);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t bw[4] = {bv[j].x, bv[j].y, bv[j].z, bv[j].w};
+            const uint4 bvj = __ldg(bp + j);
+            const uint32_t bw[4] = {bvj.x, bvj.y, bvj.z, bvj.w};
+            uint4 nvj = make_uint4(0, 0, 0, 0);
+            if (EPI == EPI_QKV && which < 2) nvj = __ldg(np + j);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               // v = bf16(acc + bias): the Linear's bf16 output
@@ -303,7 +299,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 v = pack_bf16x2(gelu_tanh_fast(bf16lo(v)), gelu_tanh_fast(bf16hi(v)));
               }
               if (EPI == EPI_QKV && which < 2) {
-                const uint32_t nw4[4] = {nv[j].x, nv[j].y, nv[j].z, nv[j].w};
+                const uint32_t nw4[4] = {nvj.x, nvj.y, nvj.z, nvj.w};
                 // RMSNorm: fp32 normalise -> bf16 -> * weight -> bf16   (vLLM rms_norm)
                 uint32_t x = bmul2(pack_bf16x2(bf16lo(v) * rstd, bf16hi(v) * rstd), nw4[e]);
                 // interleaved RoPE, every op rounded to bf16: x*cos + rotate_half(x)*sin with
@@ -328,8 +324,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ---- stage to smem (16 B chunk index XOR row&7 -> conflict-free), then coalesced stores ----
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          uint4 v = make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+          sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]));
         }
         __syncwarp();
         const int c16 = lane & 7;
@@ -339,7 +334,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + (lane >> 3);
-          yv[it] = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+          yv[it] = lds_v4(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
         }
         if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
 #pragma unroll
@@ -348,26 +343,30 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (gm < P.M && gn < P.N) stg_v4(P.out + (size_t)gm * P.ldo + gn, yv[it]);
           }
         } else if (EPI == EPI_BIAS_GATE_RES) {
-          uint4 xv[8], gv[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int gm = gm0 + it * 4;
-            if (gm < P.M && gn < P.N) {
-              xv[it] = ldg_v4(P.out + (size_t)gm * P.ldo + gn);
-              gv[it] = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)(gm / P.rows_per_batch) * P.gate_stride + gn));
+          for (int hh = 0; hh < 2; ++hh) {  // two batches of 4 rows: loads first, then math + stores
+            uint4 xv[4], gv[4];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int gm = gm0 + (hh * 4 + i4) * 4;
+              if (gm < P.M && gn < P.N) {
+                xv[i4] = ldg_v4(P.out + (size_t)gm * P.ldo + gn);
+                gv[i4] = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)(gm / P.rows_per_batch) * P.gate_stride + gn));
+              }
             }
-          }
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int gm = gm0 + it * 4;
-            if (gm < P.M && gn < P.N) {
-              // x = bf16(x + bf16(gate * y))
-              uint4 o;
-              o.x = badd2(xv[it].x, bmul2(gv[it].x, yv[it].x));
-              o.y = badd2(xv[it].y, bmul2(gv[it].y, yv[it].y));
-              o.z = badd2(xv[it].z, bmul2(gv[it].z, yv[it].z));
-              o.w = badd2(xv[it].w, bmul2(gv[it].w, yv[it].w));
-              stg_v4(P.out + (size_t)gm * P.ldo + gn, o);
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int it = hh * 4 + i4;
+              const int gm = gm0 + it * 4;
+              if (gm < P.M && gn < P.N) {
+                // x = bf16(x + bf16(gate * y))
+                uint4 o;
+                o.x = badd2(xv[i4].x, bmul2(gv[i4].x, yv[it].x));
+                o.y = badd2(xv[i4].y, bmul2(gv[i4].y, yv[it].y));
+                o.z = badd2(xv[i4].z, bmul2(gv[i4].z, yv[it].z));
+                o.w = badd2(xv[i4].w, bmul2(gv[i4].w, yv[it].w));
+                stg_v4(P.out + (size_t)gm * P.ldo + gn, o);
+              }
             }
           }
         } else {  // EPI_QKV: scatter into the joint [B,H,S,128] head-major layout
