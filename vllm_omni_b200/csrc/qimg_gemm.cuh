@@ -217,11 +217,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const int m_own = tc.m_blk * GEMM_BM + q * 32 + lane;  // this thread's accumulator row
 
+      // batch / in-batch index of the first row of this warp's 32-row slab: one division per tile, rows
+      // then advance incrementally (no per-row integer division in the store loops)
+      const int slab_m0 = tc.m_blk * GEMM_BM + q * 32;
+      const int slab_b0 = slab_m0 / P.rows_per_batch;
+      const int slab_i0 = slab_m0 - slab_b0 * P.rows_per_batch;
       float rstd = 0.f;
       const bf16* cos_row = nullptr;
       const bf16* sin_row = nullptr;
       if (EPI == EPI_QKV) {
-        const int i_own = (m_own < P.M) ? (m_own % P.rows_per_batch) : 0;
+        int i_own = slab_i0 + lane;
+        while (i_own >= P.rows_per_batch) i_own -= P.rows_per_batch;
+        if (m_own >= P.M) i_own = 0;
         cos_row = P.cos + (size_t)i_own * 64;
         sin_row = P.sin + (size_t)i_own * 64;
       }
@@ -351,7 +358,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const int gm = gm0 + (hh * 4 + i4) * 4;
               if (gm < P.M && gn < P.N) {
                 xv[i4] = ldg_v4(P.out + (size_t)gm * P.ldo + gn);
-                gv[i4] = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)(gm / P.rows_per_batch) * P.gate_stride + gn));
+                int b = slab_b0, i = slab_i0 + (gm - slab_m0);
+                while (i >= P.rows_per_batch) {
+                  i -= P.rows_per_batch;
+                  ++b;
+                }
+                gv[i4] = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)b * P.gate_stride + gn));
               }
             }
 #pragma unroll
@@ -375,8 +387,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int it = 0; it < 8; ++it) {
             const int gm = gm0 + it * 4;
             if (gm < P.M && gn < P.N) {
-              const int b = gm / P.rows_per_batch;
-              const int i = gm - b * P.rows_per_batch;
+              int b = slab_b0, i = slab_i0 + (gm - slab_m0);
+              while (i >= P.rows_per_batch) {
+                i -= P.rows_per_batch;
+                ++b;
+              }
               const size_t off = (((size_t)b * P.H + head) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
               stg_v4(base + off, yv[it]);
             }
