@@ -25,6 +25,15 @@ def gen(seed):
     return torch.Generator().manual_seed(seed)
 
 
+@pytest.fixture(params=[0, 1], ids=["cta1", "cta2pair"])
+def gemm_mode(request):
+    """Run a GEMM-bearing test under both tcgen05 tile modes (cta_group::1 and the cta_group::2 CTA pair)."""
+    prev = q.get_gemm_mode()
+    q.set_gemm_mode(request.param)
+    yield request.param
+    q.set_gemm_mode(prev)
+
+
 def make_model(L, H, joint, seed, norm_jitter=0.1):
     from vllm_omni_b200.diffusion.models.qwen_image.qwen_image_transformer import QwenImageTransformer2DModel
     torch.set_default_dtype(bf)
@@ -120,7 +129,7 @@ def test_cfg_euler_step_matches_oracle(cfg):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 768, 256), (1024, 3072, 3072), (77, 64, 512), (512, 12288, 3072), (5, 384, 128)])
-def test_gemm_bias_and_gelu(M, N, K):
+def test_gemm_bias_and_gelu(M, N, K, gemm_mode):
     g = gen(6)
     x = torch.randn(M, K, generator=g).bfloat16()
     W = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
@@ -133,7 +142,7 @@ def test_gemm_bias_and_gelu(M, N, K):
         assert O.rel_fro(y, F.gelu(F.linear(x, W, b), approximate="tanh")) < 5e-3  # reference bf16 op order
 
 
-def test_gemm_grouped_gate_residual():
+def test_gemm_grouped_gate_residual(gemm_mode):
     g = gen(7)
     Mi, Mt, D, K = 2 * 200, 2 * 24, 256, 1024
     xi, xt = torch.randn(Mi, D, generator=g).bfloat16(), torch.randn(Mt, D, generator=g).bfloat16()
@@ -168,7 +177,7 @@ def _qkv_reference(w, p, img, txt, H, rope):
 
 
 @pytest.mark.parametrize("B,h,wd,T,H", [(1, 8, 16, 128, 2), (2, 10, 9, 37, 2), (1, 32, 32, 128, 4), (1, 3, 5, 300, 1)])
-def test_qkv_epilogue_and_joint_attention(B, h, wd, T, H):
+def test_qkv_epilogue_and_joint_attention(B, h, wd, T, H, gemm_mode):
     g = gen(8)
     S_img, D = h * wd, H * 128
     S = S_img + T
@@ -227,7 +236,7 @@ def test_fmha_large_scores_lazy_rescale():
 
 
 @pytest.mark.parametrize("name", ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1"])
-def test_model_forward_vs_reference_golden(golden_dir, name):
+def test_model_forward_vs_reference_golden(golden_dir, name, gemm_mode):
     fx = torch.load(os.path.join(golden_dir, name + ".pt"))
     c = fx["case"]
     m = make_model(c["L"], c["H"], c["joint"], c["seed"])

@@ -1,12 +1,14 @@
 // C-ABI entry points (include/qimg_b200.h) and host launchers for the sm_100a kernels.
 #include "../../include/qimg_b200.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "qimg_elementwise.cuh"
 #include "qimg_fmha.cuh"
 #include "qimg_gemm.cuh"
+#include "qimg_gemm2.cuh"
 #include "qimg_host.cuh"
 
 namespace qimg {
@@ -166,11 +168,39 @@ static int launch_gemm_inst(const CUtensorMap* tA[2], const CUtensorMap* tB[2], 
   return 0;
 }
 
+template <int EPI>
+static int launch_gemm2_inst(const CUtensorMap* tA[2], const CUtensorMap* tB[2], const GemmParams& prm, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+    attr_set = true;
+  }
+  int sms = device_sm_count();
+  if (sms <= 0) return fail("no CUDA device");
+  int clusters = sms / 2;
+  if (prm.total_tiles < clusters) clusters = prm.total_tiles;
+  gemm_umma2_kernel<EPI><<<2 * clusters, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(*tA[0], *tB[0], *tA[1], *tB[1], prm);
+  QIMG_LAUNCH_CHECK("gemm_umma2_kernel");
+  return 0;
+}
+
+// 0 = one CTA per tile (128x256, cta_group::1); 1 = CTA pair per tile (256x256, cta_group::2)
+static int g_gemm_mode = -1;
+static int gemm_mode() {
+  if (g_gemm_mode < 0) {
+    const char* e = getenv("QIMG_GEMM_MODE");
+    g_gemm_mode = e ? atoi(e) : 0;
+  }
+  return g_gemm_mode;
+}
+
 static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStream_t st) {
   if (nprob < 1 || nprob > 2) return fail("qimg_gemm: nprob must be 1 or 2");
   int maxN = 0;
   for (int i = 0; i < nprob; ++i) maxN = pr[i].N > maxN ? pr[i].N : maxN;
   const int BN = (maxN <= 64 && epi == QIMG_EPI_BIAS) ? 64 : 256;
+  const bool pair = (BN == 256) && gemm_mode() == 1;
+  const int tile_m = pair ? 256 : GEMM_BM;
   GemmParams prm;
   memset(&prm, 0, sizeof prm);
   prm.nprob = nprob;
@@ -203,12 +233,12 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
       return fail("qimg_gemm: out missing or ldo not a multiple of 8");
     }
     if (epi == QIMG_EPI_BIAS_GATE_RES && !s.gate) return fail("qimg_gemm: gate missing");
-    d.m_tiles = (s.M + GEMM_BM - 1) / GEMM_BM;
+    d.m_tiles = (s.M + tile_m - 1) / tile_m;
     d.n_tiles = (s.N + BN - 1) / BN;
     d.tile_begin = tiles;
     tiles += d.m_tiles * d.n_tiles;
     tA[i] = get_tmap_2d(s.A, (uint64_t)s.K, (uint64_t)s.M, GEMM_BM);
-    tB[i] = get_tmap_2d(s.W, (uint64_t)s.K, (uint64_t)s.N, (uint32_t)BN);
+    tB[i] = get_tmap_2d(s.W, (uint64_t)s.K, (uint64_t)s.N, pair ? 128u : (uint32_t)BN);
     if (!tA[i] || !tB[i]) return 1;
   }
   if (nprob == 1) {
@@ -220,6 +250,15 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
   for (int i = 0; i < nprob; ++i) flops += 2.0 * pr[i].M * (double)pr[i].N * pr[i].K;
   ProfScope prof(0, flops, st);
   if (BN == 64) return launch_gemm_inst<64, EPI_BIAS>(tA, tB, prm, st);
+  if (pair) {
+    switch (epi) {
+      case QIMG_EPI_BIAS: return launch_gemm2_inst<EPI_BIAS>(tA, tB, prm, st);
+      case QIMG_EPI_BIAS_GELU: return launch_gemm2_inst<EPI_BIAS_GELU>(tA, tB, prm, st);
+      case QIMG_EPI_BIAS_GATE_RES: return launch_gemm2_inst<EPI_BIAS_GATE_RES>(tA, tB, prm, st);
+      case QIMG_EPI_QKV: return launch_gemm2_inst<EPI_QKV>(tA, tB, prm, st);
+    }
+    return fail("qimg_gemm: unknown epilogue");
+  }
   switch (epi) {
     case QIMG_EPI_BIAS: return launch_gemm_inst<256, EPI_BIAS>(tA, tB, prm, st);
     case QIMG_EPI_BIAS_GELU: return launch_gemm_inst<256, EPI_BIAS_GELU>(tA, tB, prm, st);
@@ -329,6 +368,13 @@ long long qimg_launch_count(void) { return g_launch_count.load(); }
 void qimg_reset_launch_count(void) { g_launch_count.store(0); }
 
 void qimg_prof_enable(int on) { g_prof_on = on != 0; }
+
+int qimg_set_gemm_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail("qimg_set_gemm_mode: mode must be 0 (cta_group::1) or 1 (cta_group::2 pair)");
+  g_gemm_mode = mode;
+  return 0;
+}
+int qimg_get_gemm_mode(void) { return gemm_mode(); }
 
 int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* flops_total) {
   if (kind < 0 || kind > 1) return fail("qimg_prof_collect: kind");

@@ -18,6 +18,8 @@
 // Online softmax with lazy (warp-uniform, threshold 2^8) rescaling of the O accumulator.
 #pragma once
 
+#include <type_traits>
+
 #include "qimg_common.cuh"
 
 namespace qimg {
@@ -90,8 +92,12 @@ __device__ __forceinline__ uint64_t exp2_poly_f32x2(uint64_t x) {
   return pack_f32x2(pl + (tl << 23), ph + (th << 23));
 }
 
+// Measured on B200 (profiles/r01_fmha_v3): with 37.5 % of the pairs on the polynomial the XU pipe sat at 31 %
+// and the kernel was bound by softmax issue slots / latency, not by MUFU, so the default routes everything
+// to MUFU.EX2 (fewest instructions per element); the polynomial stays available for head sizes / chips where
+// the XU pipe saturates first.
 #ifndef FMHA_POLY_MASK
-#define FMHA_POLY_MASK 0x52u  // of every 8 pairs, pairs {1,4,6} use the polynomial (37.5 %)
+#define FMHA_POLY_MASK 0x00u  // bit k set => pair (k mod 8) of every 8 pairs uses the FMA-pipe polynomial
 #endif
 
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
@@ -232,79 +238,86 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       const int kv_valid = prm.S - j * 128;  // < 128 only on a ragged last tile
-      // ---- one TMEM round trip: the whole 128-wide score row lives in registers ----
-      uint32_t r[128];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(tS + cc * 32, r + cc * 32);
-      tmem_ld_wait();
-      if (kv_valid < 128) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= kv_valid) r[i] = 0xff800000u;  // -inf
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 128; i += 8) {
-        mx0 = max3_f32(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        mx1 = max3_f32(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-        mx2 = max3_f32(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-        mx3 = max3_f32(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        const float m_new = fmaxf(m_used, mx);
-        const bool need = (m_new - m_used) * c > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          // rescale O and l to the new reference max (PV(j-1) of this tile is complete: s_full(j)
-          // was committed after it in the in-order tensor pipe)
-          const float f = ex2_approx((m_used - m_new) * c);
-          l *= f;
-#pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tO + cc * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st_32x32b_x32(tO + cc * 32, o);
-          }
-          tmem_st_wait();
-          m_used = m_new;
+      // The body is instantiated twice; only the ragged last KV tile pays for the 128 compare/selects
+      // of the -inf masking (as one predicated block they would be executed on every tile).
+      auto softmax_tile = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        // ---- one TMEM round trip: the whole 128-wide score row lives in registers ----
+        uint32_t r[128];
+  #pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(tS + cc * 32, r + cc * 32);
+        tmem_ld_wait();
+        if (MASKED) {
+  #pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= kv_valid) r[i] = 0xff800000u;  // -inf
         }
-      }
-      // ---- P = exp2(s*c - m*c) (masked columns give exp2(-inf) = 0), row sum, bf16 P -> TMEM ----
-      const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_used * c);
-      uint64_t la = 0, lb = 0;  // two packed partial row sums (bit pattern 0 = +0.0f pairs)
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int k = cc * 16 + i;  // pair index 0..63
-          const uint64_t x = fma_f32x2(pack_f32x2(r[2 * k], r[2 * k + 1]), c2, nmc2);
-          uint64_t p;
-          if ((FMHA_POLY_MASK >> (k & 7)) & 1u) {
-            p = exp2_poly_f32x2(x);
-          } else {
-            uint32_t xl, xh;
-            unpack_f32x2(x, xl, xh);
-            p = pack_f32x2(__float_as_uint(ex2_approx(__uint_as_float(xl))), __float_as_uint(ex2_approx(__uint_as_float(xh))));
-          }
-          if (i & 1) lb = add_f32x2(lb, p); else la = add_f32x2(la, p);
-          uint32_t pl, ph;
-          unpack_f32x2(p, pl, ph);
-          pk[i] = pack_bf16x2(__uint_as_float(pl), __uint_as_float(ph));
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+  #pragma unroll
+        for (int i = 0; i < 128; i += 8) {
+          mx0 = max3_f32(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          mx1 = max3_f32(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          mx2 = max3_f32(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+          mx3 = max3_f32(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
         }
-        tmem_st_32x32b_x16(tS + cc * 16, pk);
-      }
-      {
-        uint32_t a0, a1, b0, b1;
-        unpack_f32x2(la, a0, a1);
-        unpack_f32x2(lb, b0, b1);
-        l += (__uint_as_float(a0) + __uint_as_float(a1)) + (__uint_as_float(b0) + __uint_as_float(b1));
-      }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          const float m_new = fmaxf(m_used, mx);
+          const bool need = (m_new - m_used) * c > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            // rescale O and l to the new reference max (PV(j-1) of this tile is complete: s_full(j)
+            // was committed after it in the in-order tensor pipe)
+            const float f = ex2_approx((m_used - m_new) * c);
+            l *= f;
+  #pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(tO + cc * 32, o);
+              tmem_ld_wait();
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st_32x32b_x32(tO + cc * 32, o);
+            }
+            tmem_st_wait();
+            m_used = m_new;
+          }
+        }
+        // ---- P = exp2(s*c - m*c) (masked columns give exp2(-inf) = 0), row sum, bf16 P -> TMEM ----
+        const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_used * c);
+        uint64_t la = 0, lb = 0;  // two packed partial row sums (bit pattern 0 = +0.0f pairs)
+  #pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t pk[16];
+  #pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = cc * 16 + i;  // pair index 0..63
+            const uint64_t x = fma_f32x2(pack_f32x2(r[2 * k], r[2 * k + 1]), c2, nmc2);
+            uint64_t p;
+            if ((FMHA_POLY_MASK >> (k & 7)) & 1u) {
+              p = exp2_poly_f32x2(x);
+            } else {
+              uint32_t xl, xh;
+              unpack_f32x2(x, xl, xh);
+              p = pack_f32x2(__float_as_uint(ex2_approx(__uint_as_float(xl))), __float_as_uint(ex2_approx(__uint_as_float(xh))));
+            }
+            if (i & 1) lb = add_f32x2(lb, p); else la = add_f32x2(la, p);
+            uint32_t pl, ph;
+            unpack_f32x2(p, pl, ph);
+            pk[i] = pack_bf16x2(__uint_as_float(pl), __uint_as_float(ph));
+          }
+          tmem_st_32x32b_x16(tS + cc * 16, pk);
+        }
+        {
+          uint32_t a0, a1, b0, b1;
+          unpack_f32x2(la, a0, a1);
+          unpack_f32x2(lb, b0, b1);
+          l += (__uint_as_float(a0) + __uint_as_float(a1)) + (__uint_as_float(b0) + __uint_as_float(b1));
+        }
+      };
+      if (kv_valid < 128) softmax_tile(std::true_type{});
+      else softmax_tile(std::false_type{});
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

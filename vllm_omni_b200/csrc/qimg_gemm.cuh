@@ -72,19 +72,210 @@ struct TileCoord {
   int pi, m_blk, n_blk;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& prm, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& prm, int tile, int group_m = GEMM_GROUP_M) {
   TileCoord tc;
   tc.pi = (prm.nprob > 1 && tile >= prm.p[1].tile_begin) ? 1 : 0;
   const GemmProblem& P = prm.p[tc.pi];
   int t = tile - P.tile_begin;
-  int per_band = GEMM_GROUP_M * P.n_tiles;
+  int per_band = group_m * P.n_tiles;
   int band = t / per_band;
   int within = t - band * per_band;
-  int m0 = band * GEMM_GROUP_M;
-  int gm = min(GEMM_GROUP_M, P.m_tiles - m0);
+  int m0 = band * group_m;
+  int gm = min(group_m, P.m_tiles - m0);
   tc.m_blk = m0 + within % gm;
   tc.n_blk = within / gm;
   return tc;
+}
+
+// One accumulator tile (128 rows x BN columns, rows [m_blk*128, +128)) -> global memory.  Executed by the 8
+// epilogue warps of a CTA; warp (q = lane quarter, chunk range) owns 32 rows x (chunk_hi-chunk_lo)*64 columns.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmProblem& P, int m_blk, int n_blk, uint32_t t_row, uint32_t stg,
+                                              int lane, int q, int chunk_lo, int chunk_hi) {
+  const int m_own = m_blk * GEMM_BM + q * 32 + lane;  // this thread's accumulator row
+
+  // batch / in-batch index of the first row of this warp's 32-row slab: one division per tile, rows
+  // then advance incrementally (no per-row integer division in the store loops)
+  const int slab_m0 = m_blk * GEMM_BM + q * 32;
+  const int slab_b0 = slab_m0 / P.rows_per_batch;
+  const int slab_i0 = slab_m0 - slab_b0 * P.rows_per_batch;
+  float rstd = 0.f;
+  const bf16* cos_row = nullptr;
+  const bf16* sin_row = nullptr;
+  if (EPI == EPI_QKV) {
+    int i_own = slab_i0 + lane;
+    while (i_own >= P.rows_per_batch) i_own -= P.rows_per_batch;
+    if (m_own >= P.M) i_own = 0;
+    cos_row = P.cos + (size_t)i_own * 64;
+    sin_row = P.sin + (size_t)i_own * 64;
+  }
+
+#pragma unroll 1
+  for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+    const int n0 = n_blk * BN + chunk * 64;
+    int which = 0, head = 0, half = 0;
+    if (EPI == EPI_QKV) {
+      const int D = P.N / 3;
+      which = n0 / D;                // 0 = q, 1 = k, 2 = v
+      head = (n0 - which * D) >> 7;  // head index
+      half = (n0 >> 6) & 1;          // which 64-column half of the head
+      if (which < 2 && half == 0 && n0 < P.N) {
+        // pass 1 over the whole head (128 columns): sum of squares of bf16(acc + bias)
+        float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(t_row + chunk * 64 + c4 * 32, t);
+          const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0 + c4 * 32);
+          uint4 bv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bv[j] = __ldg(bp + j);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t bw[4] = {bv[j].x, bv[j].y, bv[j].z, bv[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t v = pack_bf16x2(__uint_as_float(t[j * 8 + e * 2]) + bf16lo(bw[e]),
+                                             __uint_as_float(t[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
+              ss0 = fmaf(bf16lo(v), bf16lo(v), ss0);
+              ss1 = fmaf(bf16hi(v), bf16hi(v), ss1);
+            }
+          }
+        }
+        rstd = rsqrtf((ss0 + ss1) * (1.0f / 128.0f) + P.eps);
+      }
+    }
+    uint32_t r[64];
+    tmem_ld_32x32b_x32(t_row + chunk * 64, r);
+    tmem_ld_32x32b_x32(t_row + chunk * 64 + 32, r + 32);
+    // this row's cos/sin (per-thread addresses) are fetched while the TMEM read is in flight;
+    // bias / norm weights are warp-uniform broadcast loads issued just in time (keeps registers < 168)
+    uint4 cv[4], sv[4];
+    if (EPI == EPI_QKV && which < 2 && n0 < P.N) {
+      const uint4* cp = reinterpret_cast<const uint4*>(cos_row + half * 32);
+      const uint4* sp = reinterpret_cast<const uint4*>(sin_row + half * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cv[j] = __ldg(cp + j);
+        sv[j] = __ldg(sp + j);
+      }
+    }
+    tmem_ld_wait();
+
+    // ---- math on this thread's 64 columns -> 32 packed bf16x2 words ----
+    uint32_t pk[32];
+    if (n0 < P.N) {
+      const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0);
+      const uint4* np = reinterpret_cast<const uint4*>((which == 0 ? P.nq_w : P.nk_w) + half * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 bvj = __ldg(bp + j);
+        const uint32_t bw[4] = {bvj.x, bvj.y, bvj.z, bvj.w};
+        uint4 nvj = make_uint4(0, 0, 0, 0);
+        if (EPI == EPI_QKV && which < 2) nvj = __ldg(np + j);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // v = bf16(acc + bias): the Linear's bf16 output
+          uint32_t v = pack_bf16x2(__uint_as_float(r[j * 8 + e * 2]) + bf16lo(bw[e]),
+                                   __uint_as_float(r[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
+          if (EPI == EPI_BIAS_GELU) {
+            v = pack_bf16x2(gelu_tanh_fast(bf16lo(v)), gelu_tanh_fast(bf16hi(v)));
+          }
+          if (EPI == EPI_QKV && which < 2) {
+            const uint32_t nw4[4] = {nvj.x, nvj.y, nvj.z, nvj.w};
+            // RMSNorm: fp32 normalise -> bf16 -> * weight -> bf16   (vLLM rms_norm)
+            uint32_t x = bmul2(pack_bf16x2(bf16lo(v) * rstd, bf16hi(v) * rstd), nw4[e]);
+            // interleaved RoPE, every op rounded to bf16: x*cos + rotate_half(x)*sin with
+            // rotate_half(x) = (-x[2i+1], x[2i]); pair index within this 64-col chunk = j*4 + e
+            const int pi = j * 4 + e;  // 0..31 -> 16-byte vector pi/8, word (pi%8)/2, half pi&1
+            const uint4 c4 = cv[pi >> 3], s4 = sv[pi >> 3];
+            const uint32_t cw4[4] = {c4.x, c4.y, c4.z, c4.w}, sw4[4] = {s4.x, s4.y, s4.z, s4.w};
+            const uint32_t cw = cw4[(pi & 7) >> 1], sw = sw4[(pi & 7) >> 1];
+            const uint32_t cc = (pi & 1) ? dup_hi(cw) : dup_lo(cw);
+            const uint32_t ssn = (pi & 1) ? dup_hi(sw) : dup_lo(sw);
+            const uint32_t rot = swap_halves(x) ^ 0x00008000u;  // (-x_hi, x_lo)
+            v = badd2(bmul2(x, cc), bmul2(rot, ssn));
+          }
+          pk[j * 4 + e] = v;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pk[j] = 0;
+    }
+
+    // ---- stage to smem (16 B chunk index XOR row&7 -> conflict-free), then coalesced stores ----
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]));
+    }
+    __syncwarp();
+    const int c16 = lane & 7;
+    const int gn = n0 + c16 * 8;
+    const int gm0 = m_blk * GEMM_BM + q * 32 + (lane >> 3);
+    uint4 yv[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      yv[it] = lds_v4(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+    }
+    if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int gm = gm0 + it * 4;
+        if (gm < P.M && gn < P.N) stg_v4(P.out + (size_t)gm * P.ldo + gn, yv[it]);
+      }
+    } else if (EPI == EPI_BIAS_GATE_RES) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {  // two batches of 4 rows: loads first, then math + stores
+        uint4 xv[4], gv[4];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int gm = gm0 + (hh * 4 + i4) * 4;
+          if (gm < P.M && gn < P.N) {
+            xv[i4] = ldg_v4(P.out + (size_t)gm * P.ldo + gn);
+            int b = slab_b0, i = slab_i0 + (gm - slab_m0);
+            while (i >= P.rows_per_batch) {
+              i -= P.rows_per_batch;
+              ++b;
+            }
+            gv[i4] = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)b * P.gate_stride + gn));
+          }
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int it = hh * 4 + i4;
+          const int gm = gm0 + it * 4;
+          if (gm < P.M && gn < P.N) {
+            // x = bf16(x + bf16(gate * y))
+            uint4 o;
+            o.x = badd2(xv[i4].x, bmul2(gv[i4].x, yv[it].x));
+            o.y = badd2(xv[i4].y, bmul2(gv[i4].y, yv[it].y));
+            o.z = badd2(xv[i4].z, bmul2(gv[i4].z, yv[it].z));
+            o.w = badd2(xv[i4].w, bmul2(gv[i4].w, yv[it].w));
+            stg_v4(P.out + (size_t)gm * P.ldo + gn, o);
+          }
+        }
+      }
+    } else {  // EPI_QKV: scatter into the joint [B,H,S,128] head-major layout
+      bf16* base = (which == 0) ? P.q : (which == 1 ? P.k : P.v);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int gm = gm0 + it * 4;
+        if (gm < P.M && gn < P.N) {
+          int b = slab_b0, i = slab_i0 + (gm - slab_m0);
+          while (i >= P.rows_per_batch) {
+            i -= P.rows_per_batch;
+            ++b;
+          }
+          const size_t off = (((size_t)b * P.H + head) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
+          stg_v4(base + off, yv[it]);
+        }
+      }
+    }
+    __syncwarp();
+  }
 }
 
 template <int BN, int EPI>
@@ -215,190 +406,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      const int m_own = tc.m_blk * GEMM_BM + q * 32 + lane;  // this thread's accumulator row
-
-      // batch / in-batch index of the first row of this warp's 32-row slab: one division per tile, rows
-      // then advance incrementally (no per-row integer division in the store loops)
-      const int slab_m0 = tc.m_blk * GEMM_BM + q * 32;
-      const int slab_b0 = slab_m0 / P.rows_per_batch;
-      const int slab_i0 = slab_m0 - slab_b0 * P.rows_per_batch;
-      float rstd = 0.f;
-      const bf16* cos_row = nullptr;
-      const bf16* sin_row = nullptr;
-      if (EPI == EPI_QKV) {
-        int i_own = slab_i0 + lane;
-        while (i_own >= P.rows_per_batch) i_own -= P.rows_per_batch;
-        if (m_own >= P.M) i_own = 0;
-        cos_row = P.cos + (size_t)i_own * 64;
-        sin_row = P.sin + (size_t)i_own * 64;
-      }
-
-#pragma unroll 1
-      for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
-        const int n0 = tc.n_blk * BN + chunk * 64;
-        int which = 0, head = 0, half = 0;
-        if (EPI == EPI_QKV) {
-          const int D = P.N / 3;
-          which = n0 / D;                // 0 = q, 1 = k, 2 = v
-          head = (n0 - which * D) >> 7;  // head index
-          half = (n0 >> 6) & 1;          // which 64-column half of the head
-          if (which < 2 && half == 0 && n0 < P.N) {
-            // pass 1 over the whole head (128 columns): sum of squares of bf16(acc + bias)
-            float ss0 = 0.f, ss1 = 0.f;
-#pragma unroll 1
-            for (int c4 = 0; c4 < 4; ++c4) {
-              uint32_t t[32];
-              tmem_ld_32x32b_x32(t_row + chunk * 64 + c4 * 32, t);
-              const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0 + c4 * 32);
-              uint4 bv[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) bv[j] = __ldg(bp + j);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t bw[4] = {bv[j].x, bv[j].y, bv[j].z, bv[j].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const uint32_t v = pack_bf16x2(__uint_as_float(t[j * 8 + e * 2]) + bf16lo(bw[e]),
-                                                 __uint_as_float(t[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
-                  ss0 = fmaf(bf16lo(v), bf16lo(v), ss0);
-                  ss1 = fmaf(bf16hi(v), bf16hi(v), ss1);
-                }
-              }
-            }
-            rstd = rsqrtf((ss0 + ss1) * (1.0f / 128.0f) + P.eps);
-          }
-        }
-        uint32_t r[64];
-        tmem_ld_32x32b_x32(t_row + chunk * 64, r);
-        tmem_ld_32x32b_x32(t_row + chunk * 64 + 32, r + 32);
-        // this row's cos/sin (per-thread addresses) are fetched while the TMEM read is in flight;
-        // bias / norm weights are warp-uniform broadcast loads issued just in time (keeps registers < 168)
-        uint4 cv[4], sv[4];
-        if (EPI == EPI_QKV && which < 2 && n0 < P.N) {
-          const uint4* cp = reinterpret_cast<const uint4*>(cos_row + half * 32);
-          const uint4* sp = reinterpret_cast<const uint4*>(sin_row + half * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            cv[j] = __ldg(cp + j);
-            sv[j] = __ldg(sp + j);
-          }
-        }
-        tmem_ld_wait();
-
-        // ---- math on this thread's 64 columns -> 32 packed bf16x2 words ----
-        uint32_t pk[32];
-        if (n0 < P.N) {
-          const uint4* bp = reinterpret_cast<const uint4*>(P.bias + n0);
-          const uint4* np = reinterpret_cast<const uint4*>((which == 0 ? P.nq_w : P.nk_w) + half * 64);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 bvj = __ldg(bp + j);
-            const uint32_t bw[4] = {bvj.x, bvj.y, bvj.z, bvj.w};
-            uint4 nvj = make_uint4(0, 0, 0, 0);
-            if (EPI == EPI_QKV && which < 2) nvj = __ldg(np + j);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              // v = bf16(acc + bias): the Linear's bf16 output
-              uint32_t v = pack_bf16x2(__uint_as_float(r[j * 8 + e * 2]) + bf16lo(bw[e]),
-                                       __uint_as_float(r[j * 8 + e * 2 + 1]) + bf16hi(bw[e]));
-              if (EPI == EPI_BIAS_GELU) {
-                v = pack_bf16x2(gelu_tanh_fast(bf16lo(v)), gelu_tanh_fast(bf16hi(v)));
-              }
-              if (EPI == EPI_QKV && which < 2) {
-                const uint32_t nw4[4] = {nvj.x, nvj.y, nvj.z, nvj.w};
-                // RMSNorm: fp32 normalise -> bf16 -> * weight -> bf16   (vLLM rms_norm)
-                uint32_t x = bmul2(pack_bf16x2(bf16lo(v) * rstd, bf16hi(v) * rstd), nw4[e]);
-                // interleaved RoPE, every op rounded to bf16: x*cos + rotate_half(x)*sin with
-                // rotate_half(x) = (-x[2i+1], x[2i]); pair index within this 64-col chunk = j*4 + e
-                const int pi = j * 4 + e;  // 0..31 -> 16-byte vector pi/8, word (pi%8)/2, half pi&1
-                const uint4 c4 = cv[pi >> 3], s4 = sv[pi >> 3];
-                const uint32_t cw4[4] = {c4.x, c4.y, c4.z, c4.w}, sw4[4] = {s4.x, s4.y, s4.z, s4.w};
-                const uint32_t cw = cw4[(pi & 7) >> 1], sw = sw4[(pi & 7) >> 1];
-                const uint32_t cc = (pi & 1) ? dup_hi(cw) : dup_lo(cw);
-                const uint32_t ssn = (pi & 1) ? dup_hi(sw) : dup_lo(sw);
-                const uint32_t rot = swap_halves(x) ^ 0x00008000u;  // (-x_hi, x_lo)
-                v = badd2(bmul2(x, cc), bmul2(rot, ssn));
-              }
-              pk[j * 4 + e] = v;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) pk[j] = 0;
-        }
-
-        // ---- stage to smem (16 B chunk index XOR row&7 -> conflict-free), then coalesced stores ----
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]));
-        }
-        __syncwarp();
-        const int c16 = lane & 7;
-        const int gn = n0 + c16 * 8;
-        const int gm0 = tc.m_blk * GEMM_BM + q * 32 + (lane >> 3);
-        uint4 yv[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3);
-          yv[it] = lds_v4(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
-        }
-        if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int gm = gm0 + it * 4;
-            if (gm < P.M && gn < P.N) stg_v4(P.out + (size_t)gm * P.ldo + gn, yv[it]);
-          }
-        } else if (EPI == EPI_BIAS_GATE_RES) {
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {  // two batches of 4 rows: loads first, then math + stores
-            uint4 xv[4], gv[4];
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const int gm = gm0 + (hh * 4 + i4) * 4;
-              if (gm < P.M && gn < P.N) {
-                xv[i4] = ldg_v4(P.out + (size_t)gm * P.ldo + gn);
-                int b = slab_b0, i = slab_i0 + (gm - slab_m0);
-                while (i >= P.rows_per_batch) {
-                  i -= P.rows_per_batch;
-                  ++b;
-                }
-                gv[i4] = __ldg(reinterpret_cast<const uint4*>(P.gate + (size_t)b * P.gate_stride + gn));
-              }
-            }
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const int it = hh * 4 + i4;
-              const int gm = gm0 + it * 4;
-              if (gm < P.M && gn < P.N) {
-                // x = bf16(x + bf16(gate * y))
-                uint4 o;
-                o.x = badd2(xv[i4].x, bmul2(gv[i4].x, yv[it].x));
-                o.y = badd2(xv[i4].y, bmul2(gv[i4].y, yv[it].y));
-                o.z = badd2(xv[i4].z, bmul2(gv[i4].z, yv[it].z));
-                o.w = badd2(xv[i4].w, bmul2(gv[i4].w, yv[it].w));
-                stg_v4(P.out + (size_t)gm * P.ldo + gn, o);
-              }
-            }
-          }
-        } else {  // EPI_QKV: scatter into the joint [B,H,S,128] head-major layout
-          bf16* base = (which == 0) ? P.q : (which == 1 ? P.k : P.v);
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int gm = gm0 + it * 4;
-            if (gm < P.M && gn < P.N) {
-              int b = slab_b0, i = slab_i0 + (gm - slab_m0);
-              while (i >= P.rows_per_batch) {
-                i -= P.rows_per_batch;
-                ++b;
-              }
-              const size_t off = (((size_t)b * P.H + head) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
-              stg_v4(base + off, yv[it]);
-            }
-          }
-        }
-        __syncwarp();
-      }
+      epilogue_tile<BN, EPI>(P, tc.m_blk, tc.n_blk, t_row, stg, lane, q, chunk_lo, chunk_hi);
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
