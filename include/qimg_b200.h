@@ -38,7 +38,7 @@ void qimg_prof_enable(int on);
 int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* flops_total);
 
 /* GEMM tile mode: 0 = one CTA per 128x256 tile (tcgen05 cta_group::1), 1 = CTA pair per 256x256 tile
- * (cta_group::2, cluster of 2).  Default from env QIMG_GEMM_MODE (else 0). */
+ * (cta_group::2, cluster of 2).  Default 1; env QIMG_GEMM_MODE overrides. */
 int qimg_set_gemm_mode(int mode);
 int qimg_get_gemm_mode(void);
 

@@ -189,7 +189,7 @@ static int g_gemm_mode = -1;
 static int gemm_mode() {
   if (g_gemm_mode < 0) {
     const char* e = getenv("QIMG_GEMM_MODE");
-    g_gemm_mode = e ? atoi(e) : 0;
+    g_gemm_mode = e ? atoi(e) : 1;  // CTA pair: +6 % over cta_group::1 on every block GEMM (profiles/r01_kernel_bench.md)
   }
   return g_gemm_mode;
 }
@@ -415,8 +415,16 @@ int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* 
   if (rows <= 0) return 0;
   if (D % 8 || D > EW_MAX_CHUNKS * 256) return fail("qimg_ln_modulate: D must be a multiple of 8 and <= 4096");
   if (rows_per_batch <= 0) return fail("qimg_ln_modulate: rows_per_batch");
-  ln_modulate_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)shift, (const bf16*)scale,
-                                                                       (bf16*)y, rows, D, rows_per_batch, mod_stride, eps);
+  const dim3 grid((rows + 3) / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16 *xp = (const bf16*)x, *shp = (const bf16*)shift, *scp = (const bf16*)scale;
+  if (D == 3072) {  // Qwen-Image width: compile-time row length
+    ln_modulate_fast_kernel<12><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps);
+  } else if (D == 256) {
+    ln_modulate_fast_kernel<1><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps);
+  } else {
+    ln_modulate_kernel<<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, D, rows_per_batch, mod_stride, eps);
+  }
   QIMG_LAUNCH_CHECK("ln_modulate_kernel");
   return 0;
 }

@@ -72,6 +72,96 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
   }
 }
 
+// Same op for D = NCH * 256 known at compile time (D = 3072 -> NCH = 12): no per-chunk predicates, the row is
+// unpacked once into packed fp32x2 registers and all three passes (mean, variance, normalise+modulate) run on
+// FADD2/FFMA2 + packed bf16 ops: ~5 instructions per element instead of ~15 (the generic kernel above is
+// issue-bound at 2.4 TB/s; profiles/r01_ln_modulate).
+__device__ __forceinline__ uint64_t ew_pack2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void ew_unpack2(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ew_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t ew_add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ew_splat2(float v) { return ew_pack2(__float_as_uint(v), __float_as_uint(v)); }
+__device__ __forceinline__ float ew_hsum2(uint64_t v) {
+  uint32_t a, b;
+  ew_unpack2(v, a, b);
+  return __uint_as_float(a) + __uint_as_float(b);
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(128) ln_modulate_fast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
+                                                               const bf16* __restrict__ scale, bf16* __restrict__ y,
+                                                               int rows, int rows_per_batch, long long mod_stride,
+                                                               float eps) {
+  constexpr int D = NCH * 256;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* xr = x + (size_t)row * D + lane * 8;
+  uint64_t c[NCH * 4];  // the row as fp32 pairs
+  {
+    uint4 v[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) v[i] = ldg_nc_v4(xr + i * 256);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[i * 4 + k] = ew_pack2(w[k] << 16, w[k] & 0xffff0000u);
+    }
+  }
+  uint64_t s0 = 0, s1 = 0;
+#pragma unroll
+  for (int i = 0; i < NCH * 4; i += 2) {
+    s0 = ew_add2(s0, c[i]);
+    s1 = ew_add2(s1, c[i + 1]);
+  }
+  const float mean = warp_sum(ew_hsum2(ew_add2(s0, s1))) * (1.0f / (float)D);
+  const uint64_t nmean2 = ew_splat2(-mean);
+  uint64_t q0 = 0, q1 = 0;
+#pragma unroll
+  for (int i = 0; i < NCH * 4; i += 2) {
+    c[i] = ew_add2(c[i], nmean2);
+    c[i + 1] = ew_add2(c[i + 1], nmean2);
+    q0 = ew_fma2(c[i], c[i], q0);
+    q1 = ew_fma2(c[i + 1], c[i + 1], q1);
+  }
+  const float rstd = rsqrtf(warp_sum(ew_hsum2(ew_add2(q0, q1))) * (1.0f / (float)D) + eps);
+  const uint64_t rstd2 = ew_splat2(rstd), zero2 = 0;
+  const int b = row / rows_per_batch;
+  const bf16* sh = shift + (size_t)b * mod_stride + lane * 8;
+  const bf16* sc = scale + (size_t)b * mod_stride + lane * 8;
+  bf16* yr = y + (size_t)row * D + lane * 8;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const uint4 shv = __ldg(reinterpret_cast<const uint4*>(sh + i * 256));
+    const uint4 scv = __ldg(reinterpret_cast<const uint4*>(sc + i * 256));
+    const uint32_t s1w[4] = {shv.x, shv.y, shv.z, shv.w}, s2w[4] = {scv.x, scv.y, scv.z, scv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t lo, hi;
+      ew_unpack2(ew_fma2(c[i * 4 + k], rstd2, zero2), lo, hi);
+      const uint32_t n = pack_bf16x2(__uint_as_float(lo), __uint_as_float(hi));
+      o[k] = badd2(bmul2(n, badd2(0x3F803F80u, s2w[k])), s1w[k]);
+    }
+    stg_v4(yr + i * 256, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
 // y = bf16( bf16(x * rsqrt(mean(x^2) + eps)) * w )     (vLLM RMSNorm, used for txt_norm :758)
 __global__ void __launch_bounds__(128) rms_norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                        bf16* __restrict__ y, int rows, int D, float eps) {
