@@ -42,6 +42,11 @@ int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* f
 int qimg_set_gemm_mode(int mode);
 int qimg_get_gemm_mode(void);
 
+/* Attention pipeline: 0 = 128-row KV tiles, one score buffer per query tile; 1 = 64-row KV tiles with
+ * double-buffered scores in TMEM (QK^T of tile j+1 issued before softmax(j) finishes).  Env QIMG_FMHA_MODE. */
+int qimg_set_fmha_mode(int mode);
+int qimg_get_fmha_mode(void);
+
 /* ---- bandwidth-bound fused ops ------------------------------------------------------ */
 /* y[r,:] = LN(x[r,:]; eps, no affine) * (1 + scale[b,:]) + shift[b,:],  b = r / rows_per_batch.
  * Replaces AdaLayerNorm.forward_cuda/forward_native, vllm_omni/diffusion/layers/adalayernorm.py:62-68,94-102

@@ -52,6 +52,15 @@ def test_library_loaded_and_device():
     assert os.path.exists(q.LIB_PATH)
 
 
+@pytest.fixture(params=[0, 1], ids=["kv128", "kv64dbuf"])
+def fmha_mode(request):
+    """Both attention pipelines (first-generation 128-row KV tiles / double-buffered 64-row KV tiles)."""
+    prev = q.get_fmha_mode()
+    q.set_fmha_mode(request.param)
+    yield request.param
+    q.set_fmha_mode(prev)
+
+
 def test_umma_probe_all_operand_paths():
     g = gen(0)
     A = torch.randn(128, 128, generator=g).bfloat16()
@@ -177,7 +186,7 @@ def _qkv_reference(w, p, img, txt, H, rope):
 
 
 @pytest.mark.parametrize("B,h,wd,T,H", [(1, 8, 16, 128, 2), (2, 10, 9, 37, 2), (1, 32, 32, 128, 4), (1, 3, 5, 300, 1)])
-def test_qkv_epilogue_and_joint_attention(B, h, wd, T, H, gemm_mode):
+def test_qkv_epilogue_and_joint_attention(B, h, wd, T, H, gemm_mode, fmha_mode):
     g = gen(8)
     S_img, D = h * wd, H * 128
     S = S_img + T
@@ -211,7 +220,7 @@ def test_qkv_epilogue_and_joint_attention(B, h, wd, T, H, gemm_mode):
     assert O.rel_fro(oi.cpu().view(B, S_img, D), o_ref[:, T:]) < TOL_KERNEL
 
 
-def test_attention_backend_plugin_matches_sdpa():
+def test_attention_backend_plugin_matches_sdpa(fmha_mode):
     from vllm_omni_b200.diffusion.attention.layer import Attention
     g = gen(9)
     qq, kk, vv = (torch.randn(2, 300, 3, 128, generator=g).bfloat16() for _ in range(3))
@@ -221,7 +230,7 @@ def test_attention_backend_plugin_matches_sdpa():
     assert out.shape == ref.shape and O.rel_fro(out, ref) < TOL_KERNEL
 
 
-def test_fmha_large_scores_lazy_rescale():
+def test_fmha_large_scores_lazy_rescale(fmha_mode):
     """Growing score magnitudes along kv force the lazy O-rescale path (threshold 2^8)."""
     g = gen(10)
     B, H, S = 1, 1, 1024
@@ -236,7 +245,7 @@ def test_fmha_large_scores_lazy_rescale():
 
 
 @pytest.mark.parametrize("name", ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1"])
-def test_model_forward_vs_reference_golden(golden_dir, name, gemm_mode):
+def test_model_forward_vs_reference_golden(golden_dir, name, gemm_mode, fmha_mode):
     fx = torch.load(os.path.join(golden_dir, name + ".pt"))
     c = fx["case"]
     m = make_model(c["L"], c["H"], c["joint"], c["seed"])

@@ -7,6 +7,7 @@
 
 #include "qimg_elementwise.cuh"
 #include "qimg_fmha.cuh"
+#include "qimg_fmha2.cuh"
 #include "qimg_gemm.cuh"
 #include "qimg_gemm2.cuh"
 #include "qimg_host.cuh"
@@ -499,16 +500,35 @@ int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_s
   return launch_gemm(problems, nprob, epilogue, (cudaStream_t)stream);
 }
 
+// 0 = first-generation pipeline (128-row KV tiles), 1 = double-buffered-S pipeline (64-row KV tiles)
+static int g_fmha_mode = -1;
+static int fmha_mode() {
+  if (g_fmha_mode < 0) {
+    const char* e = getenv("QIMG_FMHA_MODE");
+    g_fmha_mode = e ? atoi(e) : 0;
+  }
+  return g_fmha_mode;
+}
+int qimg_set_fmha_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail("qimg_set_fmha_mode: mode must be 0 or 1");
+  g_fmha_mode = mode;
+  return 0;
+}
+int qimg_get_fmha_mode(void) { return fmha_mode(); }
+
 int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
                     int T, float softmax_scale, qimg_stream_t stream) {
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
+  const bool v5 = fmha_mode() == 1;
+  const uint32_t kv_rows = v5 ? FMHA2_KV : 128;
   const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
-  const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, 128);
-  const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, 128);
+  const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
+  const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
   if (!tq || !tk || !tv) return 1;
   static bool attr_set = false;
   if (!attr_set) {
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
     attr_set = true;
   }
   FmhaParams prm;
@@ -518,7 +538,8 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
   dim3 grid((S + 255) / 256, B * H);
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
-  fmha_joint_kernel<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, (cudaStream_t)stream>>>(*tq, *tk, *tv, prm);
+  if (v5) fmha_joint_kernel_v5<<<grid, FMHA_THREADS, FMHA2_SMEM_BYTES, (cudaStream_t)stream>>>(*tq, *tk, *tv, prm);
+  else fmha_joint_kernel<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, (cudaStream_t)stream>>>(*tq, *tk, *tv, prm);
   QIMG_LAUNCH_CHECK("fmha_joint_kernel");
   return 0;
 }

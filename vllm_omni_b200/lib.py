@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "qimg_ln_modulate", "qimg_gate_residual", "qimg_rms_norm", "qimg_linear_small_m", "qimg_timestep_sinusoid",
     "qimg_cfg_euler_step", "qimg_gemm", "qimg_fmha_joint", "qimg_engine_create", "qimg_engine_destroy",
     "qimg_engine_workspace_bytes", "qimg_engine_forward", "qimg_engine_ws_offset_img", "qimg_engine_ws_offset_txt",
-    "qimg_umma_probe", "qimg_prof_enable", "qimg_prof_collect", "qimg_set_gemm_mode", "qimg_get_gemm_mode",
+    "qimg_umma_probe", "qimg_prof_enable", "qimg_prof_collect", "qimg_set_gemm_mode", "qimg_get_gemm_mode", "qimg_set_fmha_mode", "qimg_get_fmha_mode",
 ]
 
 
@@ -101,6 +101,7 @@ def load():
     lib.qimg_engine_forward.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp, sz, vp]
     lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.qimg_set_gemm_mode.argtypes = [i]
+    lib.qimg_set_fmha_mode.argtypes = [i]
     lib.qimg_prof_enable.argtypes = [i]
     lib.qimg_prof_enable.restype = None
     lib.qimg_prof_collect.argtypes = [i, C.POINTER(C.c_double), C.POINTER(ll), C.POINTER(C.c_double)]
@@ -155,6 +156,14 @@ def set_gemm_mode(mode: int):
 
 def get_gemm_mode() -> int:
     return int(load().qimg_get_gemm_mode())
+
+
+def set_fmha_mode(mode: int):
+    check(load().qimg_set_fmha_mode(int(mode)), "qimg_set_fmha_mode")
+
+
+def get_fmha_mode() -> int:
+    return int(load().qimg_get_fmha_mode())
 
 
 def prof_enable(on: bool):
