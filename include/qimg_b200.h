@@ -59,6 +59,11 @@ int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* 
 int qimg_gate_residual(void* x, const void* y, const void* gate, int rows, int D, int rows_per_batch,
                        long long gate_stride, qimg_stream_t stream);
 
+/* Tensor-parallel form of the gated residual: y is the ALL-REDUCED partial sum of a row-parallel linear
+ * (to_out / net.2 sharded over K), bias is added after the reduction:  x += gate * (y + bias). */
+int qimg_gate_residual_bias(void* x, const void* y, const void* bias, const void* gate, int rows, int D, int rows_per_batch,
+                            long long gate_stride, qimg_stream_t stream);
+
 /* y = RMSNorm(x; w, eps) over the last dim (vLLM RMSNorm used as txt_norm, qwen_image_transformer.py:669,758). */
 int qimg_rms_norm(const void* x, const void* w, void* y, int rows, int D, float eps, qimg_stream_t stream);
 
@@ -148,6 +153,17 @@ typedef struct qimg_global_weights {
 } qimg_global_weights;
 
 typedef struct qimg_engine qimg_engine;
+
+/* Tensor parallelism over attention heads / FFN (not present in the reference, whose Qwen-Image
+ * linears are all `disable_tp=True`, qwen_image_transformer.py:318-349).  With tp_size P the caller passes
+ * per-rank weight shards: to_qkv/add_kv_proj rows of the local H/P heads ([3D/P, D], q|k|v), to_out/to_add_out
+ * columns of the local heads ([D, D/P]), MLP up rows / down columns of the local FF/P slice; biases of the
+ * row-parallel linears (to_out, to_add_out, net.2) are passed in full and applied once after the reduction.
+ * Everything else is replicated.  The engine calls `allreduce(buf, count, user, stream)` (sum over the TP
+ * group, in place, `count` bf16 elements, enqueued on `stream`) twice per block: after the attention
+ * out-projection and after the MLP down-projection (image and text partial sums share one buffer). */
+typedef int (*qimg_allreduce_fn)(void* buf, long long count, void* user, qimg_stream_t stream);
+int qimg_engine_set_tp(qimg_engine* e, int tp_size, qimg_allreduce_fn allreduce, void* user);
 
 int qimg_engine_create(const qimg_dims* dims, const qimg_global_weights* g, const qimg_block_weights* blocks,
                        qimg_engine** out);

@@ -21,7 +21,7 @@ def _worker(rank, world, port, tp, q):
         t = torch.full((4,), float(rank))
         torch.distributed.all_reduce(t, group=ps.get_tp_group())
         q.put(("tp", rank, t.tolist()))
-    if out is not None and dpr == 0:
+    if tp == 1 and out is not None and dpr == 0:
         q.put(("gather", rank, out[:, 0, 0].tolist()))
     ps.destroy_distributed_env()
 

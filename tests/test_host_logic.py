@@ -152,3 +152,33 @@ def test_flops_formula_matches_survey():
     assert abs(flops_per_forward(60, 4096, 128) / 7.056e13 - 1) < 2e-3
     assert abs(flops_per_forward(60, 16384, 128) / 4.254e14 - 1) < 2e-3
     assert abs(flops_per_forward(60, 4096, 128) - O.flops_per_forward(O.DiTDims(), 4096, 128)) < 1
+
+
+def test_tensor_parallel_weight_sharding():
+    """TP (new vs the reference, whose Qwen-Image linears are disable_tp=True): q|k|v rows of the local heads,
+    out-projection / MLP-down columns, MLP-up rows; row-parallel biases stay whole."""
+    H, joint, P = 4, 256, 2
+    D = H * 128
+    full = dict(synthetic.synthetic_weights(1, seed=1, num_heads=H, joint_dim=joint))
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        ms = [QwenImageTransformer2DModel(num_layers=1, num_attention_heads=H, joint_attention_dim=joint, tp_size=P, tp_rank=r)
+              for r in range(P)]
+    finally:
+        torch.set_default_dtype(torch.float32)
+    ms[0].load_weights(synthetic.split_qkv_checkpoint_names(full.items()))   # q/k/v-separate checkpoint names
+    ms[1].load_weights(full.items())                                         # already stacked names
+    ps_ = [dict(m.named_parameters()) for m in ms]
+    b = "transformer_blocks.0."
+    qf, kf, vf = full[b + "attn.to_qkv.weight"].chunk(3, 0)
+    for r in range(P):
+        sl = slice(r * D // P, (r + 1) * D // P)
+        assert torch.equal(ps_[r][b + "attn.to_qkv.weight"], torch.cat([qf[sl], kf[sl], vf[sl]]))
+        assert ps_[r][b + "attn.to_out.0.bias"].shape == (D,)
+        assert ps_[r][b + "img_mlp.net.2.bias"].shape == (D,)
+    for k, dim in ((b + "attn.to_out.0.weight", 1), (b + "attn.to_add_out.weight", 1), (b + "img_mlp.net.0.proj.weight", 0),
+                   (b + "txt_mlp.net.0.proj.bias", 0), (b + "txt_mlp.net.2.weight", 1)):
+        assert torch.equal(torch.cat([ps_[0][k], ps_[1][k]], dim), full[k]), k
+    assert torch.equal(ps_[0][b + "img_mod.1.weight"], full[b + "img_mod.1.weight"])  # replicated
+    with pytest.raises(ValueError):
+        QwenImageTransformer2DModel(num_layers=1, num_attention_heads=3, joint_attention_dim=64, tp_size=2, tp_rank=0)

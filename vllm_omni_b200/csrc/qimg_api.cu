@@ -452,6 +452,20 @@ int qimg_gate_residual(void* x, const void* y, const void* gate, int rows, int D
   return 0;
 }
 
+int qimg_gate_residual_bias(void* x, const void* y, const void* bias, const void* gate, int rows, int D, int rows_per_batch,
+                            long long gate_stride, qimg_stream_t stream) {
+  if (rows <= 0) return 0;
+  if (D % 8) return fail("qimg_gate_residual_bias: D must be a multiple of 8");
+  const long long n_vec = (long long)rows * (D / 8);
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gate_residual_bias_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)x, (const bf16*)y, (const bf16*)bias,
+                                                                           (const bf16*)gate, n_vec, D, rows_per_batch, gate_stride);
+  QIMG_LAUNCH_CHECK("gate_residual_bias_kernel");
+  return 0;
+}
+
 int qimg_linear_small_m(const void* x, const void* W, const void* bias, void* y, int M, long long N, int K,
                         long long ldy, int act_silu, qimg_stream_t stream) {
   if (M <= 0 || N <= 0) return 0;

@@ -114,6 +114,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully active warp (deterministic for the full mask).  The producer / MMA warps keep their
+// control flow warp-uniform (all 32 lanes wait on barriers and compute descriptors) and wrap only the
+// tcgen05 / TMA issue in `if (elect_one())`: under a divergent `if (lane == 0)` ptxas cannot prove the
+// descriptor operands uniform and emits an ELECT / R2UR / BRA.U.ANY loop around EVERY tcgen05.mma
+// (~18 SASS instructions per MMA; the FMHA's 64-cycle MMAs were issue-bound by it, profiles/r01_fmha_v3).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+
 // ---------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, mbarrier completion
 // ---------------------------------------------------------------------------------------

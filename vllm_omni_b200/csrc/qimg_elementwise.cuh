@@ -220,6 +220,30 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(bf16* __restrict__ x
   }
 }
 
+// Tensor-parallel form: y is the all-reduced partial sum of a row-parallel linear (no bias yet):
+//   x = bf16( x + bf16( gate * bf16(y + bias) ) )
+__global__ void __launch_bounds__(256) gate_residual_bias_kernel(bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                                 const bf16* __restrict__ bias, const bf16* __restrict__ gate,
+                                                                 long long n_vec, int D, int rows_per_batch,
+                                                                 long long gate_stride) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int dv = D >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const long long row = i / dv;
+    const int col = (int)(i - row * dv) << 3;
+    const long long b = row / rows_per_batch;
+    const uint4 xv = ldg_v4(x + i * 8), yv = ldg_nc_v4(y + i * 8);
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate + b * gate_stride + col));
+    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + col));
+    uint4 o;
+    o.x = badd2(xv.x, bmul2(gv.x, badd2(yv.x, bv.x)));
+    o.y = badd2(xv.y, bmul2(gv.y, badd2(yv.y, bv.y)));
+    o.z = badd2(xv.z, bmul2(gv.z, badd2(yv.z, bv.z)));
+    o.w = badd2(xv.w, bmul2(gv.w, badd2(yv.w, bv.w)));
+    stg_v4(x + i * 8, o);
+  }
+}
+
 // Small-M linear ("GEMV"): y[m, n] = bf16( sum_k act(x[m,k]) * W[n,k] + bias[n] ), M <= 8 per pass.
 // HBM-bound on W (read exactly once).  Used for the timestep MLP (qwen_image_transformer.py:50-62),
 // all 2*L modulation projections img_mod/txt_mod (:552-557, batched into ONE launch over the

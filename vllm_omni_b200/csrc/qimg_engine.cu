@@ -19,6 +19,9 @@ struct qimg_engine {
   qimg_dims dims;
   qimg_global_weights g;
   std::vector<qimg_block_weights> blocks;
+  int tp_size = 1;
+  qimg_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
 };
 
 namespace {
@@ -26,12 +29,15 @@ namespace {
 inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t x_img, x_txt, xm_img, xm_txt, q, k, v, at_img, at_txt, h_img, h_txt, txt_normed, tsin, t1, temb, mod_all, emb_out, total;
+  size_t x_img, x_txt, xm_img, xm_txt, q, k, v, at_img, at_txt, h_img, h_txt, txt_normed, tsin, t1, temb, mod_all, emb_out,
+      part, zero_bias, total;
 };
 
-WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max) {
+// tp > 1: head-sharded q/k/v/attention-output and FF-sharded MLP hidden buffers are 1/tp of the full size
+WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max, int tp = 1) {
   const size_t D = (size_t)d.num_heads * d.head_dim, FF = 4 * D, S = (size_t)S_img + T;
   const size_t Mi = (size_t)B * S_img, Mt = (size_t)B * T;
+  const size_t Hl = (size_t)d.num_heads / tp, Dl = D / tp, FFl = FF / tp;
   WsLayout w;
   size_t off = 0;
   auto take = [&](size_t elems) {
@@ -43,19 +49,21 @@ WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max) {
   w.x_txt = take(Mt * D);
   w.xm_img = take(Mi * D);
   w.xm_txt = take(Mt * D);
-  w.q = take((size_t)B * d.num_heads * S * 128);
-  w.k = take((size_t)B * d.num_heads * S * 128);
-  w.v = take((size_t)B * d.num_heads * S * 128);
-  w.at_img = take(Mi * D);
-  w.at_txt = take(Mt * D);
-  w.h_img = take(Mi * FF);
-  w.h_txt = take(Mt * FF);
+  w.q = take((size_t)B * Hl * S * 128);
+  w.k = take((size_t)B * Hl * S * 128);
+  w.v = take((size_t)B * Hl * S * 128);
+  w.at_img = take(Mi * Dl);
+  w.at_txt = take(Mt * Dl);
+  w.h_img = take(Mi * FFl);
+  w.h_txt = take(Mt * FFl);
   w.txt_normed = take(Mt * d.joint_dim);
   w.tsin = take((size_t)n_t_max * 256);
   w.t1 = take((size_t)n_t_max * D);
   w.temb = take((size_t)n_t_max * D);
   w.mod_all = take((size_t)n_t_max * d.num_layers * 12 * D);
   w.emb_out = take((size_t)n_t_max * 2 * D);
+  w.part = take(tp > 1 ? (Mi + Mt) * D : 0);  // [img rows | txt rows] x D partial sums of the row-parallel linears
+  w.zero_bias = take(tp > 1 ? D : 0);
   w.total = off;
   return w;
 }
@@ -81,11 +89,21 @@ int qimg_engine_create(const qimg_dims* dims, const qimg_global_weights* g, cons
 
 void qimg_engine_destroy(qimg_engine* e) { delete e; }
 
-size_t qimg_engine_workspace_bytes(const qimg_engine* e, int B, int S_img, int T) {
-  return ws_layout(e->dims, B, S_img, T, B).total;
+int qimg_engine_set_tp(qimg_engine* e, int tp_size, qimg_allreduce_fn allreduce, void* user) {
+  if (!e) return fail("qimg_engine_set_tp: null engine");
+  if (tp_size < 1 || e->dims.num_heads % tp_size) return fail("qimg_engine_set_tp: tp_size must divide num_heads");
+  if (tp_size > 1 && !allreduce) return fail("qimg_engine_set_tp: an all-reduce callback is required for tp_size > 1");
+  e->tp_size = tp_size;
+  e->allreduce = allreduce;
+  e->allreduce_user = user;
+  return 0;
 }
-size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B).x_img; }
-size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B).x_txt; }
+
+size_t qimg_engine_workspace_bytes(const qimg_engine* e, int B, int S_img, int T) {
+  return ws_layout(e->dims, B, S_img, T, B, e->tp_size).total;
+}
+size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size).x_img; }
+size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size).x_txt; }
 
 #define QIMG_TRY(expr)      \
   do {                      \
@@ -100,11 +118,16 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
   if (B <= 0 || S_img <= 0 || T <= 0) return fail("qimg_engine_forward: bad shape");
   if (n_t != 1 && n_t != B) return fail("qimg_engine_forward: n_t must be 1 or B");
   const qimg_dims& d = e->dims;
-  const WsLayout w = ws_layout(d, B, S_img, T, B);
+  const int tp = e->tp_size;
+  const WsLayout w = ws_layout(d, B, S_img, T, B, tp);
   if (workspace_bytes < w.total) return fail("qimg_engine_forward: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail("qimg_engine_forward: workspace must be 1024-byte aligned");
   char* ws = static_cast<char*>(workspace);
   const int H = d.num_heads, D = H * 128, FF = 4 * D, L = d.num_layers, S = S_img + T;
+  const int Hl = H / tp, Dl = D / tp, FFl = FF / tp;  // local heads / widths under tensor parallelism
+  void *part = ws + w.part, *zero_bias = ws + w.zero_bias;
+  char* part_txt = (char*)part + (size_t)B * S_img * D * 2;
+  if (tp > 1) QIMG_CUDA_CHECK(cudaMemsetAsync(zero_bias, 0, (size_t)D * 2, (cudaStream_t)st));
   const int Mi = B * S_img, Mt = B * T;
   void *x_img = ws + w.x_img, *x_txt = ws + w.x_txt, *xm_img = ws + w.xm_img, *xm_txt = ws + w.xm_txt;
   void *q = ws + w.q, *k = ws + w.k, *v = ws + w.v, *at_img = ws + w.at_img, *at_txt = ws + w.at_txt;
@@ -154,17 +177,17 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
     {
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
-      p[0].A = xm_img; p[0].W = bw.to_qkv_w; p[0].bias = bw.to_qkv_b; p[0].M = Mi; p[0].N = 3 * D; p[0].K = D;
+      p[0].A = xm_img; p[0].W = bw.to_qkv_w; p[0].bias = bw.to_qkv_b; p[0].M = Mi; p[0].N = 3 * Dl; p[0].K = D;
       p[0].rows_per_batch = S_img; p[0].q = q; p[0].k = k; p[0].v = v; p[0].norm_q_w = bw.norm_q; p[0].norm_k_w = bw.norm_k;
-      p[0].rope_cos = img_cos; p[0].rope_sin = img_sin; p[0].S_joint = S; p[0].pos_off = T; p[0].H = H; p[0].eps = d.eps;
+      p[0].rope_cos = img_cos; p[0].rope_sin = img_sin; p[0].S_joint = S; p[0].pos_off = T; p[0].H = Hl; p[0].eps = d.eps;
       p[1] = p[0];
       p[1].A = xm_txt; p[1].W = bw.add_kv_w; p[1].bias = bw.add_kv_b; p[1].M = Mt; p[1].rows_per_batch = T;
       p[1].norm_q_w = bw.norm_added_q; p[1].norm_k_w = bw.norm_added_k; p[1].rope_cos = txt_cos; p[1].rope_sin = txt_sin;
       p[1].pos_off = 0;
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_QKV, st));
     }
-    QIMG_TRY(qimg_fmha_joint(q, k, v, at_txt, at_img, B, H, S, T, sm_scale, st));
-    {
+    QIMG_TRY(qimg_fmha_joint(q, k, v, at_txt, at_img, B, Hl, S, T, sm_scale, st));
+    if (tp == 1) {
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
       p[0].A = at_img; p[0].W = bw.to_out_w; p[0].bias = bw.to_out_b; p[0].M = Mi; p[0].N = D; p[0].K = D;
@@ -173,19 +196,31 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
       p[1].A = at_txt; p[1].W = bw.to_add_out_w; p[1].bias = bw.to_add_out_b; p[1].M = Mt; p[1].rows_per_batch = T;
       p[1].out = x_txt; p[1].gate = seg(mt, 2);
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS_GATE_RES, st));
+    } else {
+      // row-parallel out-projection: partial sums over the local heads -> all-reduce -> bias + gate + residual
+      qimg_gemm_problem p[2];
+      memset(p, 0, sizeof p);
+      p[0].A = at_img; p[0].W = bw.to_out_w; p[0].bias = zero_bias; p[0].M = Mi; p[0].N = D; p[0].K = Dl;
+      p[0].rows_per_batch = S_img; p[0].out = part; p[0].ldo = D;
+      p[1] = p[0];
+      p[1].A = at_txt; p[1].W = bw.to_add_out_w; p[1].M = Mt; p[1].rows_per_batch = T; p[1].out = part_txt;
+      QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS, st));
+      if (e->allreduce(part, (long long)(Mi + Mt) * D, e->allreduce_user, st)) return fail("TP all-reduce callback failed");
+      QIMG_TRY(qimg_gate_residual_bias(x_img, part, bw.to_out_b, seg(mi, 2), Mi, D, S_img, mod_stride, st));
+      QIMG_TRY(qimg_gate_residual_bias(x_txt, part_txt, bw.to_add_out_b, seg(mt, 2), Mt, D, T, mod_stride, st));
     }
     QIMG_TRY(qimg_ln_modulate(x_img, seg(mi, 3), seg(mi, 4), xm_img, Mi, D, S_img, mod_stride, d.eps, st));
     QIMG_TRY(qimg_ln_modulate(x_txt, seg(mt, 3), seg(mt, 4), xm_txt, Mt, D, T, mod_stride, d.eps, st));
     {
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
-      p[0].A = xm_img; p[0].W = bw.img_mlp_w1; p[0].bias = bw.img_mlp_b1; p[0].M = Mi; p[0].N = FF; p[0].K = D;
-      p[0].rows_per_batch = S_img; p[0].out = h_img; p[0].ldo = FF;
+      p[0].A = xm_img; p[0].W = bw.img_mlp_w1; p[0].bias = bw.img_mlp_b1; p[0].M = Mi; p[0].N = FFl; p[0].K = D;
+      p[0].rows_per_batch = S_img; p[0].out = h_img; p[0].ldo = FFl;
       p[1] = p[0];
       p[1].A = xm_txt; p[1].W = bw.txt_mlp_w1; p[1].bias = bw.txt_mlp_b1; p[1].M = Mt; p[1].rows_per_batch = T; p[1].out = h_txt;
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS_GELU, st));
     }
-    {
+    if (tp == 1) {
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
       p[0].A = h_img; p[0].W = bw.img_mlp_w2; p[0].bias = bw.img_mlp_b2; p[0].M = Mi; p[0].N = D; p[0].K = FF;
@@ -194,6 +229,17 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
       p[1].A = h_txt; p[1].W = bw.txt_mlp_w2; p[1].bias = bw.txt_mlp_b2; p[1].M = Mt; p[1].rows_per_batch = T;
       p[1].out = x_txt; p[1].gate = seg(mt, 5);
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS_GATE_RES, st));
+    } else {
+      qimg_gemm_problem p[2];
+      memset(p, 0, sizeof p);
+      p[0].A = h_img; p[0].W = bw.img_mlp_w2; p[0].bias = zero_bias; p[0].M = Mi; p[0].N = D; p[0].K = FFl;
+      p[0].rows_per_batch = S_img; p[0].out = part; p[0].ldo = D;
+      p[1] = p[0];
+      p[1].A = h_txt; p[1].W = bw.txt_mlp_w2; p[1].M = Mt; p[1].rows_per_batch = T; p[1].out = part_txt;
+      QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS, st));
+      if (e->allreduce(part, (long long)(Mi + Mt) * D, e->allreduce_user, st)) return fail("TP all-reduce callback failed");
+      QIMG_TRY(qimg_gate_residual_bias(x_img, part, bw.img_mlp_b2, seg(mi, 5), Mi, D, S_img, mod_stride, st));
+      QIMG_TRY(qimg_gate_residual_bias(x_txt, part_txt, bw.txt_mlp_b2, seg(mt, 5), Mt, D, T, mod_stride, st));
     }
   }
 

@@ -152,78 +152,96 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * FMHA_TILE_BYTES);
       for (int t = 0; t < 2; ++t)
         for (int s = 0; s < 2; ++s)
           tma_load_3d(sQ + t * FMHA_TILE_BYTES + s * 16384, &tmQ, q_full, s * 64, q_row0 + t * 128, bh);
-      for (int j = 0; j < n_kv; ++j) {
-        const int ks = j % FMHA_KS, vs = j % FMHA_VS;
-        mbar_wait(&k_empty[ks], ((j / FMHA_KS) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int ks = j % FMHA_KS, vs = j % FMHA_VS;
+      mbar_wait(&k_empty[ks], ((j / FMHA_KS) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[ks], FMHA_TILE_BYTES);
         for (int s = 0; s < 2; ++s)
           tma_load_3d(sK + ks * FMHA_TILE_BYTES + s * 16384, &tmK, &k_full[ks], s * 64, j * 128, bh);
-        mbar_wait(&v_empty[vs], ((j / FMHA_VS) & 1) ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[vs], ((j / FMHA_VS) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[vs], FMHA_TILE_BYTES);
         for (int s = 0; s < 2; ++s)
           tma_load_3d(sV + vs * FMHA_TILE_BYTES + s * 16384, &tmV, &v_full[vs], s * 64, j * 128, bh);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
-      const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
-      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
-      auto issue_qk = [&](int t, int ks) {
-        const uint32_t qa = smem_u32(sQ + t * FMHA_TILE_BYTES);
-        const uint32_t ka = smem_u32(sK + ks * FMHA_TILE_BYTES);
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
+    const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
+    const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+    auto issue_qk = [&](int t, int ks) {
+      const uint32_t qa = smem_u32(sQ + t * FMHA_TILE_BYTES);
+      const uint32_t ka = smem_u32(sK + ks * FMHA_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(tS[t], make_kmajor_sw128_desc(qa + off), make_kmajor_sw128_desc(ka + off), IDESC_QK, k != 0);
-        }
-      };
-      auto issue_pv = [&](int t, int vs, bool accumulate) {
-        const uint32_t va = smem_u32(sV + vs * FMHA_TILE_BYTES);
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+        umma_ss(tS[t], make_kmajor_sw128_desc(qa + off), make_kmajor_sw128_desc(ka + off), IDESC_QK, k != 0);
+      }
+    };
+    auto issue_pv = [&](int t, int vs, bool accumulate) {
+      const uint32_t va = smem_u32(sV + vs * FMHA_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // A = P (bf16 pairs, 8 TMEM columns per K=16 step); B = V rows [16k, 16k+16) x 128 (MN-major)
-          umma_ts(tO[t], tS[t] + k * 8, make_mnmajor_sw128_desc(va + k * 2048, 16384), IDESC_PV,
-                  (accumulate || k != 0) ? 1u : 0u);
-        }
-      };
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int ks = j % FMHA_KS;
-        mbar_wait(&k_full[ks], (j / FMHA_KS) & 1);
-        tc_fence_after();
+      for (int k = 0; k < 8; ++k) {
+        // A = P (bf16 pairs, 8 TMEM columns per K=16 step); B = V rows [16k, 16k+16) x 128 (MN-major)
+        umma_ts(tO[t], tS[t] + k * 8, make_mnmajor_sw128_desc(va + k * 2048, 16384), IDESC_PV,
+                (accumulate || k != 0) ? 1u : 0u);
+      }
+    };
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int ks = j % FMHA_KS;
+      mbar_wait(&k_full[ks], (j / FMHA_KS) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         issue_qk(0, ks);
         umma_commit(&s_full[0]);
-        if (j > 0) {
-          mbar_wait(&p_ready[1], (j - 1) & 1);
-          tc_fence_after();
+      }
+      __syncwarp();
+      if (j > 0) {
+        mbar_wait(&p_ready[1], (j - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
           issue_pv(1, (j - 1) % FMHA_VS, j - 1 > 0);
           umma_commit(&v_empty[(j - 1) % FMHA_VS]);
         }
+        __syncwarp();
+      }
+      if (elect_one()) {
         issue_qk(1, ks);
         umma_commit(&s_full[1]);
         umma_commit(&k_empty[ks]);
-        const int vs = j % FMHA_VS;
-        mbar_wait(&v_full[vs], (j / FMHA_VS) & 1);
-        mbar_wait(&p_ready[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, vs, j > 0);
       }
-      mbar_wait(&p_ready[1], (n_kv - 1) & 1);
+      __syncwarp();
+      const int vs = j % FMHA_VS;
+      mbar_wait(&v_full[vs], (j / FMHA_VS) & 1);
+      mbar_wait(&p_ready[0], j & 1);
       tc_fence_after();
+      if (elect_one()) issue_pv(0, vs, j > 0);
+      __syncwarp();
+    }
+    mbar_wait(&p_ready[1], (n_kv - 1) & 1);
+    tc_fence_after();
+    if (elect_one()) {
       issue_pv(1, (n_kv - 1) % FMHA_VS, n_kv - 1 > 0);
       umma_commit(&v_empty[(n_kv - 1) % FMHA_VS]);
       umma_commit(&o_full[0]);
       umma_commit(&o_full[1]);
     }
+    __syncwarp();
   } else {
     // ===================== softmax / correction / output warps =====================
     const int t = (warp - 2) >> 2;  // query tile handled by this warpgroup

@@ -84,85 +84,96 @@ fmha_joint_kernel_v5(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * FMHA2_Q_BYTES);
       for (int t = 0; t < 2; ++t)
         for (int s = 0; s < 2; ++s)
           tma_load_3d(sQ + t * FMHA2_Q_BYTES + s * 16384, &tmQ, q_full, s * 64, q_row0 + t * 128, bh);
-      for (int j = 0; j < n_kv; ++j) {
-        const int ks = j % FMHA2_KS, vs = j % FMHA2_VS;
-        mbar_wait(&k_empty[ks], ((j / FMHA2_KS) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int ks = j % FMHA2_KS, vs = j % FMHA2_VS;
+      mbar_wait(&k_empty[ks], ((j / FMHA2_KS) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[ks], FMHA2_KV_BYTES);
         for (int s = 0; s < 2; ++s)
           tma_load_3d(sK + ks * FMHA2_KV_BYTES + s * 8192, &tmK, &k_full[ks], s * 64, j * FMHA2_KV, bh);
-        mbar_wait(&v_empty[vs], ((j / FMHA2_VS) & 1) ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[vs], ((j / FMHA2_VS) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[vs], FMHA2_KV_BYTES);
         for (int s = 0; s < 2; ++s)
           tma_load_3d(sV + vs * FMHA2_KV_BYTES + s * 8192, &tmV, &v_full[vs], s * 64, j * FMHA2_KV, bh);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_QK = make_idesc_bf16(128, FMHA2_KV, 0, 0);
-      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
-      auto issue_qk = [&](int t, int b, int ks) {
-        const uint32_t qa = smem_u32(sQ + t * FMHA2_Q_BYTES);
-        const uint32_t ka = smem_u32(sK + ks * FMHA2_KV_BYTES);
-        const uint32_t d = tmem_base + (2 * t + b) * 64;
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    constexpr uint32_t IDESC_QK = make_idesc_bf16(128, FMHA2_KV, 0, 0);
+    constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
+    auto issue_qk = [&](int t, int b, int ks) {
+      const uint32_t qa = smem_u32(sQ + t * FMHA2_Q_BYTES);
+      const uint32_t ka = smem_u32(sK + ks * FMHA2_KV_BYTES);
+      const uint32_t d = tmem_base + (2 * t + b) * 64;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          umma_ss(d, make_kmajor_sw128_desc(qa + (k >> 2) * 16384 + (k & 3) * 32),
-                  make_kmajor_sw128_desc(ka + (k >> 2) * 8192 + (k & 3) * 32), IDESC_QK, k != 0);
-        }
-      };
-      auto issue_pv = [&](int t, int b, int vs, bool accumulate) {
-        const uint32_t va = smem_u32(sV + vs * FMHA2_KV_BYTES);
-        const uint32_t d = tmem_base + 256 + t * 128;
-        const uint32_t p = tmem_base + (2 * t + b) * 64;
+      for (int k = 0; k < 8; ++k) {
+        umma_ss(d, make_kmajor_sw128_desc(qa + (k >> 2) * 16384 + (k & 3) * 32),
+                make_kmajor_sw128_desc(ka + (k >> 2) * 8192 + (k & 3) * 32), IDESC_QK, k != 0);
+      }
+    };
+    auto issue_pv = [&](int t, int b, int vs, bool accumulate) {
+      const uint32_t va = smem_u32(sV + vs * FMHA2_KV_BYTES);
+      const uint32_t d = tmem_base + 256 + t * 128;
+      const uint32_t p = tmem_base + (2 * t + b) * 64;
 #pragma unroll
-        for (int k = 0; k < FMHA2_KV / 16; ++k) {
-          // A = P (bf16 pairs, 8 TMEM columns per K=16 step); B = V rows [16k,16k+16) x 128 (MN-major, slabs 8 KB apart)
-          umma_ts(d, p + k * 8, make_mnmajor_sw128_desc(va + k * 2048, 8192), IDESC_PV, (accumulate || k != 0) ? 1u : 0u);
-        }
-      };
-      mbar_wait(q_full, 0);
-      // prologue: scores of the first two KV tiles for both query tiles
-      for (int jj = 0; jj < 2 && jj < n_kv; ++jj) {
-        const int ks = jj % FMHA2_KS;
-        mbar_wait(&k_full[ks], (jj / FMHA2_KS) & 1);
-        tc_fence_after();
+      for (int k = 0; k < FMHA2_KV / 16; ++k) {
+        // A = P (bf16 pairs, 8 TMEM columns per K=16 step); B = V rows [16k,16k+16) x 128 (MN-major, slabs 8 KB apart)
+        umma_ts(d, p + k * 8, make_mnmajor_sw128_desc(va + k * 2048, 8192), IDESC_PV, (accumulate || k != 0) ? 1u : 0u);
+      }
+    };
+    mbar_wait(q_full, 0);
+    // prologue: scores of the first two KV tiles for both query tiles
+    for (int jj = 0; jj < 2 && jj < n_kv; ++jj) {
+      const int ks = jj % FMHA2_KS;
+      mbar_wait(&k_full[ks], (jj / FMHA2_KS) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         for (int t = 0; t < 2; ++t) {
           issue_qk(t, jj & 1, ks);
           umma_commit(&s_full[2 * t + (jj & 1)]);
         }
         umma_commit(&k_empty[ks]);
       }
-      for (int j = 0; j < n_kv; ++j) {
-        const int b = j & 1, vs = j % FMHA2_VS;
-        const int jn = j + 2, ksn = jn % FMHA2_KS;
-        mbar_wait(&v_full[vs], (j / FMHA2_VS) & 1);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_ready[2 * t + b], (j >> 1) & 1);
-          tc_fence_after();
+      __syncwarp();
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int b = j & 1, vs = j % FMHA2_VS;
+      const int jn = j + 2, ksn = jn % FMHA2_KS;
+      mbar_wait(&v_full[vs], (j / FMHA2_VS) & 1);
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_ready[2 * t + b], (j >> 1) & 1);
+        if (jn < n_kv && t == 0) mbar_wait(&k_full[ksn], (jn / FMHA2_KS) & 1);
+        tc_fence_after();
+        if (elect_one()) {
           issue_pv(t, b, vs, j > 0);
           umma_commit(&pv_done[t]);
           if (jn < n_kv) {
-            if (t == 0) {
-              mbar_wait(&k_full[ksn], (jn / FMHA2_KS) & 1);
-              tc_fence_after();
-            }
             issue_qk(t, b, ksn);  // reuses S[t][b]: P(j) was consumed by the PV issued just above (in-order pipe)
             umma_commit(&s_full[2 * t + b]);
             if (t == 1) umma_commit(&k_empty[ksn]);
           }
+          if (t == 1) umma_commit(&v_empty[vs]);
         }
-        umma_commit(&v_empty[vs]);
+        __syncwarp();
       }
+    }
+    if (elect_one()) {
       umma_commit(&o_full[0]);
       umma_commit(&o_full[1]);
     }
+    __syncwarp();
   } else {
     // ===================== softmax / correction / output warps =====================
     const int t = (warp - 2) >> 2;  // query tile handled by this warpgroup

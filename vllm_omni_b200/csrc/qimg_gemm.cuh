@@ -327,47 +327,48 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-        TileCoord tc = decode_tile(prm, tile);
-        const GemmProblem& P = prm.p[tc.pi];
-        const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
-        const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
-        const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      TileCoord tc = decode_tile(prm, tile);
+      const GemmProblem& P = prm.p[tc.pi];
+      const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
+      const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
+      const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(sa, ta, &full_bar[stage], kb * GEMM_BK, tc.m_blk * GEMM_BM);
           tma_load_2d(sb, tb, &full_bar[stage], kb * GEMM_BK, tc.n_blk * BN);
-          if (++stage == GEMM_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == GEMM_STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-        TileCoord tc = decode_tile(prm, tile);
-        const GemmProblem& P = prm.p[tc.pi];
-        const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      TileCoord tc = decode_tile(prm, tile);
+      const GemmProblem& P = prm.p[tc.pi];
+      const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
           const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
@@ -376,17 +377,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // +32 B per K=16 step inside the 128 B swizzle row (descriptor start field is >>4)
             umma_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs complete
-          if (++stage == GEMM_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          umma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs complete
+          if (kb == kblocks - 1) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
         }
-        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == GEMM_STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {

@@ -121,35 +121,36 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; completion lands on the leader's full barrier) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < prm.total_tiles; tile += num_clusters) {
-        TileCoord tc = decode_tile(prm, tile, GEMM2_GROUP_M);
-        const GemmProblem& P = prm.p[tc.pi];
-        const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
-        const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
-        const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
-        const int m_row = (tc.m_blk * 2 + (int)rank) * 128;
-        const int n_row = tc.n_blk * BN + (int)rank * 128;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < prm.total_tiles; tile += num_clusters) {
+      TileCoord tc = decode_tile(prm, tile, GEMM2_GROUP_M);
+      const GemmProblem& P = prm.p[tc.pi];
+      const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
+      const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
+      const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
+      const int m_row = (tc.m_blk * 2 + (int)rank) * 128;
+      const int n_row = tc.n_blk * BN + (int)rank * 128;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * GEMM2_STAGE_BYTES);
           const uint32_t sb = sa + GEMM2_A_BYTES;
           const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * GEMM2_STAGE_BYTES);
           tma_load_2d_cg2(sa, ta, leader_full, kb * GEMM_BK, m_row);
           tma_load_2d_cg2(sb, tb, leader_full, kb * GEMM_BK, n_row);
-          if (++stage == GEMM2_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == GEMM2_STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0 && lane == 0) {
+    // ===================== MMA issuer (leader CTA only; warp-uniform control flow, one elected lane issues) =====================
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -164,19 +165,22 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * GEMM2_STAGE_BYTES);
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + GEMM2_A_BYTES);
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * GEMM2_STAGE_BYTES);
+            const uint64_t adesc = make_kmajor_sw128_desc(sa);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sa + GEMM2_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_ss_cg2(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) != 0);
-          umma_commit_cg2_mc(&empty_bar[stage]);
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_ss_cg2(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) != 0);
+            umma_commit_cg2_mc(&empty_bar[stage]);
+            if (kb == kblocks - 1) umma_commit_cg2_mc(&tmem_full[acc]);
+          }
+          __syncwarp();
           if (++stage == GEMM2_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_cg2_mc(&tmem_full[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

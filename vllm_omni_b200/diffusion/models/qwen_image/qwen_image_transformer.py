@@ -88,26 +88,29 @@ class _GELUProj(nn.Module):
 
 
 class _FeedForward(nn.Module):
-    """diffusers FeedForward parameter layout: net.0.proj, net.2 (qwen_image_transformer.py:491,501)."""
+    """diffusers FeedForward parameter layout: net.0.proj, net.2 (qwen_image_transformer.py:491,501).
+    Under tensor parallelism net.0.proj holds FF/P rows (column-parallel) and net.2 FF/P input columns
+    (row-parallel; its bias is kept whole and applied after the all-reduce)."""
 
-    def __init__(self, dim: int):
+    def __init__(self, dim: int, tp: int = 1):
         super().__init__()
-        self.net = nn.ModuleList([_GELUProj(dim, 4 * dim), nn.Identity(), _Linear(4 * dim, dim)])
+        self.net = nn.ModuleList([_GELUProj(dim, 4 * dim // tp), nn.Identity(), _Linear(4 * dim // tp, dim)])
 
 
 class _Attn(nn.Module):
     """QwenImageCrossAttention parameter layout (:288-368)."""
 
-    def __init__(self, dim: int, head_dim: int, eps: float):
+    def __init__(self, dim: int, head_dim: int, eps: float, tp: int = 1):
         super().__init__()
-        self.to_qkv = _Linear(dim, 3 * dim)
-        self.add_kv_proj = _Linear(dim, 3 * dim)
+        # TP: q|k|v rows of the local heads (column-parallel); out-projections take the local heads' columns
+        self.to_qkv = _Linear(dim, 3 * dim // tp)
+        self.add_kv_proj = _Linear(dim, 3 * dim // tp)
         self.norm_q = _RMSNormWeight(head_dim, eps)
         self.norm_k = _RMSNormWeight(head_dim, eps)
         self.norm_added_q = _RMSNormWeight(head_dim, eps)
         self.norm_added_k = _RMSNormWeight(head_dim, eps)
-        self.to_out = nn.ModuleList([_Linear(dim, dim)])
-        self.to_add_out = _Linear(dim, dim)
+        self.to_out = nn.ModuleList([_Linear(dim // tp, dim)])
+        self.to_add_out = _Linear(dim // tp, dim)
 
 
 class _AdaLNHolder(nn.Module):
@@ -122,7 +125,7 @@ class QwenImageTransformerBlock(nn.Module):
     """Parameter holder with the reference block's sub-module names (:461-505)."""
 
     def __init__(self, dim: int, num_attention_heads: int, attention_head_dim: int, eps: float,
-                 mod_w: torch.Tensor, mod_b: torch.Tensor):
+                 mod_w: torch.Tensor, mod_b: torch.Tensor, tp: int = 1):
         super().__init__()
         self.dim = dim
         self.num_attention_heads = num_attention_heads
@@ -135,9 +138,9 @@ class QwenImageTransformerBlock(nn.Module):
         self.img_norm2 = _AdaLNHolder(dim, eps)
         self.txt_norm1 = _AdaLNHolder(dim, eps)
         self.txt_norm2 = _AdaLNHolder(dim, eps)
-        self.attn = _Attn(dim, attention_head_dim, eps)
-        self.img_mlp = _FeedForward(dim)
-        self.txt_mlp = _FeedForward(dim)
+        self.attn = _Attn(dim, attention_head_dim, eps, tp)
+        self.img_mlp = _FeedForward(dim, tp)
+        self.txt_mlp = _FeedForward(dim, tp)
 
 
 class QwenEmbedRope(nn.Module):
@@ -224,6 +227,9 @@ class QwenImageTransformer2DModel(nn.Module):
         zero_cond_t: bool = False,
         use_additional_t_cond: bool = False,
         use_layer3d_rope: bool = False,
+        tp_size: int | None = None,
+        tp_rank: int | None = None,
+        tp_group=None,
     ):
         super().__init__()
         if od_config is not None and getattr(od_config, "tf_model_config", None) is not None:
@@ -234,6 +240,15 @@ class QwenImageTransformer2DModel(nn.Module):
         if attention_head_dim != 128:
             raise ValueError("the sm_100a kernels are specialised for head_dim 128 (Qwen-Image)")
         self.parallel_config = getattr(od_config, "parallel_config", None)
+        # tensor parallelism over heads / FFN (new; the reference builds these linears with disable_tp=True)
+        if tp_size is None:
+            tp_size = getattr(self.parallel_config, "tensor_parallel_size", 1) if self.parallel_config is not None else 1
+        if tp_size > 1 and tp_rank is None:
+            from vllm_omni_b200.diffusion.distributed import parallel_state as _ps
+            tp_rank, tp_group = _ps.get_tensor_model_parallel_rank(), _ps.get_tp_group()
+        self.tp_size, self.tp_rank, self.tp_group = int(tp_size), int(tp_rank or 0), tp_group
+        if num_attention_heads % self.tp_size:
+            raise ValueError(f"tensor_parallel_size {self.tp_size} must divide num_attention_heads {num_attention_heads}")
         self.in_channels = in_channels
         self.out_channels = out_channels or in_channels
         self.inner_dim = num_attention_heads * attention_head_dim
@@ -255,7 +270,8 @@ class QwenImageTransformer2DModel(nn.Module):
         self._mod_all_w = torch.empty(num_layers, 2, 6 * D, D)
         self._mod_all_b = torch.empty(num_layers, 2, 6 * D)
         self.transformer_blocks = nn.ModuleList(
-            [QwenImageTransformerBlock(D, num_attention_heads, attention_head_dim, self.eps, self._mod_all_w[i], self._mod_all_b[i])
+            [QwenImageTransformerBlock(D, num_attention_heads, attention_head_dim, self.eps, self._mod_all_w[i], self._mod_all_b[i],
+                                       self.tp_size)
              for i in range(num_layers)])
         self.norm_out = _NormOut(D)
         self.proj_out = _Linear(D, patch_size * patch_size * self.out_channels)
@@ -276,6 +292,16 @@ class QwenImageTransformer2DModel(nn.Module):
         ]
         params = dict(self.named_parameters())
         loaded: set[str] = set()
+        P, r = self.tp_size, self.tp_rank
+
+        def rows(t):  # this rank's slice of an output-feature (column-parallel) dimension
+            n = t.shape[0] // P
+            return t[r * n:(r + 1) * n]
+
+        def cols(t):  # this rank's slice of an input-feature (row-parallel) dimension
+            n = t.shape[1] // P
+            return t[:, r * n:(r + 1) * n]
+
         for name, w in weights:
             for param_name, weight_name, shard in stacked:
                 if weight_name not in name:
@@ -283,10 +309,17 @@ class QwenImageTransformer2DModel(nn.Module):
                 name = name.replace(weight_name, param_name)
                 p = params[name]
                 n = p.shape[0] // 3
-                p.data[shard * n:(shard + 1) * n].copy_(w.to(p.dtype))
+                p.data[shard * n:(shard + 1) * n].copy_(rows(w).to(p.dtype))  # local heads of q / k / v
                 break
             else:
                 p = params[name]
+                if P > 1:
+                    if ".attn.to_qkv." in name or ".attn.add_kv_proj." in name:   # already stacked [q;k;v]
+                        w = torch.cat([rows(c) for c in w.chunk(3, dim=0)], dim=0)
+                    elif name.endswith(".net.0.proj.weight") or name.endswith(".net.0.proj.bias"):
+                        w = rows(w)
+                    elif name.endswith(("attn.to_out.0.weight", "attn.to_add_out.weight", ".net.2.weight")):
+                        w = cols(w)
                 if tuple(p.shape) != tuple(w.shape):
                     raise ValueError(f"shape mismatch for {name}: {tuple(p.shape)} vs {tuple(w.shape)}")
                 p.data.copy_(w.to(p.dtype))
@@ -353,6 +386,21 @@ class QwenImageTransformer2DModel(nn.Module):
         qlib.check(qlib.load().qimg_engine_create(C.byref(dims), C.byref(g), blocks, C.byref(handle)), "qimg_engine_create")
         self._engine = handle
         self._engine_keepalive = (dims, g, blocks)
+        if self.tp_size > 1:
+            import torch.distributed as dist
+
+            def _allreduce(buf, count, user, stream):  # called by the engine twice per block, on its stream
+                try:
+                    ws, off, _ = self._ws_current
+                    o = buf - ws.data_ptr()
+                    dist.all_reduce(ws[o:o + count * 2].view(torch.bfloat16), group=self.tp_group)
+                    return 0
+                except Exception as exc:  # surfaces as "TP all-reduce callback failed"
+                    self._tp_error = exc
+                    return 1
+
+            self._allreduce_cb = qlib.ALLREDUCE_FN(_allreduce)
+            qlib.check(qlib.load().qimg_engine_set_tp(self._engine, self.tp_size, self._allreduce_cb, None), "qimg_engine_set_tp")
 
     def __del__(self):
         try:
@@ -416,6 +464,7 @@ class QwenImageTransformer2DModel(nn.Module):
         if s_expected != S_img:
             raise ValueError(f"img_shapes implies {s_expected} image tokens, hidden_states has {S_img}")
         buf, off, nbytes = self._workspace(B, S_img, T, dev)
+        self._ws_current = (buf, off, nbytes)
         out = torch.empty((B, S_img, self.proj_out.out_features), dtype=torch.bfloat16, device=dev)
         rc = qlib.load().qimg_engine_forward(
             self._engine, hs.data_ptr(), enc.data_ptr(), ts.data_ptr(), n_t, ic.data_ptr(), isn.data_ptr(), tc.data_ptr(),

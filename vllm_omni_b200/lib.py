@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "qimg_ln_modulate", "qimg_gate_residual", "qimg_rms_norm", "qimg_linear_small_m", "qimg_timestep_sinusoid",
     "qimg_cfg_euler_step", "qimg_gemm", "qimg_fmha_joint", "qimg_engine_create", "qimg_engine_destroy",
     "qimg_engine_workspace_bytes", "qimg_engine_forward", "qimg_engine_ws_offset_img", "qimg_engine_ws_offset_txt",
-    "qimg_umma_probe", "qimg_prof_enable", "qimg_prof_collect", "qimg_set_gemm_mode", "qimg_get_gemm_mode", "qimg_set_fmha_mode", "qimg_get_fmha_mode",
+    "qimg_umma_probe", "qimg_prof_enable", "qimg_prof_collect", "qimg_set_gemm_mode", "qimg_get_gemm_mode", "qimg_set_fmha_mode", "qimg_get_fmha_mode", "qimg_gate_residual_bias", "qimg_engine_set_tp",
 ]
 
 
@@ -52,6 +52,10 @@ GLOBAL_FIELDS = [
     "t_lin1_w", "t_lin1_b", "t_lin2_w", "t_lin2_b", "txt_norm_w", "img_in_w", "img_in_b", "txt_in_w", "txt_in_b",
     "norm_out_w", "norm_out_b", "proj_out_w", "proj_out_b", "mod_all_w", "mod_all_b",
 ]
+
+
+# int (*qimg_allreduce_fn)(void* buf, long long count, void* user, qimg_stream_t stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p)
 
 
 class BlockWeights(C.Structure):
@@ -84,6 +88,8 @@ def load():
     lib.qimg_ln_modulate.argtypes = [vp, vp, vp, vp, i, i, i, ll, f, vp]
     lib.qimg_gate_residual.argtypes = [vp, vp, vp, i, i, i, ll, vp]
     lib.qimg_rms_norm.argtypes = [vp, vp, vp, i, i, f, vp]
+    lib.qimg_gate_residual_bias.argtypes = [vp, vp, vp, vp, i, i, i, ll, vp]
+    lib.qimg_engine_set_tp.argtypes = [vp, i, ALLREDUCE_FN, vp]
     lib.qimg_linear_small_m.argtypes = [vp, vp, vp, vp, i, ll, i, ll, i, vp]
     lib.qimg_timestep_sinusoid.argtypes = [vp, vp, i, vp]
     lib.qimg_cfg_euler_step.argtypes = [vp, vp, vp, ll, i, f, f, f, vp]
