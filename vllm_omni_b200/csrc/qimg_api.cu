@@ -524,27 +524,37 @@ static int fmha_mode() {
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode != 0 && mode != 1) return fail("qimg_set_fmha_mode: mode must be 0 or 1");
+  if (mode < 0 || mode > 7) return fail("qimg_set_fmha_mode: mode must be in [0, 7]");
   g_fmha_mode = mode;
   return 0;
 }
 int qimg_get_fmha_mode(void) { return fmha_mode(); }
 
+template <uint32_t MASK>
+static int launch_fmha_inst(bool v5, dim3 grid, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
+                            const FmhaParams& prm, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
+    attr_set = true;
+  }
+  if (v5) fmha_joint_kernel_v5<MASK><<<grid, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else fmha_joint_kernel<MASK><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  QIMG_LAUNCH_CHECK("fmha_joint_kernel");
+  return 0;
+}
+
 int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
                     int T, float softmax_scale, qimg_stream_t stream) {
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
-  const bool v5 = fmha_mode() == 1;
+  const int mode = fmha_mode();
+  const bool v5 = (mode & 1) != 0;
   const uint32_t kv_rows = v5 ? FMHA2_KV : 128;
   const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
   const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
   const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
   if (!tq || !tk || !tv) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
-    attr_set = true;
-  }
   FmhaParams prm;
   prm.out_txt = (bf16*)out_txt;
   prm.out_img = (bf16*)out_img;
@@ -552,10 +562,13 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
   dim3 grid((S + 255) / 256, B * H);
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
-  if (v5) fmha_joint_kernel_v5<<<grid, FMHA_THREADS, FMHA2_SMEM_BYTES, (cudaStream_t)stream>>>(*tq, *tk, *tv, prm);
-  else fmha_joint_kernel<<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, (cudaStream_t)stream>>>(*tq, *tk, *tv, prm);
-  QIMG_LAUNCH_CHECK("fmha_joint_kernel");
-  return 0;
+  // bits 1-2 of the mode: share of the exponentials computed by the FMA-pipe polynomial (0, 25, 37.5, 50 %)
+  switch ((mode >> 1) & 3) {
+    case 0: return launch_fmha_inst<0x00u>(v5, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+    case 1: return launch_fmha_inst<0x11u>(v5, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+    case 2: return launch_fmha_inst<0x52u>(v5, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+    default: return launch_fmha_inst<0x55u>(v5, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+  }
 }
 
 int qimg_umma_probe(const void* A, const void* B, float* D, int N, int K, int mode, qimg_stream_t stream) {

@@ -100,6 +100,7 @@ __device__ __forceinline__ uint64_t exp2_poly_f32x2(uint64_t x) {
 #define FMHA_POLY_MASK 0x00u  // bit k set => pair (k mod 8) of every 8 pairs uses the FMA-pipe polynomial
 #endif
 
+template <uint32_t POLY_MASK>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
@@ -313,7 +314,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const int k = cc * 16 + i;  // pair index 0..63
             const uint64_t x = fma_f32x2(pack_f32x2(r[2 * k], r[2 * k + 1]), c2, nmc2);
             uint64_t p;
-            if ((FMHA_POLY_MASK >> (k & 7)) & 1u) {
+            if ((POLY_MASK >> (k & 7)) & 1u) {
               p = exp2_poly_f32x2(x);
             } else {
               uint32_t xl, xh;

@@ -28,6 +28,7 @@ constexpr int FMHA2_SMEM_BYTES = 2 * FMHA2_Q_BYTES + (FMHA2_KS + FMHA2_VS) * FMH
 #define FMHA2_POLY_MASK 0x11u  // pairs {0,4} of every 8 -> 25 % of the exponentials on the FMA pipe
 #endif
 
+template <uint32_t POLY_MASK>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_joint_kernel_v5(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
@@ -242,7 +243,7 @@ fmha_joint_kernel_v5(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int k = 0; k < 32; ++k) {  // pair index
           const uint64_t x = fma_f32x2(pack_f32x2(r[2 * k], r[2 * k + 1]), c2, nmc2);
           uint64_t p;
-          if ((FMHA2_POLY_MASK >> (k & 7)) & 1u) {
+          if ((POLY_MASK >> (k & 7)) & 1u) {
             p = exp2_poly_f32x2(x);
           } else {
             uint32_t xl, xh;
