@@ -52,7 +52,7 @@ def test_library_loaded_and_device():
     assert os.path.exists(q.LIB_PATH)
 
 
-@pytest.fixture(params=[0, 1, 4, 3], ids=["kv128", "kv64dbuf", "kv128-poly37", "kv64dbuf-poly25"])
+@pytest.fixture(params=[0, 1, 4, 3, 12], ids=["kv128", "kv64dbuf", "kv128-poly37", "kv64dbuf-poly25", "kv128-poly37-pingpong"])
 def fmha_mode(request):
     """Both attention pipelines (first-generation 128-row KV tiles / double-buffered 64-row KV tiles)."""
     prev = q.get_fmha_mode()

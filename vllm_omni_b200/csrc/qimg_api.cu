@@ -524,23 +524,25 @@ static int fmha_mode() {
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode < 0 || mode > 7) return fail("qimg_set_fmha_mode: mode must be in [0, 7]");
+  if (mode < 0 || mode > 15) return fail("qimg_set_fmha_mode: mode must be in [0, 15]");
   g_fmha_mode = mode;
   return 0;
 }
 int qimg_get_fmha_mode(void) { return fmha_mode(); }
 
 template <uint32_t MASK>
-static int launch_fmha_inst(bool v5, dim3 grid, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
+static int launch_fmha_inst(bool v5, bool pingpong, dim3 grid, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
                             const FmhaParams& prm, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
     attr_set = true;
   }
   if (v5) fmha_joint_kernel_v5<MASK><<<grid, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else fmha_joint_kernel<MASK><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else if (pingpong) fmha_joint_kernel<MASK, true><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else fmha_joint_kernel<MASK, false><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   QIMG_LAUNCH_CHECK("fmha_joint_kernel");
   return 0;
 }
@@ -563,11 +565,12 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   dim3 grid((S + 255) / 256, B * H);
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
   // bits 1-2 of the mode: share of the exponentials computed by the FMA-pipe polynomial (0, 25, 37.5, 50 %)
+  const bool pp = (mode & 8) != 0;  // bit 3: strict alternation of the two softmax warpgroups' exp phases
   switch ((mode >> 1) & 3) {
-    case 0: return launch_fmha_inst<0x00u>(v5, grid, tq, tk, tv, prm, (cudaStream_t)stream);
-    case 1: return launch_fmha_inst<0x11u>(v5, grid, tq, tk, tv, prm, (cudaStream_t)stream);
-    case 2: return launch_fmha_inst<0x52u>(v5, grid, tq, tk, tv, prm, (cudaStream_t)stream);
-    default: return launch_fmha_inst<0x55u>(v5, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+    case 0: return launch_fmha_inst<0x00u>(v5, pp, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+    case 1: return launch_fmha_inst<0x11u>(v5, pp, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+    case 2: return launch_fmha_inst<0x52u>(v5, pp, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+    default: return launch_fmha_inst<0x55u>(v5, pp, grid, tq, tk, tv, prm, (cudaStream_t)stream);
   }
 }
 

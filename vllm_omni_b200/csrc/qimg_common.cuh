@@ -125,6 +125,14 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// named barriers (sub-CTA): `nthreads` = total threads that arrive or sync on `id` per phase
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, mbarrier completion
 // ---------------------------------------------------------------------------------------

@@ -100,7 +100,7 @@ __device__ __forceinline__ uint64_t exp2_poly_f32x2(uint64_t x) {
 #define FMHA_POLY_MASK 0x00u  // bit k set => pair (k mod 8) of every 8 pairs uses the FMA-pipe polynomial
 #endif
 
-template <uint32_t POLY_MASK>
+template <uint32_t POLY_MASK, bool PINGPONG>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
@@ -253,6 +253,11 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float c = prm.scale_log2;
     float m_used = -INFINITY;  // row max (raw score units) the exponentials are referenced to
     float l = 0.f;             // running row sum
+    // Exponential phases of the two query tiles strictly alternate (named barriers 1 / 2, 256 threads): the
+    // two warpgroups would otherwise run their MUFU-heavy phases at the same time, halving each other's
+    // XU throughput and then both waiting for the tensor pipe.  Alternation keeps tile 0's softmax under
+    // tile 1's MMAs and vice versa (the issue order QK0 PV1 QK1 PV0 assumes exactly that).
+    if (PINGPONG && t == 1) named_bar_arrive(1, 256);
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -304,6 +309,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
         // ---- P = exp2(s*c - m*c) (masked columns give exp2(-inf) = 0), row sum, bf16 P -> TMEM ----
+        if (PINGPONG) named_bar_sync(1 + t, 256);  // my turn on the XU pipe
         const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_used * c);
         uint64_t la = 0, lb = 0;  // two packed partial row sums (bit pattern 0 = +0.0f pairs)
   #pragma unroll
@@ -328,6 +334,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
           tmem_st_32x32b_x16(tS + cc * 16, pk);
         }
+        if (PINGPONG && !(t == 1 && j == n_kv - 1)) named_bar_arrive(1 + (t ^ 1), 256);  // hand the XU pipe over
         {
           uint32_t a0, a1, b0, b1;
           unpack_f32x2(la, a0, a1);
