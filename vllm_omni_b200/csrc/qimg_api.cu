@@ -361,6 +361,23 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 using namespace qimg;
 
+template <uint32_t MASK>
+static int launch_fmha_inst(bool v5, bool pingpong, dim3 grid, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
+                            const FmhaParams& prm, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
+    attr_set = true;
+  }
+  if (v5) fmha_joint_kernel_v5<MASK><<<grid, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else if (pingpong) fmha_joint_kernel<MASK, true><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else fmha_joint_kernel<MASK, false><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  QIMG_LAUNCH_CHECK("fmha_joint_kernel");
+  return 0;
+}
+
 extern "C" {
 
 int qimg_abi_version(void) { return 1; }
@@ -529,23 +546,6 @@ int qimg_set_fmha_mode(int mode) {
   return 0;
 }
 int qimg_get_fmha_mode(void) { return fmha_mode(); }
-
-template <uint32_t MASK>
-static int launch_fmha_inst(bool v5, bool pingpong, dim3 grid, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
-                            const FmhaParams& prm, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
-    attr_set = true;
-  }
-  if (v5) fmha_joint_kernel_v5<MASK><<<grid, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else if (pingpong) fmha_joint_kernel<MASK, true><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else fmha_joint_kernel<MASK, false><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  QIMG_LAUNCH_CHECK("fmha_joint_kernel");
-  return 0;
-}
 
 int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
                     int T, float softmax_scale, qimg_stream_t stream) {
