@@ -536,7 +536,7 @@ static int g_fmha_mode = -1;
 static int fmha_mode() {
   if (g_fmha_mode < 0) {
     const char* e = getenv("QIMG_FMHA_MODE");
-    g_fmha_mode = e ? atoi(e) : 0;
+    g_fmha_mode = e ? atoi(e) : 10;  // 128-row KV tiles + 25 % polynomial exp2 + softmax ping-pong (best of the sweep, profiles/)
   }
   return g_fmha_mode;
 }
