@@ -272,6 +272,11 @@ def main():
         flops_img = flops_per_forward(L, S_img, T) * NS * fwd_per_ts
         achieved_job = flops_img * B * args.steps / (ms_dev / 1e3) / 1e12  # per GPU, TFLOP/s
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tj):  # dram bytes per launch of the GEMM family from the committed ncu --set full captures
+            with open(tj) as f:
+                traffic = json.load(f).get("avg_bytes_per_launch")
         gemm_tf = gemm_prof["flops"] / (gemm_prof["ms"] / 1e3) / 1e12 if gemm_prof["ms"] > 0 else None
         fmha_tf = fmha_prof["flops"] / (fmha_prof["ms"] / 1e3) / 1e12 if fmha_prof["ms"] > 0 else None
         line = {
@@ -285,7 +290,8 @@ def main():
                        "parallelism": f"dp{world}"},
             "roofline": {"bound": "tensor", "kernel": "gemm_umma_kernel (tcgen05, grouped img+txt, fused epilogues)",
                          "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None,
-                         "peak_source": f"{peak_kind} bf16_tflops_sustained (cuBLAS 8192^3 loop)", "traffic": None,
+                         "peak_source": f"{peak_kind} bf16_tflops_sustained (cuBLAS 8192^3 loop)", "traffic": traffic,
+                         "flops_per_launch": gemm_prof["flops"] / max(gemm_prof["launches"], 1),
                          "launches": gemm_prof["launches"], "share_of_step": gemm_prof["ms"] / ms_dev,
                          "fmha": {"achieved": fmha_tf, "frac": (fmha_tf / peak) if fmha_tf else None,
                                   "launches": fmha_prof["launches"], "share_of_step": fmha_prof["ms"] / ms_dev},
