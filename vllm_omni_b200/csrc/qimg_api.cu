@@ -8,6 +8,7 @@
 #include "qimg_elementwise.cuh"
 #include "qimg_fmha.cuh"
 #include "qimg_fmha2.cuh"
+#include "qimg_fmha3.cuh"
 #include "qimg_gemm.cuh"
 #include "qimg_gemm2.cuh"
 #include "qimg_host.cuh"
@@ -362,18 +363,22 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 using namespace qimg;
 
 template <uint32_t MASK>
-static int launch_fmha_inst(bool v5, bool pingpong, dim3 grid, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
+static int launch_fmha_inst(int pipeline, bool pingpong, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
                             const FmhaParams& prm, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA3_SMEM_BYTES));
     attr_set = true;
   }
-  if (v5) fmha_joint_kernel_v5<MASK><<<grid, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else if (pingpong) fmha_joint_kernel<MASK, true><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else fmha_joint_kernel<MASK, false><<<grid, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  const int pairs = (prm.S + 255) / 256;
+  const dim3 grid2(pairs, prm.B * prm.H);
+  if (pipeline == 2) fmha_joint_kernel_v6<MASK><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA3_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else if (pipeline == 1) fmha_joint_kernel_v5<MASK><<<grid2, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else if (pingpong) fmha_joint_kernel<MASK, true><<<grid2, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else fmha_joint_kernel<MASK, false><<<grid2, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   QIMG_LAUNCH_CHECK("fmha_joint_kernel");
   return 0;
 }
@@ -536,12 +541,12 @@ static int g_fmha_mode = -1;
 static int fmha_mode() {
   if (g_fmha_mode < 0) {
     const char* e = getenv("QIMG_FMHA_MODE");
-    g_fmha_mode = e ? atoi(e) : 10;  // 128-row KV tiles + 25 % polynomial exp2 + softmax ping-pong (best of the sweep, profiles/)
+    g_fmha_mode = e ? atoi(e) : 20;  // 128-row KV tiles + 25 % polynomial exp2 + softmax ping-pong (best of the sweep, profiles/)
   }
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode < 0 || mode > 15) return fail("qimg_set_fmha_mode: mode must be in [0, 15]");
+  if (mode < 0 || mode > 31 || (mode & 3) == 3) return fail("qimg_set_fmha_mode: bad mode");
   g_fmha_mode = mode;
   return 0;
 }
@@ -551,8 +556,8 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
                     int T, float softmax_scale, qimg_stream_t stream) {
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
   const int mode = fmha_mode();
-  const bool v5 = (mode & 1) != 0;
-  const uint32_t kv_rows = v5 ? FMHA2_KV : 128;
+  const int pipeline = mode & 3;             // 0: 128-row KV tiles; 1: 64-row, double-buffered S; 2: 80-row, decoupled P
+  const uint32_t kv_rows = pipeline == 2 ? FMHA3_KV : (pipeline == 1 ? FMHA2_KV : 128);
   const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
   const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
   const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
@@ -562,15 +567,13 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   prm.out_img = (bf16*)out_img;
   prm.B = B; prm.H = H; prm.S = S; prm.T = T;
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
-  dim3 grid((S + 255) / 256, B * H);
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
-  // bits 1-2 of the mode: share of the exponentials computed by the FMA-pipe polynomial (0, 25, 37.5, 50 %)
-  const bool pp = (mode & 8) != 0;  // bit 3: strict alternation of the two softmax warpgroups' exp phases
-  switch ((mode >> 1) & 3) {
-    case 0: return launch_fmha_inst<0x00u>(v5, pp, grid, tq, tk, tv, prm, (cudaStream_t)stream);
-    case 1: return launch_fmha_inst<0x11u>(v5, pp, grid, tq, tk, tv, prm, (cudaStream_t)stream);
-    case 2: return launch_fmha_inst<0x52u>(v5, pp, grid, tq, tk, tv, prm, (cudaStream_t)stream);
-    default: return launch_fmha_inst<0x55u>(v5, pp, grid, tq, tk, tv, prm, (cudaStream_t)stream);
+  const bool pp = (mode & 16) != 0;  // strict alternation of the two softmax warpgroups' exp phases (pipeline 0)
+  switch ((mode >> 2) & 3) {         // share of the exponentials on the FMA-pipe polynomial: 0 / 25 / 37.5 / 50 %
+    case 0: return launch_fmha_inst<0x00u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
+    case 1: return launch_fmha_inst<0x11u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
+    case 2: return launch_fmha_inst<0x52u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
+    default: return launch_fmha_inst<0x55u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
   }
 }
 
