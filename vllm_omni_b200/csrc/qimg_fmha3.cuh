@@ -259,17 +259,18 @@ fmha_joint_kernel_v6(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             mx3 = max3_f32(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
           }
           const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+          bool pv_waited = (j == 0);
           if (j == 0) {
             m_used = mx;
           } else {
-            // PV(j-1) must be complete before P is overwritten below (and before O is rescaled).  pv_done[t]
-            // completes one phase per PV; phases 0..j-2 are certainly complete here, so the parity of phase
-            // j-1 is unambiguous.  In steady state this wait returns immediately.
-            mbar_wait(&pv_done[t], (j - 1) & 1);
-            tc_fence_after();
             const float m_new = fmaxf(m_used, mx);
             const bool need = (m_new - m_used) * c > 8.0f;
             if (__any_sync(0xffffffffu, need)) {
+              // rare: rescale O and l.  PV(j-1) must be complete first.  pv_done[t] completes one phase per PV;
+              // phases 0..j-2 are certainly complete here, so the parity of phase j-1 is unambiguous.
+              mbar_wait(&pv_done[t], (j - 1) & 1);
+              tc_fence_after();
+              pv_waited = true;
               const float f = ex2_approx((m_used - m_new) * c);
               l *= f;
 #pragma unroll 1
@@ -303,6 +304,12 @@ fmha_joint_kernel_v6(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             uint32_t pl, ph;
             unpack_f32x2(p, pl, ph);
             pk[k] = pack_bf16x2(__uint_as_float(pl), __uint_as_float(ph));
+          }
+          // P(j-1) must have been consumed by PV(j-1) before it is overwritten; the exponentials above ran
+          // concurrently with that MMA, so this wait normally returns immediately.
+          if (!pv_waited) {
+            mbar_wait(&pv_done[t], (j - 1) & 1);
+            tc_fence_after();
           }
           tmem_st_32x32b_x32(tP, pk);
           tmem_st_32x32b_x8(tP + 32, pk + 32);
