@@ -370,12 +370,14 @@ static int launch_fmha_inst(int pipeline, bool pingpong, const CUtensorMap* tq, 
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA3_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmha3_smem_bytes<80>()));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmha3_smem_bytes<64>()));
     attr_set = true;
   }
   const int pairs = (prm.S + 255) / 256;
   const dim3 grid2(pairs, prm.B * prm.H);
-  if (pipeline == 2) fmha_joint_kernel_v6<MASK><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA3_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  if (pipeline == 2) fmha_joint_kernel_v6<MASK, 80><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<80>(), st>>>(*tq, *tk, *tv, prm);
+  else if (pipeline == 3) fmha_joint_kernel_v6<MASK, 64><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<64>(), st>>>(*tq, *tk, *tv, prm);
   else if (pipeline == 1) fmha_joint_kernel_v5<MASK><<<grid2, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   else if (pingpong) fmha_joint_kernel<MASK, true><<<grid2, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   else fmha_joint_kernel<MASK, false><<<grid2, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
@@ -546,7 +548,7 @@ static int fmha_mode() {
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode < 0 || mode > 31 || (mode & 3) == 3) return fail("qimg_set_fmha_mode: bad mode");
+  if (mode < 0 || mode > 31) return fail("qimg_set_fmha_mode: bad mode");
   g_fmha_mode = mode;
   return 0;
 }
@@ -557,7 +559,7 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
   const int mode = fmha_mode();
   const int pipeline = mode & 3;             // 0: 128-row KV tiles; 1: 64-row, double-buffered S; 2: 80-row, decoupled P
-  const uint32_t kv_rows = pipeline == 2 ? FMHA3_KV : (pipeline == 1 ? FMHA2_KV : 128);
+  const uint32_t kv_rows = pipeline == 2 ? 80 : (pipeline == 3 ? 64 : (pipeline == 1 ? FMHA2_KV : 128));
   const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
   const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
   const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);

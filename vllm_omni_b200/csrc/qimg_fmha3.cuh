@@ -22,13 +22,13 @@
 
 namespace qimg {
 
-constexpr int FMHA3_KV = 80;
 constexpr int FMHA3_KS = 3;
 constexpr int FMHA3_VS = 3;
 constexpr int FMHA3_Q_BYTES = 128 * 128 * 2;       // 32 KB per query tile (two 64-col SW128 slabs of 16 KB)
-constexpr int FMHA3_SLAB = FMHA3_KV * 128;          // 10240 B: one 64-column slab of a K/V tile
-constexpr int FMHA3_KV_BYTES = 2 * FMHA3_SLAB;      // 20 KB per K or V tile
-constexpr int FMHA3_SMEM_BYTES = 2 * FMHA3_Q_BYTES + (FMHA3_KS + FMHA3_VS) * FMHA3_KV_BYTES + 1024 + 512;
+template <int KV>
+constexpr int fmha3_smem_bytes() {
+  return 2 * FMHA3_Q_BYTES + (FMHA3_KS + FMHA3_VS) * (2 * KV * 128) + 1024 + 512;
+}
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -50,10 +50,15 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                : "memory");
 }
 
-template <uint32_t POLY_MASK>
+template <uint32_t POLY_MASK, int FMHA3_KV>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_joint_kernel_v6(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
+  static_assert(FMHA3_KV == 64 || FMHA3_KV == 80, "KV tile");
+  constexpr int FMHA3_SLAB = FMHA3_KV * 128;      // one 64-column slab of a K/V tile (multiple of 1024 B)
+  constexpr int FMHA3_KV_BYTES = 2 * FMHA3_SLAB;
+  constexpr int P_BASE = 2 * FMHA3_KV;            // TMEM: S[t] at t*KV, P[t] at 2*KV + t*KV/2, O[t] at 256 + 128 t
+  constexpr int P_COLS = FMHA3_KV / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -164,7 +169,7 @@ fmha_joint_kernel_v6(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     auto issue_pv = [&](int t, int vs, bool accumulate) {
       const uint32_t va = smem_u32(sV + vs * FMHA3_KV_BYTES);
       const uint32_t d = tmem_base + 256 + t * 128;
-      const uint32_t p = tmem_base + 160 + t * 40;
+      const uint32_t p = tmem_base + P_BASE + t * P_COLS;
 #pragma unroll
       for (int k = 0; k < FMHA3_KV / 16; ++k) {
         // A = P (bf16 pairs, 8 TMEM columns per K=16 step); B = V rows [16k,16k+16) x 128 (MN-major)
@@ -225,7 +230,7 @@ fmha_joint_kernel_v6(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int q = warp & 3;         // TMEM lane quarter
       const uint32_t lane_off = (uint32_t)(q * 32) << 16;
       const uint32_t tS = tmem_base + lane_off + t * FMHA3_KV;
-      const uint32_t tP = tmem_base + lane_off + 160 + t * 40;
+      const uint32_t tP = tmem_base + lane_off + P_BASE + t * P_COLS;
       const uint32_t tO = tmem_base + lane_off + 256 + t * 128;
       const float c = prm.scale_log2;
       float m_used = -INFINITY;  // row max (raw score units) the exponentials are referenced to
@@ -236,7 +241,7 @@ fmha_joint_kernel_v6(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t r[FMHA3_KV];
         tmem_ld_32x32b_x32(tS, r);
         tmem_ld_32x32b_x32(tS + 32, r + 32);
-        tmem_ld_32x32b_x16(tS + 64, r + 64);
+        if (FMHA3_KV > 64) tmem_ld_32x32b_x16(tS + 64, r + 64);
         tmem_ld_wait();
         // the score row is in registers: QK(j+1) may overwrite S right away
         tc_fence_before();
@@ -312,7 +317,7 @@ fmha_joint_kernel_v6(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tc_fence_after();
           }
           tmem_st_32x32b_x32(tP, pk);
-          tmem_st_32x32b_x8(tP + 32, pk + 32);
+          if (FMHA3_KV > 64) tmem_st_32x32b_x8(tP + 32, pk + 32);
           uint32_t a0, a1, b0, b1;
           unpack_f32x2(la, a0, a1);
           unpack_f32x2(lb, b0, b1);
