@@ -379,8 +379,8 @@ static int launch_fmha_inst(int pipeline, bool pingpong, const CUtensorMap* tq, 
   if (pipeline == 2) fmha_joint_kernel_v6<MASK, 80><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<80>(), st>>>(*tq, *tk, *tv, prm);
   else if (pipeline == 3) fmha_joint_kernel_v6<MASK, 64><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<64>(), st>>>(*tq, *tk, *tv, prm);
   else if (pipeline == 1) fmha_joint_kernel_v5<MASK><<<grid2, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else if (pingpong) fmha_joint_kernel<MASK, true><<<grid2, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else fmha_joint_kernel<MASK, false><<<grid2, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else if (pingpong) fmha_joint_kernel<MASK, true><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  else fmha_joint_kernel<MASK, false><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   QIMG_LAUNCH_CHECK("fmha_joint_kernel");
   return 0;
 }

@@ -122,8 +122,21 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int bh = blockIdx.y;
-  const int q_row0 = blockIdx.x * 256;
+  // 1-D grid, remapped so that the query-tile pairs whose SECOND tile lies completely beyond S run last and
+  // skip that tile (S = 4224 -> 16 full pairs + 1 half pair per head; 1536 full + 96 half CTAs fill 148 SMs in
+  // ~11.1 instead of 12 CTA-times)
+  const int full_pairs = prm.S / 256 + ((prm.S % 256) > 128 ? 1 : 0);
+  const int n_bh = prm.B * prm.H;
+  int bh, pair_idx;
+  if ((int)blockIdx.x < full_pairs * n_bh) {
+    bh = blockIdx.x / full_pairs;
+    pair_idx = blockIdx.x - bh * full_pairs;
+  } else {
+    bh = blockIdx.x - full_pairs * n_bh;
+    pair_idx = full_pairs;
+  }
+  const int q_row0 = pair_idx * 256;
+  const bool two = q_row0 + 128 < prm.S;  // is the second query tile (partly) in range?
   const int n_kv = (prm.S + 127) / 128;
 
   if (warp == 0 && lane == 0) {
@@ -155,8 +168,8 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, 2 * FMHA_TILE_BYTES);
-      for (int t = 0; t < 2; ++t)
+      mbar_arrive_expect_tx(q_full, (two ? 2 : 1) * FMHA_TILE_BYTES);
+      for (int t = 0; t < (two ? 2 : 1); ++t)
         for (int s = 0; s < 2; ++s)
           tma_load_3d(sQ + t * FMHA_TILE_BYTES + s * 16384, &tmQ, q_full, s * 64, q_row0 + t * 128, bh);
     }
@@ -212,18 +225,18 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         umma_commit(&s_full[0]);
       }
       __syncwarp();
-      if (j > 0) {
+      if (two && j > 0) {
         mbar_wait(&p_ready[1], (j - 1) & 1);
         tc_fence_after();
-        if (elect_one()) {
-          issue_pv(1, (j - 1) % FMHA_VS, j - 1 > 0);
-          umma_commit(&v_empty[(j - 1) % FMHA_VS]);
-        }
+        if (elect_one()) issue_pv(1, (j - 1) % FMHA_VS, j - 1 > 0);
         __syncwarp();
       }
       if (elect_one()) {
-        issue_qk(1, ks);
-        umma_commit(&s_full[1]);
+        if (j > 0) umma_commit(&v_empty[(j - 1) % FMHA_VS]);  // V(j-1): PV0(j-1) and PV1(j-1) are both issued
+        if (two) {
+          issue_qk(1, ks);
+          umma_commit(&s_full[1]);
+        }
         umma_commit(&k_empty[ks]);
       }
       __syncwarp();
@@ -234,10 +247,12 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (elect_one()) issue_pv(0, vs, j > 0);
       __syncwarp();
     }
-    mbar_wait(&p_ready[1], (n_kv - 1) & 1);
-    tc_fence_after();
+    if (two) {
+      mbar_wait(&p_ready[1], (n_kv - 1) & 1);
+      tc_fence_after();
+    }
     if (elect_one()) {
-      issue_pv(1, (n_kv - 1) % FMHA_VS, n_kv - 1 > 0);
+      if (two) issue_pv(1, (n_kv - 1) % FMHA_VS, n_kv - 1 > 0);
       umma_commit(&v_empty[(n_kv - 1) % FMHA_VS]);
       umma_commit(&o_full[0]);
       umma_commit(&o_full[1]);
@@ -246,6 +261,8 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   } else {
     // ===================== softmax / correction / output warps =====================
     const int t = (warp - 2) >> 2;  // query tile handled by this warpgroup
+    if (t == 0 || two) {
+    const bool pingpong = PINGPONG && two;
     const int q = warp & 3;         // TMEM lane quarter
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t tS = tmem_base + lane_off + t * 128;
@@ -257,7 +274,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // two warpgroups would otherwise run their MUFU-heavy phases at the same time, halving each other's
     // XU throughput and then both waiting for the tensor pipe.  Alternation keeps tile 0's softmax under
     // tile 1's MMAs and vice versa (the issue order QK0 PV1 QK1 PV0 assumes exactly that).
-    if (PINGPONG && t == 1) named_bar_arrive(1, 256);
+    if (pingpong && t == 1) named_bar_arrive(1, 256);
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -309,7 +326,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
         // ---- P = exp2(s*c - m*c) (masked columns give exp2(-inf) = 0), row sum, bf16 P -> TMEM ----
-        if (PINGPONG) named_bar_sync(1 + t, 256);  // my turn on the XU pipe
+        if (pingpong) named_bar_sync(1 + t, 256);  // my turn on the XU pipe
         const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_used * c);
         uint64_t la = 0, lb = 0;  // two packed partial row sums (bit pattern 0 = +0.0f pairs)
   #pragma unroll
@@ -334,7 +351,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
           tmem_st_32x32b_x16(tS + cc * 16, pk);
         }
-        if (PINGPONG && !(t == 1 && j == n_kv - 1)) named_bar_arrive(1 + (t ^ 1), 256);  // hand the XU pipe over
+        if (pingpong && !(t == 1 && j == n_kv - 1)) named_bar_arrive(1 + (t ^ 1), 256);  // hand the XU pipe over
         {
           uint32_t a0, a1, b0, b1;
           unpack_f32x2(la, a0, a1);
@@ -387,6 +404,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         stg_v4(dst + h * 128 + c16 * 8, v);
       }
     }
+    }  // active tile
   }
 
   tc_fence_before();
