@@ -107,6 +107,32 @@ def test_rms_norm_and_gate_residual():
     assert torch.equal(xd.cpu().view(2, 19, 256), x + gate[:, None, :] * y)
 
 
+def test_gate_residual_bias_tp_form():
+    g = gen(31)
+    x = torch.randn(2, 19, 256, generator=g).bfloat16()
+    y = torch.randn(2, 19, 256, generator=g).bfloat16()
+    bias = torch.randn(256, generator=g).bfloat16()
+    gate = torch.randn(2, 256, generator=g).bfloat16()
+    xd = x.view(-1, 256).to(dev).clone()
+    q.check(q.load().qimg_gate_residual_bias(xd.data_ptr(), y.view(-1, 256).to(dev).data_ptr(), bias.to(dev).data_ptr(),
+                                            gate.to(dev).data_ptr(), 38, 256, 19, 256, q.stream_ptr()))
+    assert torch.equal(xd.cpu().view(2, 19, 256), x + gate[:, None, :] * (y + bias))
+
+
+def test_row_parallel_partial_sums_match_full_gemm(gemm_mode):
+    """The TP engine's row-parallel linears: sum over K-shards of (A_shard @ W_shard^T) with a zero bias equals
+    the full linear (bf16 partial sums, so only to bf16 accuracy) — what the all-reduce reconstructs."""
+    g = gen(32)
+    M, N, K, P = 300, 512, 1024, 2
+    A = torch.randn(M, K, generator=g).bfloat16()
+    W = (torch.randn(N, K, generator=g) / 32).bfloat16()
+    zero = torch.zeros(N, dtype=bf, device=dev)
+    parts = [q.linear(A[:, r * K // P:(r + 1) * K // P].contiguous().to(dev), W[:, r * K // P:(r + 1) * K // P].contiguous().to(dev), zero)
+             for r in range(P)]
+    total = (parts[0].float() + parts[1].float()).cpu()
+    assert O.rel_fro(total, A.float() @ W.float().T) < TOL_KERNEL
+
+
 @pytest.mark.parametrize("M,N,K,act", [(1, 1536, 256, True), (4, 6216, 3072, True), (3, 512, 256, False), (11, 640, 512, True)])
 def test_linear_small_m(M, N, K, act):
     g = gen(4)
