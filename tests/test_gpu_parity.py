@@ -113,9 +113,10 @@ def test_gate_residual_bias_tp_form():
     y = torch.randn(2, 19, 256, generator=g).bfloat16()
     bias = torch.randn(256, generator=g).bfloat16()
     gate = torch.randn(2, 256, generator=g).bfloat16()
-    xd = x.view(-1, 256).to(dev).clone()
-    q.check(q.load().qimg_gate_residual_bias(xd.data_ptr(), y.view(-1, 256).to(dev).data_ptr(), bias.to(dev).data_ptr(),
-                                            gate.to(dev).data_ptr(), 38, 256, 19, 256, q.stream_ptr()))
+    xd, yd, bd, gd = x.view(-1, 256).to(dev).clone(), y.view(-1, 256).to(dev), bias.to(dev), gate.to(dev)  # keep alive
+    q.check(q.load().qimg_gate_residual_bias(xd.data_ptr(), yd.data_ptr(), bd.data_ptr(), gd.data_ptr(), 38, 256, 19, 256,
+                                            q.stream_ptr()))
+    torch.cuda.synchronize()
     assert torch.equal(xd.cpu().view(2, 19, 256), x + gate[:, None, :] * (y + bias))
 
 
