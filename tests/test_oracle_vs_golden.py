@@ -36,6 +36,20 @@ def test_oracle_matches_reference_golden(golden_dir, name):
     assert 1e-3 < O.rel_fro(fx["ref_bf16"], fx["ref_fp32"]) < 2e-2
 
 
+def test_oracle_matches_reference_golden_depth12(golden_dir):
+    """Full-width (D=3072) 12-layer case: bf16 restatement still bit-exact; the reference's own bf16 path is
+    1.26e-2 away from its fp32 path at this depth, which is why deep parity is judged by criterion (iii)."""
+    fx = torch.load(os.path.join(golden_dir, "fullwidth_L12.pt"))
+    c = fx["case"]
+    w = _weights(c)
+    chk = sum(float(w[k].double().abs().sum()) for k in sorted(w))
+    assert abs(chk - fx["weights_checksum"]) <= 1e-9 * abs(fx["weights_checksum"])
+    dims = O.DiTDims(num_layers=c["L"], num_heads=c["H"], joint_dim=c["joint"])
+    out = O.model_forward(w, dims, fx["hidden_states"], fx["encoder_hidden_states"], fx["timestep"], (1,) + tuple(c["grid"]))
+    assert O.rel_fro(out, fx["ref_bf16"]) <= 1e-6
+    assert 1.0e-2 < fx["ref_bf16_vs_fp32"] < 1.6e-2
+
+
 def test_scheduler_tables_and_step():
     sig = O.flow_match_sigmas(50, 4096)
     assert sig.shape == (51,) and sig[-1] == 0.0
