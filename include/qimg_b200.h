@@ -42,13 +42,15 @@ int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* f
 int qimg_set_gemm_mode(int mode);
 int qimg_get_gemm_mode(void);
 
-/* Attention pipeline tuning, mode = pipeline | (poly << 2) | (pingpong << 4):
+/* Attention pipeline tuning, mode = pipeline | (poly << 3) | (pingpong << 5):
  *   pipeline 0 = 128-row KV tiles, P aliases S in TMEM (fixed issue order QK0 PV1 QK1 PV0);
  *            1 = 64-row KV tiles, double-buffered S;
  *            2 = 80-row KV tiles, P in its own TMEM region: softmax and tensor pipes fully decoupled, the MMA
- *                warp issues whatever is ready; half-empty query-tile pairs skip the empty tile and run last.
+ *                warp issues whatever is ready; half-empty query-tile pairs skip the empty tile and run last;
+ *            3 = like 2 with 64-row KV tiles;
+ *            4 = like 0 with TWO softmax threads per query row (16 softmax warps).
  *   poly 0..3 = 0 / 25 / 37.5 / 50 % of the softmax exponentials on a degree-3 FMA-pipe polynomial.
- *   pingpong  = strict alternation of the two softmax warpgroups' exp phases (pipeline 0 only).
+ *   pingpong  = strict alternation of the two softmax warpgroups' exp phases (pipelines 0 and 4).
  * Env QIMG_FMHA_MODE overrides the default. */
 int qimg_set_fmha_mode(int mode);
 int qimg_get_fmha_mode(void);

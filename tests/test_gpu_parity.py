@@ -52,7 +52,7 @@ def test_library_loaded_and_device():
     assert os.path.exists(q.LIB_PATH)
 
 
-@pytest.fixture(params=[0, 1, 2, 8, 5, 20, 6], ids=["kv128", "kv64dbuf", "kv80decoupled", "kv128-poly37", "kv64dbuf-poly25", "kv128-poly25-pingpong", "kv80decoupled-poly25"])
+@pytest.fixture(params=[0, 1, 2, 3, 4, 16, 9, 40, 44], ids=["kv128", "kv64dbuf", "kv80decoupled", "kv64decoupled", "kv128-2thr", "kv128-poly37", "kv64dbuf-poly25", "kv128-poly25-pingpong", "kv128-2thr-poly25-pingpong"])
 def fmha_mode(request):
     """Both attention pipelines (first-generation 128-row KV tiles / double-buffered 64-row KV tiles)."""
     prev = q.get_fmha_mode()

@@ -9,6 +9,7 @@
 #include "qimg_fmha.cuh"
 #include "qimg_fmha2.cuh"
 #include "qimg_fmha3.cuh"
+#include "qimg_fmha4.cuh"
 #include "qimg_gemm.cuh"
 #include "qimg_gemm2.cuh"
 #include "qimg_host.cuh"
@@ -369,6 +370,8 @@ static int launch_fmha_inst(int pipeline, bool pingpong, const CUtensorMap* tq, 
   if (!attr_set) {
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v7<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v7<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmha3_smem_bytes<80>()));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmha3_smem_bytes<64>()));
@@ -376,7 +379,10 @@ static int launch_fmha_inst(int pipeline, bool pingpong, const CUtensorMap* tq, 
   }
   const int pairs = (prm.S + 255) / 256;
   const dim3 grid2(pairs, prm.B * prm.H);
-  if (pipeline == 2) fmha_joint_kernel_v6<MASK, 80><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<80>(), st>>>(*tq, *tk, *tv, prm);
+  if (pipeline == 4) {
+    if (pingpong) fmha_joint_kernel_v7<MASK, true><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+    else fmha_joint_kernel_v7<MASK, false><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  } else if (pipeline == 2) fmha_joint_kernel_v6<MASK, 80><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<80>(), st>>>(*tq, *tk, *tv, prm);
   else if (pipeline == 3) fmha_joint_kernel_v6<MASK, 64><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<64>(), st>>>(*tq, *tk, *tv, prm);
   else if (pipeline == 1) fmha_joint_kernel_v5<MASK><<<grid2, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   else if (pingpong) fmha_joint_kernel<MASK, true><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
@@ -543,12 +549,12 @@ static int g_fmha_mode = -1;
 static int fmha_mode() {
   if (g_fmha_mode < 0) {
     const char* e = getenv("QIMG_FMHA_MODE");
-    g_fmha_mode = e ? atoi(e) : 20;  // 128-row KV tiles + 25 % polynomial exp2 + softmax ping-pong (best of the sweep, profiles/)
+    g_fmha_mode = e ? atoi(e) : 40;  // 128-row KV tiles + 25 % polynomial exp2 + softmax ping-pong (best of the sweep, profiles/)
   }
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode < 0 || mode > 31) return fail("qimg_set_fmha_mode: bad mode");
+  if (mode < 0 || mode > 63 || (mode & 7) > 4) return fail("qimg_set_fmha_mode: bad mode");
   g_fmha_mode = mode;
   return 0;
 }
@@ -558,7 +564,7 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
                     int T, float softmax_scale, qimg_stream_t stream) {
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
   const int mode = fmha_mode();
-  const int pipeline = mode & 3;             // 0: 128-row KV tiles; 1: 64-row, double-buffered S; 2: 80-row, decoupled P
+  const int pipeline = mode & 7;  // 0: 128-row KV tiles; 1: 64-row dbuf S; 2/3: decoupled P (80/64 rows); 4: 2 threads per row
   const uint32_t kv_rows = pipeline == 2 ? 80 : (pipeline == 3 ? 64 : (pipeline == 1 ? FMHA2_KV : 128));
   const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
   const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
@@ -570,8 +576,8 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   prm.B = B; prm.H = H; prm.S = S; prm.T = T;
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
-  const bool pp = (mode & 16) != 0;  // strict alternation of the two softmax warpgroups' exp phases (pipeline 0)
-  switch ((mode >> 2) & 3) {         // share of the exponentials on the FMA-pipe polynomial: 0 / 25 / 37.5 / 50 %
+  const bool pp = (mode & 32) != 0;  // strict alternation of the two softmax warpgroups' exp phases (pipeline 0)
+  switch ((mode >> 3) & 3) {         // share of the exponentials on the FMA-pipe polynomial: 0 / 25 / 37.5 / 50 %
     case 0: return launch_fmha_inst<0x00u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
     case 1: return launch_fmha_inst<0x11u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
     case 2: return launch_fmha_inst<0x52u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
