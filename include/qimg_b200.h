@@ -173,6 +173,28 @@ typedef struct qimg_engine qimg_engine;
 typedef int (*qimg_allreduce_fn)(void* buf, long long count, void* user, qimg_stream_t stream);
 int qimg_engine_set_tp(qimg_engine* e, int tp_size, qimg_allreduce_fn allreduce, void* user);
 
+/* Peer-memory tensor parallelism (one node, NVLink/NVSwitch): instead of the all-reduce callback + epilogue
+ * kernel, each rank reduces ITS slice of rows straight out of every rank's partial-sum buffer (P2P loads, fp32
+ * accumulation, one rounding), applies bias + gate + residual and stores the new residual rows into every
+ * rank's workspace (P2P stores) — reduce-scatter + epilogue + all-gather in one kernel, bracketed by two
+ * cross-GPU flag barriers.  No NCCL on the data path.
+ *   qimg_p2p_alloc            cudaMalloc'ed, zero-filled buffer (IPC-exportable, unlike a sub-allocation of a
+ *                             caching allocator); the workspace and a >= 128-byte flag buffer come from here
+ *   qimg_ipc_get_handle       64-byte cudaIpcMemHandle_t of such a buffer, to be sent to the peer processes
+ *   qimg_ipc_open_handle      maps a peer's buffer into this process (enables peer access lazily)
+ *   qimg_engine_set_tp_p2p    peer_workspaces[p] / peer_flags[p] for p in [0, tp_size): this rank's own
+ *                             (local) pointers at index tp_rank, the opened peer mappings elsewhere.
+ *                             qimg_engine_forward must then be given peer_workspaces[tp_rank] as workspace,
+ *                             and all ranks must issue the same sequence of forwards.
+ *   qimg_engine_p2p_error     synchronising read of the barrier time-out flag (0 = healthy). */
+int qimg_p2p_alloc(size_t bytes, void** out);
+int qimg_p2p_free(void* ptr);
+int qimg_ipc_get_handle(const void* dev_ptr, void* handle64);
+int qimg_ipc_open_handle(const void* handle64, void** out);
+int qimg_ipc_close_handle(void* ptr);
+int qimg_engine_set_tp_p2p(qimg_engine* e, int tp_size, int tp_rank, void* const* peer_workspaces, void* const* peer_flags);
+int qimg_engine_p2p_error(qimg_engine* e, int* out);
+
 int qimg_engine_create(const qimg_dims* dims, const qimg_global_weights* g, const qimg_block_weights* blocks,
                        qimg_engine** out);
 void qimg_engine_destroy(qimg_engine* e);

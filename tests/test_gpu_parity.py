@@ -375,6 +375,29 @@ def test_full_size_properties_1024px():
     # one full-width block against the CPU oracle at reduced S (the oracle at S=4224 is covered by the golden 'fullwidth_L1')
 
 
+def _torchrun(script, nproc, env=None, timeout=600):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env or {})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "tools", script)]
+    r = subprocess.run(cmd, cwd=root, env=e, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_dp2_worker_matches_single_gpu():
-    pytest.skip("covered by tools/dp_check.py under gpurun --gpus 2 (multi-process launch)")
+    """Image-sharded data parallelism through the worker protocol: gathered latents bit-equal to one GPU's."""
+    _torchrun("dp_check.py", 2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("comm", ["nccl", "p2p"])
+def test_tp2_matches_single_gpu(comm):
+    """Head/FFN-sharded tensor parallelism (NCCL all-reduce, and the fused peer-memory reduction kernel) within 1e-2 of
+    the unsharded engine (the reference's SP-vs-baseline tolerance, test_ulysses_sequence_parallel.py:332-343)."""
+    out = _torchrun("tp_check.py", 2, env={"TP_COMM": comm, "TP_LAYERS": "2", "TP_RES": "512"})
+    assert "rel_fro" in out

@@ -1,5 +1,6 @@
 """Tensor-parallel check (torchrun --nproc-per-node P, P GPUs): every rank holds the head / FFN shards of the same
-synthetic checkpoint and runs the TP engine (NCCL all-reduce of the row-parallel partial sums); rank 0 compares the
+synthetic checkpoint and runs the TP engine (TP_COMM=nccl: NCCL all-reduce of the row-parallel partial sums; TP_COMM=p2p: the fused
+peer-memory reduce + epilogue + all-gather kernel); rank 0 compares the
 output with the single-GPU engine on the same inputs (tolerance 1e-2, the reference's SP-vs-baseline convention,
 tests/diffusion/attention/test_ulysses_sequence_parallel.py:332-343), and times both.
 """
@@ -38,7 +39,8 @@ def main():
     torch.cuda.set_device(dev)
     ps.init_distributed_environment(world_size=world, rank=rank, backend="nccl")
     ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=world, backend="nccl")
-    m = build(L, dev, tp_size=world, tp_rank=ps.get_tensor_model_parallel_rank(), tp_group=ps.get_tp_group())
+    comm = os.environ.get("TP_COMM", "nccl")  # "nccl": all-reduce callback; "p2p": fused peer-memory reduction kernel
+    m = build(L, dev, tp_size=world, tp_rank=ps.get_tensor_model_parallel_rank(), tp_group=ps.get_tp_group(), tp_comm=comm)
     lat, txt = synthetic.synthetic_inputs(B, res, res, 64)
     t = torch.tensor([0.5], dtype=torch.bfloat16, device=dev)
     grid = [[(1, res // 16, res // 16)]] * B
@@ -56,6 +58,9 @@ def main():
 
     out_tp, ms_tp = run(m)
     ok = True
+    if comm == "p2p" and not m.p2p_healthy():
+        print(f"rank {rank}: peer-memory barrier timed out", flush=True)
+        ok = False
     if rank == 0:
         m1 = build(L, dev, tp_size=1)
         out_1 = m1(*args, return_dict=False, uniform_timestep=True)[0]
@@ -66,9 +71,9 @@ def main():
         torch.cuda.synchronize()
         ms_1 = (time.perf_counter() - t0) / 3 * 1e3
         err = float((out_tp.float() - out_1.float()).norm() / out_1.float().norm())
-        print(f"tp_check tp={world} L={L} {res}px B={B}: rel_fro(TP, single GPU) = {err:.3e}; "
+        print(f"tp_check tp={world} comm={comm} L={L} {res}px B={B}: rel_fro(TP, single GPU) = {err:.3e}; "
               f"forward {ms_tp:.2f} ms (TP{world}) vs {ms_1:.2f} ms (1 GPU) -> speed-up {ms_1 / ms_tp:.2f}x")
-        ok = err <= 1e-2 and not torch.isnan(out_tp).any()
+        ok = ok and err <= 1e-2 and not torch.isnan(out_tp).any()
     dist.barrier()
     ps.destroy_distributed_env()
     sys.exit(0 if ok else 1)

@@ -12,7 +12,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libqimg_b200.so")
-SOURCES = ["qimg_api.cu", "qimg_engine.cu"]
+SOURCES = ["qimg_api.cu", "qimg_engine.cu", "qimg_tp_p2p.cu"]
 HEADERS = ["qimg_common.cuh", "qimg_elementwise.cuh", "qimg_gemm.cuh", "qimg_gemm2.cuh", "qimg_fmha.cuh", "qimg_fmha2.cuh", "qimg_fmha3.cuh", "qimg_fmha4.cuh", "qimg_host.cuh",
            os.path.join("..", "..", "include", "qimg_b200.h")]
 

@@ -22,7 +22,18 @@ struct qimg_engine {
   int tp_size = 1;
   qimg_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  // peer-memory TP (qimg_engine_set_tp_p2p): every rank's workspace and barrier flags, mapped into this process
+  bool p2p = false;
+  int tp_rank = 0;
+  void* peer_ws[8] = {};
+  void* peer_flags[8] = {};
 };
+
+namespace qimg {
+int tp_p2p_barrier(void* const* flags, int P, int rank, cudaStream_t st);
+int tp_p2p_reduce(void* const* part, void* const* x, const void* bias, const void* gate, int rows, int D, int rows_per_batch,
+                  long long gate_stride, int P, int rank, cudaStream_t st);
+}  // namespace qimg
 
 namespace {
 
@@ -96,6 +107,29 @@ int qimg_engine_set_tp(qimg_engine* e, int tp_size, qimg_allreduce_fn allreduce,
   e->tp_size = tp_size;
   e->allreduce = allreduce;
   e->allreduce_user = user;
+  e->p2p = false;
+  return 0;
+}
+
+int qimg_engine_set_tp_p2p(qimg_engine* e, int tp_size, int tp_rank, void* const* peer_workspaces, void* const* peer_flags) {
+  if (!e || !peer_workspaces || !peer_flags) return fail("qimg_engine_set_tp_p2p: null argument");
+  if (tp_size != 2 && tp_size != 4 && tp_size != 8) return fail("qimg_engine_set_tp_p2p: tp_size must be 2, 4 or 8");
+  if (e->dims.num_heads % tp_size) return fail("qimg_engine_set_tp_p2p: tp_size must divide num_heads");
+  if (tp_rank < 0 || tp_rank >= tp_size) return fail("qimg_engine_set_tp_p2p: bad rank");
+  for (int p = 0; p < tp_size; ++p) {
+    if (!peer_workspaces[p] || !peer_flags[p]) return fail("qimg_engine_set_tp_p2p: null peer pointer");
+    e->peer_ws[p] = peer_workspaces[p];
+    e->peer_flags[p] = peer_flags[p];
+  }
+  e->tp_size = tp_size;
+  e->tp_rank = tp_rank;
+  e->p2p = true;
+  return 0;
+}
+
+int qimg_engine_p2p_error(qimg_engine* e, int* out) {
+  if (!e || !e->p2p || !out) return fail("qimg_engine_p2p_error: engine is not in peer-memory TP mode");
+  QIMG_CUDA_CHECK(cudaMemcpy(out, (char*)e->peer_flags[e->tp_rank] + 64, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -128,6 +162,33 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
   void *part = ws + w.part, *zero_bias = ws + w.zero_bias;
   char* part_txt = (char*)part + (size_t)B * S_img * D * 2;
   if (tp > 1) QIMG_CUDA_CHECK(cudaMemsetAsync(zero_bias, 0, (size_t)D * 2, (cudaStream_t)st));
+  if (e->p2p && workspace != e->peer_ws[e->tp_rank]) return fail("qimg_engine_forward: peer-memory TP needs the registered workspace");
+  // partial sums -> (sum over ranks) -> x += gate * (sum + bias), either through the caller's all-reduce (NCCL) followed by
+  // the epilogue kernel, or in one peer-memory kernel bracketed by two cross-GPU barriers (qimg_tp_p2p.cu)
+  auto tp_reduce = [&](const void* b_img, const void* g_img, const void* b_txt, const void* g_txt, long long gstride) -> int {
+    void* x_img_l = ws + w.x_img;
+    void* x_txt_l = ws + w.x_txt;
+    if (!e->p2p) {
+      if (!e->allreduce) return fail("TP: no all-reduce registered");
+      if (e->allreduce(part, (long long)(B * S_img + B * T) * D, e->allreduce_user, st)) return fail("TP all-reduce callback failed");
+      QIMG_TRY(qimg_gate_residual_bias(x_img_l, part, b_img, g_img, B * S_img, D, S_img, gstride, st));
+      QIMG_TRY(qimg_gate_residual_bias(x_txt_l, part_txt, b_txt, g_txt, B * T, D, T, gstride, st));
+      return 0;
+    }
+    void *pi[8], *pt[8], *xi[8], *xt[8];
+    for (int p = 0; p < tp; ++p) {
+      char* base = (char*)e->peer_ws[p];
+      pi[p] = base + w.part;
+      pt[p] = base + w.part + (size_t)B * S_img * D * 2;
+      xi[p] = base + w.x_img;
+      xt[p] = base + w.x_txt;
+    }
+    QIMG_TRY(tp_p2p_barrier(e->peer_flags, tp, e->tp_rank, (cudaStream_t)st));
+    QIMG_TRY(tp_p2p_reduce(pi, xi, b_img, g_img, B * S_img, D, S_img, gstride, tp, e->tp_rank, (cudaStream_t)st));
+    QIMG_TRY(tp_p2p_reduce(pt, xt, b_txt, g_txt, B * T, D, T, gstride, tp, e->tp_rank, (cudaStream_t)st));
+    QIMG_TRY(tp_p2p_barrier(e->peer_flags, tp, e->tp_rank, (cudaStream_t)st));
+    return 0;
+  };
   const int Mi = B * S_img, Mt = B * T;
   void *x_img = ws + w.x_img, *x_txt = ws + w.x_txt, *xm_img = ws + w.xm_img, *xm_txt = ws + w.xm_txt;
   void *q = ws + w.q, *k = ws + w.k, *v = ws + w.v, *at_img = ws + w.at_img, *at_txt = ws + w.at_txt;
@@ -205,9 +266,7 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
       p[1] = p[0];
       p[1].A = at_txt; p[1].W = bw.to_add_out_w; p[1].M = Mt; p[1].rows_per_batch = T; p[1].out = part_txt;
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS, st));
-      if (e->allreduce(part, (long long)(Mi + Mt) * D, e->allreduce_user, st)) return fail("TP all-reduce callback failed");
-      QIMG_TRY(qimg_gate_residual_bias(x_img, part, bw.to_out_b, seg(mi, 2), Mi, D, S_img, mod_stride, st));
-      QIMG_TRY(qimg_gate_residual_bias(x_txt, part_txt, bw.to_add_out_b, seg(mt, 2), Mt, D, T, mod_stride, st));
+      QIMG_TRY(tp_reduce(bw.to_out_b, seg(mi, 2), bw.to_add_out_b, seg(mt, 2), mod_stride));
     }
     QIMG_TRY(qimg_ln_modulate(x_img, seg(mi, 3), seg(mi, 4), xm_img, Mi, D, S_img, mod_stride, d.eps, st));
     QIMG_TRY(qimg_ln_modulate(x_txt, seg(mt, 3), seg(mt, 4), xm_txt, Mt, D, T, mod_stride, d.eps, st));
@@ -237,9 +296,7 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
       p[1] = p[0];
       p[1].A = h_txt; p[1].W = bw.txt_mlp_w2; p[1].M = Mt; p[1].rows_per_batch = T; p[1].out = part_txt;
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS, st));
-      if (e->allreduce(part, (long long)(Mi + Mt) * D, e->allreduce_user, st)) return fail("TP all-reduce callback failed");
-      QIMG_TRY(qimg_gate_residual_bias(x_img, part, bw.img_mlp_b2, seg(mi, 5), Mi, D, S_img, mod_stride, st));
-      QIMG_TRY(qimg_gate_residual_bias(x_txt, part_txt, bw.txt_mlp_b2, seg(mt, 5), Mt, D, T, mod_stride, st));
+      QIMG_TRY(tp_reduce(bw.img_mlp_b2, seg(mi, 5), bw.txt_mlp_b2, seg(mt, 5), mod_stride));
     }
   }
 

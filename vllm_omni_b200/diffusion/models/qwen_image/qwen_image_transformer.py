@@ -13,6 +13,8 @@ PyTorch compute path and no fallback: without the built extension and an sm_100 
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from collections.abc import Iterable
 from dataclasses import dataclass
@@ -230,6 +232,7 @@ class QwenImageTransformer2DModel(nn.Module):
         tp_size: int | None = None,
         tp_rank: int | None = None,
         tp_group=None,
+        tp_comm: str | None = None,
     ):
         super().__init__()
         if od_config is not None and getattr(od_config, "tf_model_config", None) is not None:
@@ -247,6 +250,11 @@ class QwenImageTransformer2DModel(nn.Module):
             from vllm_omni_b200.diffusion.distributed import parallel_state as _ps
             tp_rank, tp_group = _ps.get_tensor_model_parallel_rank(), _ps.get_tp_group()
         self.tp_size, self.tp_rank, self.tp_group = int(tp_size), int(tp_rank or 0), tp_group
+        # how the row-parallel partial sums are reduced: "nccl" = all-reduce callback + epilogue kernel; "p2p" = one
+        # peer-memory kernel per rank (reduce-scatter + bias/gate/residual + all-gather over NVLink, csrc/qimg_tp_p2p.cu)
+        self.tp_comm = (tp_comm or os.environ.get("QIMG_TP_COMM", "nccl")).lower()
+        if self.tp_comm not in ("nccl", "p2p"):
+            raise ValueError(f"tp_comm must be 'nccl' or 'p2p', got {self.tp_comm!r}")
         if num_attention_heads % self.tp_size:
             raise ValueError(f"tensor_parallel_size {self.tp_size} must divide num_attention_heads {num_attention_heads}")
         self.in_channels = in_channels
@@ -280,6 +288,9 @@ class QwenImageTransformer2DModel(nn.Module):
         self._engine_keepalive = None
         self._ws: dict = {}
         self._rope_dev: dict = {}
+        self._p2p_flags = None   # (local ptr, [ptr per rank]) barrier flags, exchanged once
+        self._p2p_ws: dict = {}  # shape key -> (local ptr, [ptr per rank], nbytes)
+        self._p2p_key = None
 
     # ------------------------------------------------------------------ weights
     def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
@@ -325,6 +336,7 @@ class QwenImageTransformer2DModel(nn.Module):
                 p.data.copy_(w.to(p.dtype))
             loaded.add(name)
         self._engine = None  # pointers may have been re-materialised
+        self._p2p_key = None
         return loaded
 
     def _apply(self, fn, *args, **kwargs):
@@ -345,6 +357,7 @@ class QwenImageTransformer2DModel(nn.Module):
         self._engine = None
         self._ws.clear()
         self._rope_dev.clear()
+        self._p2p_release()
         return self
 
     # ------------------------------------------------------------------ engine
@@ -386,7 +399,7 @@ class QwenImageTransformer2DModel(nn.Module):
         qlib.check(qlib.load().qimg_engine_create(C.byref(dims), C.byref(g), blocks, C.byref(handle)), "qimg_engine_create")
         self._engine = handle
         self._engine_keepalive = (dims, g, blocks)
-        if self.tp_size > 1:
+        if self.tp_size > 1 and self.tp_comm == "nccl":
             import torch.distributed as dist
 
             def _allreduce(buf, count, user, stream):  # called by the engine twice per block, on its stream
@@ -408,6 +421,57 @@ class QwenImageTransformer2DModel(nn.Module):
                 qlib.load().qimg_engine_destroy(self._engine)
         except Exception:
             pass
+
+    def _p2p_release(self):
+        """Unmap the peers' buffers and free the local ones (the next forward re-registers; collective like the set-up)."""
+        groups = list(self._p2p_ws.values()) + ([(self._p2p_flags[0], self._p2p_flags[1], 0)] if self._p2p_flags else [])
+        for local, peers, _ in groups:
+            for r, ptr in enumerate(peers):
+                if r != self.tp_rank:
+                    qlib.ipc_close_handle(ptr)
+        if groups:
+            torch.cuda.synchronize()
+            import torch.distributed as dist
+            dist.barrier(group=self.tp_group)  # nobody frees while a peer still has the buffer mapped
+            for local, _, _ in groups:
+                qlib.p2p_free(local)
+        self._p2p_ws.clear()
+        self._p2p_flags = None
+        self._p2p_key = None
+
+    def _p2p_exchange(self, ptr: int) -> list[int]:
+        """All ranks of the TP group swap the CUDA-IPC handle of `ptr`; returns the pointer per rank (own = local)."""
+        import torch.distributed as dist
+
+        handles = [None] * self.tp_size
+        dist.all_gather_object(handles, qlib.ipc_get_handle(ptr), group=self.tp_group)
+        return [ptr if r == self.tp_rank else qlib.ipc_open_handle(h) for r, h in enumerate(handles)]
+
+    def _p2p_workspace(self, B: int, S_img: int, T: int):
+        """Peer-memory TP: the workspace (and once, the barrier flags) is cudaMalloc'ed by the library, exported over
+        CUDA IPC and registered with the engine; switching between already-registered shapes is a pointer swap."""
+        key = (B, S_img, T)
+        if self._p2p_flags is None:
+            fl = qlib.p2p_alloc(128)
+            self._p2p_flags = (fl, self._p2p_exchange(fl))
+        if key not in self._p2p_ws:
+            nbytes = qlib.load().qimg_engine_workspace_bytes(self._engine, B, S_img, T)
+            ws = qlib.p2p_alloc(nbytes)
+            self._p2p_ws[key] = (ws, self._p2p_exchange(ws), nbytes)
+        ws, peers, nbytes = self._p2p_ws[key]
+        if self._p2p_key != key:
+            P = self.tp_size
+            arr_ws = (C.c_void_p * P)(*peers)
+            arr_fl = (C.c_void_p * P)(*self._p2p_flags[1])
+            qlib.check(qlib.load().qimg_engine_set_tp_p2p(self._engine, P, self.tp_rank, arr_ws, arr_fl), "qimg_engine_set_tp_p2p")
+            self._p2p_key = key
+        return ws, nbytes
+
+    def p2p_healthy(self) -> bool:
+        """Synchronising check of the cross-GPU barrier time-out flag (peer-memory TP only)."""
+        err = C.c_int(0)
+        qlib.check(qlib.load().qimg_engine_p2p_error(self._engine, C.byref(err)), "qimg_engine_p2p_error")
+        return err.value == 0
 
     def _workspace(self, B: int, S_img: int, T: int, device):
         key = (B, S_img, T, str(device))
@@ -463,12 +527,16 @@ class QwenImageTransformer2DModel(nn.Module):
         (ic, isn, tc, tsn), s_expected = self._rope(img_shapes, T, dev)
         if s_expected != S_img:
             raise ValueError(f"img_shapes implies {s_expected} image tokens, hidden_states has {S_img}")
-        buf, off, nbytes = self._workspace(B, S_img, T, dev)
-        self._ws_current = (buf, off, nbytes)
+        if self.tp_size > 1 and self.tp_comm == "p2p":
+            ws_ptr, nbytes = self._p2p_workspace(B, S_img, T)
+        else:
+            buf, off, nbytes = self._workspace(B, S_img, T, dev)
+            self._ws_current = (buf, off, nbytes)
+            ws_ptr = buf.data_ptr() + off
         out = torch.empty((B, S_img, self.proj_out.out_features), dtype=torch.bfloat16, device=dev)
         rc = qlib.load().qimg_engine_forward(
             self._engine, hs.data_ptr(), enc.data_ptr(), ts.data_ptr(), n_t, ic.data_ptr(), isn.data_ptr(), tc.data_ptr(),
-            tsn.data_ptr(), B, S_img, T, out.data_ptr(), buf.data_ptr() + off, nbytes, qlib.stream_ptr())
+            tsn.data_ptr(), B, S_img, T, out.data_ptr(), ws_ptr, nbytes, qlib.stream_ptr())
         qlib.check(rc, "qimg_engine_forward")
         return Transformer2DModelOutput(sample=out)
 

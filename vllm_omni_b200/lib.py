@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = [
     "qimg_cfg_euler_step", "qimg_gemm", "qimg_fmha_joint", "qimg_engine_create", "qimg_engine_destroy",
     "qimg_engine_workspace_bytes", "qimg_engine_forward", "qimg_engine_ws_offset_img", "qimg_engine_ws_offset_txt",
     "qimg_umma_probe", "qimg_prof_enable", "qimg_prof_collect", "qimg_set_gemm_mode", "qimg_get_gemm_mode", "qimg_set_fmha_mode", "qimg_get_fmha_mode", "qimg_gate_residual_bias", "qimg_engine_set_tp",
+    "qimg_p2p_alloc", "qimg_p2p_free", "qimg_ipc_get_handle", "qimg_ipc_open_handle", "qimg_ipc_close_handle",
+    "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error",
 ]
 
 
@@ -90,6 +92,13 @@ def load():
     lib.qimg_rms_norm.argtypes = [vp, vp, vp, i, i, f, vp]
     lib.qimg_gate_residual_bias.argtypes = [vp, vp, vp, vp, i, i, i, ll, vp]
     lib.qimg_engine_set_tp.argtypes = [vp, i, ALLREDUCE_FN, vp]
+    lib.qimg_p2p_alloc.argtypes = [sz, C.POINTER(vp)]
+    lib.qimg_p2p_free.argtypes = [vp]
+    lib.qimg_ipc_get_handle.argtypes = [vp, C.c_char_p]
+    lib.qimg_ipc_open_handle.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.qimg_ipc_close_handle.argtypes = [vp]
+    lib.qimg_engine_set_tp_p2p.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(vp)]
+    lib.qimg_engine_p2p_error.argtypes = [vp, C.POINTER(i)]
     lib.qimg_linear_small_m.argtypes = [vp, vp, vp, vp, i, ll, i, ll, i, vp]
     lib.qimg_timestep_sinusoid.argtypes = [vp, vp, i, vp]
     lib.qimg_cfg_euler_step.argtypes = [vp, vp, vp, ll, i, f, f, f, vp]
@@ -275,3 +284,32 @@ def umma_probe(A, Bm, mode: int):
     D = torch.empty((128, 128), dtype=torch.float32, device=A.device)
     check(load().qimg_umma_probe(_p(A), _p(Bm), _p(D), 128, 128, mode, stream_ptr()), "qimg_umma_probe")
     return D
+
+
+# ---- peer-memory tensor parallelism (qimg_tp_p2p.cu) ------------------------------------------------------------
+def p2p_alloc(nbytes: int) -> int:
+    """cudaMalloc'ed zero-filled device buffer that can be exported over CUDA IPC; returns the device pointer."""
+    out = C.c_void_p()
+    check(load().qimg_p2p_alloc(int(nbytes), C.byref(out)), "qimg_p2p_alloc")
+    return int(out.value)
+
+
+def p2p_free(ptr: int):
+    check(load().qimg_p2p_free(C.c_void_p(ptr)), "qimg_p2p_free")
+
+
+def ipc_get_handle(ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    check(load().qimg_ipc_get_handle(C.c_void_p(ptr), buf), "qimg_ipc_get_handle")
+    return bytes(buf.raw)
+
+
+def ipc_open_handle(handle: bytes) -> int:
+    assert len(handle) == 64
+    out = C.c_void_p()
+    check(load().qimg_ipc_open_handle(C.create_string_buffer(handle, 64), C.byref(out)), "qimg_ipc_open_handle")
+    return int(out.value)
+
+
+def ipc_close_handle(ptr: int):
+    check(load().qimg_ipc_close_handle(C.c_void_p(ptr)), "qimg_ipc_close_handle")
