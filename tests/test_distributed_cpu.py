@@ -45,3 +45,43 @@ def test_dp2_gather_gloo():
 def test_tp2_allreduce_group_gloo():
     res = sorted(_run(2, 2, 29632))
     assert res[0][2] == [1.0] * 4 and res[1][2] == [1.0] * 4
+
+
+def _cfg_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    ps.init_distributed_environment(world_size=world, rank=rank, backend="gloo")
+    ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=1, cfg_parallel_size=2, backend="gloo")
+    assert ps.get_cfg_parallel_world_size() == 2 and ps.get_cfg_parallel_rank() == rank and ps.get_data_parallel_rank() == 0
+    # each rank holds the noise prediction of ITS branch; after the exchange both hold [positive, negative]
+    pos, neg = ps.cfg_all_gather(torch.full((2, 3), float(10 + rank)))
+    q.put(("cfg", rank, pos[0, 0].item(), neg[0, 0].item()))
+    ps.destroy_distributed_env()
+
+
+def test_cfg_parallel_exchange_gloo():
+    """CFG-parallel host logic: group layout and the per-step all-gather of the two branches' predictions."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cfg_worker, args=(r, 2, 29633, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert res == [("cfg", 0, 10.0, 11.0), ("cfg", 1, 10.0, 11.0)]
+
+
+def test_rank_layout_dp_cfg_tp():
+    """rank = (dp * cfg + c) * tp + t  (the reference's "tp-sp-pp-cfg-dp" order, parallel_state.py:659)."""
+    st = ps._STATE
+    saved = (st.rank, st.tp_size, st.cfg_size, st.dp_size)
+    try:
+        st.tp_size, st.cfg_size, st.dp_size = 2, 2, 2
+        seen = set()
+        for r in range(8):
+            st.rank = r
+            seen.add((ps.get_data_parallel_rank(), ps.get_cfg_parallel_rank(), ps.get_tensor_model_parallel_rank()))
+        assert seen == {(d, c, t) for d in range(2) for c in range(2) for t in range(2)}
+        st.rank = 5
+        assert (ps.get_data_parallel_rank(), ps.get_cfg_parallel_rank(), ps.get_tensor_model_parallel_rank()) == (1, 0, 1)
+    finally:
+        st.rank, st.tp_size, st.cfg_size, st.dp_size = saved

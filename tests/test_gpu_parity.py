@@ -401,3 +401,10 @@ def test_tp2_matches_single_gpu(comm):
     the unsharded engine (the reference's SP-vs-baseline tolerance, test_ulysses_sequence_parallel.py:332-343)."""
     out = _torchrun("tp_check.py", 2, env={"TP_COMM": comm, "TP_LAYERS": "2", "TP_RES": "512"})
     assert "rel_fro" in out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_cfg_parallel_bit_equal_to_sequential():
+    """Positive / negative branch on two GPUs + one all-gather per step == the sequential two-forward path, bit for bit."""
+    out = _torchrun("cfg_check.py", 2)
+    assert "bit-equal to sequential = True" in out

@@ -6,6 +6,9 @@ reference's "tp-sp-pp-cfg-dp" string (:659): TP ranks are adjacent, DP is the ou
   * DP (data parallel over images): independent units, NO collective on the data path; only the final
     gather of the [B/P, S_img, 64] latents to rank 0.  Not wired in the reference (groups only, :661-668).
   * TP group: kept for the tensor-parallel engine mode (all-reduce of row-parallel partial sums).
+  * CFG group (size 1 or 2): with true-CFG on, the conditional and unconditional forwards of a step are independent;
+    rank 0 of the group runs the positive branch, rank 1 the negative one, and one all-gather of the [B,S_img,64]
+    noise predictions per step lets both apply the same fused combine + Euler step (SURVEY §8e "CFG parallel").
 """
 from __future__ import annotations
 
@@ -22,8 +25,10 @@ class _State:
     rank: int = 0
     dp_size: int = 1
     tp_size: int = 1
+    cfg_size: int = 1
     dp_group: "dist.ProcessGroup | None" = None
     tp_group: "dist.ProcessGroup | None" = None
+    cfg_group: "dist.ProcessGroup | None" = None
 
 
 _STATE = _State()
@@ -48,26 +53,36 @@ def init_distributed_environment(world_size: int = -1, rank: int = -1, backend: 
 
 
 def initialize_model_parallel(data_parallel_size: int = 1, tensor_parallel_size: int = 1, backend: str | None = None,
-                              **unused_reference_kwargs):
-    """reference parallel_state.py:563-713 (only the DP and TP groups are created; PP/CFG/SP groups are dead
-    scaffolding for this model — SURVEY §2b)."""
+                              cfg_parallel_size: int = 1, **unused_reference_kwargs):
+    """reference parallel_state.py:563-713 (DP, CFG and TP groups are created; PP/SP groups are dead scaffolding for
+    this model — SURVEY §2b).  rank = (dp * cfg_size + cfg) * tp_size + tp, the reference's "tp-sp-pp-cfg-dp" order."""
     ws = dist.get_world_size() if dist.is_initialized() else 1
-    if data_parallel_size * tensor_parallel_size != ws:
-        raise ValueError(f"dp({data_parallel_size}) * tp({tensor_parallel_size}) != world_size({ws})")
-    _STATE.dp_size, _STATE.tp_size = data_parallel_size, tensor_parallel_size
+    if cfg_parallel_size not in (1, 2):
+        raise ValueError("cfg_parallel_size must be 1 or 2 (positive / negative branch)")
+    if data_parallel_size * cfg_parallel_size * tensor_parallel_size != ws:
+        raise ValueError(f"dp({data_parallel_size}) * cfg({cfg_parallel_size}) * tp({tensor_parallel_size}) != world_size({ws})")
+    _STATE.dp_size, _STATE.tp_size, _STATE.cfg_size = data_parallel_size, tensor_parallel_size, cfg_parallel_size
     rank = dist.get_rank() if dist.is_initialized() else 0
     if ws == 1:
         return
-    for d in range(data_parallel_size):  # TP groups: adjacent ranks
-        ranks = list(range(d * tensor_parallel_size, (d + 1) * tensor_parallel_size))
+    tp, cfg = tensor_parallel_size, cfg_parallel_size
+    for o in range(data_parallel_size * cfg):  # TP groups: adjacent ranks
+        ranks = list(range(o * tp, (o + 1) * tp))
         g = dist.new_group(ranks, backend=backend)
         if rank in ranks:
             _STATE.tp_group = g
-    for t in range(tensor_parallel_size):  # DP groups: stride tp
-        ranks = list(range(t, ws, tensor_parallel_size))
-        g = dist.new_group(ranks, backend=backend)
-        if rank in ranks:
-            _STATE.dp_group = g
+    for d in range(data_parallel_size):  # CFG groups: stride tp inside one DP replica
+        for t in range(tp):
+            ranks = [(d * cfg + c) * tp + t for c in range(cfg)]
+            g = dist.new_group(ranks, backend=backend)
+            if rank in ranks:
+                _STATE.cfg_group = g
+    for c in range(cfg):  # DP groups: stride cfg * tp
+        for t in range(tp):
+            ranks = [(d * cfg + c) * tp + t for d in range(data_parallel_size)]
+            g = dist.new_group(ranks, backend=backend)
+            if rank in ranks:
+                _STATE.dp_group = g
 
 
 def get_world_size() -> int:
@@ -79,7 +94,26 @@ def get_data_parallel_world_size() -> int:
 
 
 def get_data_parallel_rank() -> int:
-    return _STATE.rank // _STATE.tp_size
+    return _STATE.rank // (_STATE.tp_size * _STATE.cfg_size)
+
+
+def get_cfg_parallel_world_size() -> int:
+    return _STATE.cfg_size
+
+
+def get_cfg_parallel_rank() -> int:
+    return (_STATE.rank // _STATE.tp_size) % _STATE.cfg_size
+
+
+def get_cfg_group():
+    return _STATE.cfg_group
+
+
+def cfg_all_gather(local: torch.Tensor) -> list[torch.Tensor]:
+    """[positive, negative] noise predictions on both ranks of the CFG group (one exchange per denoise step)."""
+    bufs = [torch.empty_like(local) for _ in range(_STATE.cfg_size)]
+    dist.all_gather(bufs, local.contiguous(), group=_STATE.cfg_group)
+    return bufs
 
 
 def get_tensor_model_parallel_world_size() -> int:

@@ -23,6 +23,7 @@ import torch.nn as nn
 
 from vllm_omni_b200 import lib as qlib
 from vllm_omni_b200.diffusion.data import DiffusionOutput, OmniDiffusionConfig
+from vllm_omni_b200.diffusion.distributed import parallel_state as _ps
 from vllm_omni_b200.diffusion.models.qwen_image.qwen_image_transformer import QwenImageTransformer2DModel
 from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
 
@@ -197,6 +198,11 @@ class QwenImagePipeline(nn.Module):
         # computed once for all steps; one row per step, shared by the whole batch.
         t_dev = (timesteps.to(torch.bfloat16) / 1000).to(dev).contiguous()
         self.transformer.do_true_cfg = do_true_cfg
+        # CFG parallel: rank 0 of the CFG group runs the positive branch, rank 1 the negative one
+        cfg_par = do_true_cfg and _ps.get_cfg_parallel_world_size() == 2
+        cfg_rank = _ps.get_cfg_parallel_rank() if cfg_par else 0
+        if cfg_par and cfg_rank == 1:
+            prompt_embeds, prompt_embeds_mask, txt_seq_lens = negative_prompt_embeds, negative_prompt_embeds_mask, negative_txt_seq_lens
         for i in range(len(timesteps)):
             if self.interrupt:
                 continue
@@ -206,7 +212,9 @@ class QwenImagePipeline(nn.Module):
                 encoder_hidden_states_mask=prompt_embeds_mask, encoder_hidden_states=prompt_embeds, img_shapes=img_shapes,
                 txt_seq_lens=txt_seq_lens, attention_kwargs=self.attention_kwargs, return_dict=False, uniform_timestep=True)[0]
             neg_noise_pred = None
-            if do_true_cfg:
+            if cfg_par:
+                noise_pred, neg_noise_pred = _ps.cfg_all_gather(noise_pred)
+            elif do_true_cfg:
                 neg_noise_pred = self.transformer(
                     hidden_states=latents, timestep=t_dev[i:i + 1], guidance=guidance,
                     encoder_hidden_states_mask=negative_prompt_embeds_mask, encoder_hidden_states=negative_prompt_embeds,

@@ -81,7 +81,8 @@ class GPUWorker:
             if world_size > 1:
                 ps.init_distributed_environment(world_size=world_size, rank=self.rank)
             pc = self.od_config.parallel_config
-            ps.initialize_model_parallel(data_parallel_size=pc.data_parallel_size, tensor_parallel_size=pc.tensor_parallel_size)
+            ps.initialize_model_parallel(data_parallel_size=pc.data_parallel_size, tensor_parallel_size=pc.tensor_parallel_size,
+                                         cfg_parallel_size=pc.cfg_parallel_size)
             t0 = time.perf_counter()
             prev = torch.get_default_dtype()
             torch.set_default_dtype(self.od_config.dtype)
