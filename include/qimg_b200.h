@@ -134,6 +134,11 @@ int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_s
  * backends/sdpa.py:46-66) and the cat/split around it (qwen_image_transformer.py:414-416,448-449). */
 int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
                     int T, float softmax_scale, qimg_stream_t stream);
+/* Diagnostics: when set to a device buffer of 32 int64, attention pipelines 0 and 4 (fmha mode & 7) record the cycle
+ * counters of CTA 200: [0] MMA-warp loop, [1..4] its waits on K, P1, V, P0, [5] KV tiles; [8..14] / [16..22] tile-0 /
+ * tile-1 softmax warp: loop, wait on S, score load (+ max in pipeline 4), max (pair barrier in 4), ping-pong barrier,
+ * exponentials + P stores, tail (store wait, fence, arrive).  NULL disables. */
+int qimg_set_fmha_trace(void* dev_buf_32_i64);
 
 /* ---- whole-model engine ------------------------------------------------------------- */
 typedef struct qimg_dims {

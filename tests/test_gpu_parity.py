@@ -52,7 +52,7 @@ def test_library_loaded_and_device():
     assert os.path.exists(q.LIB_PATH)
 
 
-@pytest.fixture(params=[0, 1, 2, 3, 4, 16, 9, 40, 44], ids=["kv128", "kv64dbuf", "kv80decoupled", "kv64decoupled", "kv128-2thr", "kv128-poly37", "kv64dbuf-poly25", "kv128-poly25-pingpong", "kv128-2thr-poly25-pingpong"])
+@pytest.fixture(params=[0, 1, 2, 3, 4, 16, 9, 40, 44, 5, 45, 6, 46], ids=["kv128", "kv64dbuf", "kv80decoupled", "kv64decoupled", "kv128-2thr", "kv128-poly37", "kv64dbuf-poly25", "kv128-poly25-pingpong", "kv128-2thr-poly25-pingpong", "kv128-delayedmax", "kv128-delayedmax-poly25-pingpong", "kv128-2thr-delayedmax", "kv128-2thr-delayedmax-poly25-pingpong"])
 def fmha_mode(request):
     """Both attention pipelines (first-generation 128-row KV tiles / double-buffered 64-row KV tiles)."""
     prev = q.get_fmha_mode()

@@ -13,7 +13,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libqimg_b200.so")
 SOURCES = ["qimg_api.cu", "qimg_engine.cu", "qimg_tp_p2p.cu"]
-HEADERS = ["qimg_common.cuh", "qimg_elementwise.cuh", "qimg_gemm.cuh", "qimg_gemm2.cuh", "qimg_fmha.cuh", "qimg_fmha2.cuh", "qimg_fmha3.cuh", "qimg_fmha4.cuh", "qimg_host.cuh",
+HEADERS = ["qimg_common.cuh", "qimg_elementwise.cuh", "qimg_gemm.cuh", "qimg_gemm2.cuh", "qimg_fmha.cuh", "qimg_fmha2.cuh", "qimg_fmha3.cuh", "qimg_fmha4.cuh", "qimg_fmha5.cuh", "qimg_fmha6.cuh", "qimg_host.cuh",
            os.path.join("..", "..", "include", "qimg_b200.h")]
 
 
@@ -37,6 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "--use_fast_math" if os.environ.get("QIMG_FAST_MATH") else "-DQIMG_NO_FAST_MATH",
+           *(["-DQIMG_FMHA_TRACE"] if os.environ.get("QIMG_FMHA_TRACE") else []),
+           *(["-DQIMG_FMHA_NOCLAMP"] if os.environ.get("QIMG_FMHA_NOCLAMP") else []),  # experiment only
            "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -10,6 +10,8 @@
 #include "qimg_fmha2.cuh"
 #include "qimg_fmha3.cuh"
 #include "qimg_fmha4.cuh"
+#include "qimg_fmha5.cuh"
+#include "qimg_fmha6.cuh"
 #include "qimg_gemm.cuh"
 #include "qimg_gemm2.cuh"
 #include "qimg_host.cuh"
@@ -361,6 +363,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 }  // namespace qimg
 
+static long long* g_fmha_trace = nullptr;  // qimg_set_fmha_trace (diagnostics)
 using namespace qimg;
 
 template <uint32_t MASK>
@@ -372,6 +375,10 @@ static int launch_fmha_inst(int pipeline, bool pingpong, const CUtensorMap* tq, 
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v7<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v7<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v8<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v8<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v9<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v9<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmha3_smem_bytes<80>()));
     QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmha3_smem_bytes<64>()));
@@ -379,7 +386,13 @@ static int launch_fmha_inst(int pipeline, bool pingpong, const CUtensorMap* tq, 
   }
   const int pairs = (prm.S + 255) / 256;
   const dim3 grid2(pairs, prm.B * prm.H);
-  if (pipeline == 4) {
+  if (pipeline == 6) {
+    if (pingpong) fmha_joint_kernel_v9<MASK, true><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+    else fmha_joint_kernel_v9<MASK, false><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  } else if (pipeline == 5) {
+    if (pingpong) fmha_joint_kernel_v8<MASK, true><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+    else fmha_joint_kernel_v8<MASK, false><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  } else if (pipeline == 4) {
     if (pingpong) fmha_joint_kernel_v7<MASK, true><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
     else fmha_joint_kernel_v7<MASK, false><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   } else if (pipeline == 2) fmha_joint_kernel_v6<MASK, 80><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<80>(), st>>>(*tq, *tk, *tv, prm);
@@ -549,16 +562,22 @@ static int g_fmha_mode = -1;
 static int fmha_mode() {
   if (g_fmha_mode < 0) {
     const char* e = getenv("QIMG_FMHA_MODE");
-    g_fmha_mode = e ? atoi(e) : 40;  // 128-row KV tiles + 25 % polynomial exp2 + softmax ping-pong (best of the sweep, profiles/)
+    g_fmha_mode = e ? atoi(e) : 6;  // two threads per row, delayed reference maximum, half-tile P hand-off (best of the sweep, profiles/)
   }
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode < 0 || mode > 63 || (mode & 7) > 4) return fail("qimg_set_fmha_mode: bad mode");
+  if (mode < 0 || mode > 63 || (mode & 7) > 6) return fail("qimg_set_fmha_mode: bad mode");
   g_fmha_mode = mode;
   return 0;
 }
 int qimg_get_fmha_mode(void) { return fmha_mode(); }
+
+int qimg_set_fmha_trace(void* dev_buf_32_i64) {
+  if (dev_buf_32_i64 && !kFmhaTrace) return fail("qimg_set_fmha_trace: library built without -DQIMG_FMHA_TRACE");
+  g_fmha_trace = (long long*)dev_buf_32_i64;
+  return 0;
+}
 
 int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
                     int T, float softmax_scale, qimg_stream_t stream) {
@@ -575,6 +594,7 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   prm.out_img = (bf16*)out_img;
   prm.B = B; prm.H = H; prm.S = S; prm.T = T;
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
+  prm.trace = g_fmha_trace;
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
   const bool pp = (mode & 32) != 0;  // strict alternation of the two softmax warpgroups' exp phases (pipeline 0)
   switch ((mode >> 3) & 3) {         // share of the exponentials on the FMA-pipe polynomial: 0 / 25 / 37.5 / 50 %

@@ -24,6 +24,14 @@
 
 namespace qimg {
 
+// Cycle tracing (qimg_set_fmha_trace, tools/fmha_trace.py) is compiled in only with -DQIMG_FMHA_TRACE
+// (QIMG_FMHA_TRACE=1 python -m vllm_omni_b200.build): the counters cost registers in the softmax warps.
+#ifdef QIMG_FMHA_TRACE
+constexpr bool kFmhaTrace = true;
+#else
+constexpr bool kFmhaTrace = false;
+#endif
+
 constexpr int FMHA_THREADS = 320;
 constexpr int FMHA_KS = 2;
 constexpr int FMHA_VS = 2;
@@ -35,6 +43,7 @@ struct FmhaParams {
   bf16* out_img;  // [B*S_img, H*128]
   int B, H, S, T;
   float scale_log2;  // softmax_scale * log2(e)
+  long long* trace;  // optional (qimg_set_fmha_trace): per-phase cycle counters of CTA 200 (pipelines 0 and 4)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -215,10 +224,15 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 (accumulate || k != 0) ? 1u : 0u);
       }
     };
+    const bool tr = kFmhaTrace && prm.trace != nullptr && blockIdx.x == 200;
+    long long w_k = 0, w_p1 = 0, w_v = 0, w_p0 = 0, tt = 0;
     mbar_wait(q_full, 0);
+    const long long t_begin = kFmhaTrace ? clock64() : 0;
     for (int j = 0; j < n_kv; ++j) {
       const int ks = j % FMHA_KS;
+      if (tr) tt = clock64();
       mbar_wait(&k_full[ks], (j / FMHA_KS) & 1);
+      if (tr) w_k += clock64() - tt;
       tc_fence_after();
       if (elect_one()) {
         issue_qk(0, ks);
@@ -226,7 +240,9 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       __syncwarp();
       if (two && j > 0) {
+        if (tr) tt = clock64();
         mbar_wait(&p_ready[1], (j - 1) & 1);
+        if (tr) w_p1 += clock64() - tt;
         tc_fence_after();
         if (elect_one()) issue_pv(1, (j - 1) % FMHA_VS, j - 1 > 0);
         __syncwarp();
@@ -241,8 +257,11 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       __syncwarp();
       const int vs = j % FMHA_VS;
+      if (tr) tt = clock64();
       mbar_wait(&v_full[vs], (j / FMHA_VS) & 1);
+      if (tr) w_v += clock64() - tt, tt = clock64();
       mbar_wait(&p_ready[0], j & 1);
+      if (tr) w_p0 += clock64() - tt;
       tc_fence_after();
       if (elect_one()) issue_pv(0, vs, j > 0);
       __syncwarp();
@@ -258,6 +277,14 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       umma_commit(&o_full[1]);
     }
     __syncwarp();
+    if (tr && lane == 0) {
+      prm.trace[0] = clock64() - t_begin;
+      prm.trace[1] = w_k;
+      prm.trace[2] = w_p1;
+      prm.trace[3] = w_v;
+      prm.trace[4] = w_p0;
+      prm.trace[5] = n_kv;
+    }
   } else {
     // ===================== softmax / correction / output warps =====================
     const int t = (warp - 2) >> 2;  // query tile handled by this warpgroup
@@ -275,8 +302,13 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // XU throughput and then both waiting for the tensor pipe.  Alternation keeps tile 0's softmax under
     // tile 1's MMAs and vice versa (the issue order QK0 PV1 QK1 PV0 assumes exactly that).
     if (pingpong && t == 1) named_bar_arrive(1, 256);
+    const bool tr = kFmhaTrace && prm.trace != nullptr && blockIdx.x == 200 && q == 0;
+    long long w_s = 0, w_ld = 0, w_mx = 0, w_pp = 0, w_ex = 0, w_tl = 0, tt = 0;
+    const long long t_begin = kFmhaTrace ? clock64() : 0;
     for (int j = 0; j < n_kv; ++j) {
+      if (tr) tt = clock64();
       mbar_wait(&s_full[t], j & 1);
+      if (tr) w_s += clock64() - tt, tt = clock64();
       tc_fence_after();
       const int kv_valid = prm.S - j * 128;  // < 128 only on a ragged last tile
       // The body is instantiated twice; only the ragged last KV tile pays for the 128 compare/selects
@@ -288,6 +320,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   #pragma unroll
         for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(tS + cc * 32, r + cc * 32);
         tmem_ld_wait();
+        if (tr) w_ld += clock64() - tt, tt = clock64();
         if (MASKED) {
   #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -326,7 +359,9 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
         // ---- P = exp2(s*c - m*c) (masked columns give exp2(-inf) = 0), row sum, bf16 P -> TMEM ----
+        if (tr) w_mx += clock64() - tt, tt = clock64();
         if (pingpong) named_bar_sync(1 + t, 256);  // my turn on the XU pipe
+        if (tr) w_pp += clock64() - tt, tt = clock64();
         const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_used * c);
         uint64_t la = 0, lb = 0;  // two packed partial row sums (bit pattern 0 = +0.0f pairs)
   #pragma unroll
@@ -351,6 +386,7 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
           tmem_st_32x32b_x16(tS + cc * 16, pk);
         }
+        if (tr) w_ex += clock64() - tt, tt = clock64();
         if (pingpong && !(t == 1 && j == n_kv - 1)) named_bar_arrive(1 + (t ^ 1), 256);  // hand the XU pipe over
         {
           uint32_t a0, a1, b0, b1;
@@ -365,6 +401,17 @@ fmha_joint_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[t]);
+      if (tr) w_tl += clock64() - tt;
+    }
+    if (tr && lane == 0) {
+      long long* o = prm.trace + 8 + t * 8;
+      o[0] = clock64() - t_begin;
+      o[1] = w_s;
+      o[2] = w_ld;
+      o[3] = w_mx;
+      o[4] = w_pp;
+      o[5] = w_ex;
+      o[6] = w_tl;
     }
     // ---- final: O / l -> bf16 -> smem (this tile's Q buffer is free now) -> coalesced stores ----
     mbar_wait(&o_full[t], 0);

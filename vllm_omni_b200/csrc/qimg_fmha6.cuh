@@ -1,23 +1,30 @@
-// Joint attention, 128-row KV tiles, TWO softmax threads per query row (FMHA "v7").
-// Same TMA / MMA structure, TMEM map (S0|S1|O0|O1, P aliases S) and issue order as fmha_joint_kernel
-// (qimg_fmha.cuh); only the softmax side differs: 16 softmax warps, each thread owns 64 of the 128 score columns
-// of its row.  Motivation (profiles/r01_ncu_fmha_final.csv and the v4 source-level samples): with one thread per
-// row a softmax step took ~2100 cycles, ~1000 of them XU-serial (128 MUFU.EX2 x 8 cycles per warp) and ~1000
-// latency-bound FMNMX/F2FP/TMEM work that a single warp per scheduler cannot overlap with its own MUFUs.
+// Joint attention, 128-row KV tiles, two softmax threads per query row, DELAYED reference maximum and half-tile P
+// hand-off (FMHA "v9").  Derived from fmha_joint_kernel_v7 (qimg_fmha4.cuh: same TMA side, TMEM map, P/S aliasing rules).
+//
+// Cycle traces (tools/fmha_trace.py) show the KV-tile period of v4/v7 is one serial chain per query tile:
+//   QK -> [S visible] -> score load -> row max (+ exchange) -> exponentials -> P stores -> [P visible] -> PV -> next QK,
+// T = X + 2 MMA, with the tensor pipe idle ~900-1100 cycles per KV tile waiting for tile 0's P.  v9 shortens X:
+//   1. Softmax is shift-invariant, so tile j >= 1 is exponentiated against the reference the row already has (the lazily
+//      updated maximum over tiles < j) in ONE pass over the scores, 16 columns at a time; the tile's own maximum is
+//      reduced on the side (FMNMX3 under the MUFU-bound exponentials) and only decides, at the start of tile j+1 and
+//      after the two threads of a row have exchanged their halves' maxima, whether O and l are rebased (threshold 2^8).
+//      Tile 0 still reduces its maximum first (two passes, as v7).  Exponents are clamped at 2^96 so l and O stay finite
+//      when a tile's maximum jumps far above the reference (a jump of more than 66 nats inside one tile loses the
+//      relative weights of the clamped entries; pipelines 0-4 remain exact for such inputs).
+//   2. Each thread releases its P in two halves (mbarrier per (tile, half)); P*V of the first 4 k-steps runs while the
+//      second half is exponentiated, so only half a P*V stays on the chain.
 #pragma once
 
 #include <type_traits>
 
-#include "qimg_fmha.cuh"
+#include "qimg_fmha4.cuh"
 
 namespace qimg {
 
-constexpr int FMHA4_THREADS = 32 * (2 + 16);
-constexpr int FMHA4_SMEM_BYTES = FMHA_SMEM_BYTES + 4096;
 
 template <uint32_t POLY_MASK, bool PINGPONG>
 __global__ void __launch_bounds__(FMHA4_THREADS, 1)
-fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -31,8 +38,8 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* v_full = k_empty + FMHA_KS;
   uint64_t* v_empty = v_full + FMHA_VS;
   uint64_t* s_full = v_empty + FMHA_VS;  // [2]
-  uint64_t* p_ready = s_full + 2;        // [2]
-  uint64_t* o_full = p_ready + 2;        // [2]
+  uint64_t* p_ready = s_full + 2;        // [2 tiles][2 halves]
+  uint64_t* o_full = p_ready + 4;        // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
   float* xch = reinterpret_cast<float*>(o_full + 4);  // [tile][parity][half][128 rows] partial row maxima (4 KB)
 
@@ -70,9 +77,9 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 8);
       mbar_init(&o_full[i], 1);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -122,18 +129,31 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         umma_ss(tS[t], make_kmajor_sw128_desc(qa + off), make_kmajor_sw128_desc(ka + off), IDESC_QK, k != 0);
       }
     };
-    auto issue_pv = [&](int t, int vs, bool accumulate) {
-      const uint32_t va = smem_u32(sV + vs * FMHA_TILE_BYTES);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        // A = P (bf16 pairs, 8 TMEM columns per K=16 step); B = V rows [16k, 16k+16) x 128 (MN-major)
-        // (P sits 32 columns into the S tile: see the softmax warps' aliasing note)
-        umma_ts(tO[t], tS[t] + 32 + k * 8, make_mnmajor_sw128_desc(va + k * 2048, 16384), IDESC_PV,
-                (accumulate || k != 0) ? 1u : 0u);
-      }
-    };
     const bool tr = kFmhaTrace && prm.trace != nullptr && blockIdx.x == 200;
     long long w_k = 0, w_p1 = 0, w_v = 0, w_p0 = 0, tt = 0;
+    // P*V of KV tile jj for query tile t in two halves, as the softmax threads release them: the hh=0 threads walk
+    // their chunks downwards and the hh=1 threads upwards (P/S aliasing, see below), so the first half holds k-steps
+    // {3,2,4,5} and the second {1,0,6,7}
+    auto pv_halves = [&](int t, int jj, long long& waited) {
+      const uint32_t va = smem_u32(sV + (jj % FMHA_VS) * FMHA_TILE_BYTES);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        long long t0 = 0;
+        if (tr) t0 = clock64();
+        mbar_wait(&p_ready[t * 2 + hf], jj & 1);
+        if (tr) waited += clock64() - t0;
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = hf == 0 ? (i < 2 ? 3 - i : 2 + i) : (i < 2 ? 1 - i : 4 + i);
+            umma_ts(tO[t], tS[t] + 32 + k * 8, make_mnmajor_sw128_desc(va + k * 2048, 16384), IDESC_PV,
+                    (jj > 0 || hf != 0 || i != 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      }
+    };
     mbar_wait(q_full, 0);
     const long long t_begin = kFmhaTrace ? clock64() : 0;
     for (int j = 0; j < n_kv; ++j) {
@@ -147,14 +167,7 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         umma_commit(&s_full[0]);
       }
       __syncwarp();
-      if (two && j > 0) {
-        if (tr) tt = clock64();
-        mbar_wait(&p_ready[1], (j - 1) & 1);
-        if (tr) w_p1 += clock64() - tt;
-        tc_fence_after();
-        if (elect_one()) issue_pv(1, (j - 1) % FMHA_VS, j - 1 > 0);
-        __syncwarp();
-      }
+      if (two && j > 0) pv_halves(1, j - 1, w_p1);
       if (elect_one()) {
         if (j > 0) umma_commit(&v_empty[(j - 1) % FMHA_VS]);  // V(j-1): PV0(j-1) and PV1(j-1) are both issued
         if (two) {
@@ -164,22 +177,13 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         umma_commit(&k_empty[ks]);
       }
       __syncwarp();
-      const int vs = j % FMHA_VS;
       if (tr) tt = clock64();
-      mbar_wait(&v_full[vs], (j / FMHA_VS) & 1);
-      if (tr) w_v += clock64() - tt, tt = clock64();
-      mbar_wait(&p_ready[0], j & 1);
-      if (tr) w_p0 += clock64() - tt;
-      tc_fence_after();
-      if (elect_one()) issue_pv(0, vs, j > 0);
-      __syncwarp();
+      mbar_wait(&v_full[j % FMHA_VS], (j / FMHA_VS) & 1);
+      if (tr) w_v += clock64() - tt;
+      pv_halves(0, j, w_p0);
     }
-    if (two) {
-      mbar_wait(&p_ready[1], (n_kv - 1) & 1);
-      tc_fence_after();
-    }
+    if (two) pv_halves(1, n_kv - 1, w_p1);
     if (elect_one()) {
-      if (two) issue_pv(1, (n_kv - 1) % FMHA_VS, n_kv - 1 > 0);
       umma_commit(&v_empty[(n_kv - 1) % FMHA_VS]);
       umma_commit(&o_full[0]);
       umma_commit(&o_full[1]);
@@ -216,8 +220,9 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tP = tmem_base + lane_off + t * 128 + 32 + hh * 32;   // my 32 packed P columns
     const uint32_t tO = tmem_base + lane_off + 256 + t * 128 + hh * 64;
     const float c = prm.scale_log2;
-    float m_used = -INFINITY;
-    float l = 0.f;  // partial row sum over my column half
+    float m_ref = 0.f;  // reference (raw score units) the exponentials of the current tile are taken against
+    float l = 0.f;      // partial row sum over my column half, relative to m_ref
+    float my_tile_max = -INFINITY;  // maximum of my 64 columns of the previous tile (exchanged at the next tile's start)
     if (pingpong && t == 1) named_bar_arrive(9, 512);
     const bool tr = kFmhaTrace && prm.trace != nullptr && blockIdx.x == 200 && hh == 0 && q == 0;
     long long w_s = 0, w_ld = 0, w_x = 0, w_pp = 0, w_ex = 0, w_tl = 0, tt = 0;
@@ -232,44 +237,47 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float* other_x = xch + ((t * 2 + (j & 1)) * 2 + (hh ^ 1)) * 128 + row;
       auto softmax_tile = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-        // ---- pass 1: partial row maximum over my 64 score columns (the scores are NOT kept in registers: with 18 warps
-        // the per-thread budget is 96 registers, and holding 64 scores + 16 packed P words across the exp phase spilled
-        // ~100 words per thread per tile; TMEM reads are cheap, so pass 2 reads the scores again in 16-column chunks) ----
-        float part;
-        {
-          uint32_t r[64];
-          tmem_ld_32x32b_x32(tS, r);
-          tmem_ld_32x32b_x32(tS + 32, r + 32);
-          tmem_ld_wait();
-          if (MASKED) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (i >= kv_valid) r[i] = 0xff800000u;  // -inf
-          }
-          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 64; i += 8) {
-            mx0 = max3_f32(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-            mx1 = max3_f32(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-            mx2 = max3_f32(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-            mx3 = max3_f32(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
-          }
-          part = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        }
-        *my_x = part;
         uint32_t ra[16], rb[16];
-        tmem_ld_32x32b_x16(tS + (hh ? 0 : 48), ra);  // first chunk of pass 2: its latency hides behind the exchange barrier
-        if (tr) w_ld += clock64() - tt, tt = clock64();
-        named_bar_sync(pair_bar, 64);  // partner's partial maximum is visible (buffers alternate with j)
-        if (tr) w_x += clock64() - tt, tt = clock64();
-        const float mx = fmaxf(part, *other_x);
         if (j == 0) {
-          m_used = mx;
+          // ---- first tile: no reference yet -> reduce the row maximum first (as v7), then exponentiate ----
+          float part;
+          {
+            uint32_t r[64];
+            tmem_ld_32x32b_x32(tS, r);
+            tmem_ld_32x32b_x32(tS + 32, r + 32);
+            tmem_ld_wait();
+            if (MASKED) {
+#pragma unroll
+              for (int i = 0; i < 64; ++i)
+                if (i >= kv_valid) r[i] = 0xff800000u;  // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+              mx0 = max3_f32(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+              mx1 = max3_f32(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+              mx2 = max3_f32(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+              mx3 = max3_f32(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+            }
+            part = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+          }
+          *my_x = part;
+          tmem_ld_32x32b_x16(tS + (hh ? 0 : 48), ra);
+          named_bar_sync(pair_bar, 64);
+          m_ref = fmaxf(part, *other_x);
         } else {
-          const float m_new = fmaxf(m_used, mx);
-          const bool need = (m_new - m_used) * c > 8.0f;  // identical in both warps of the pair (same rows, same mx)
+          // ---- later tiles: start loading right away; meanwhile agree with the partner thread on the previous tile's
+          // row maximum and rebase O / l if it rose by more than 2^8 (P*V(j-1) of this tile is complete: s_full(j)
+          // was committed after it in the in-order tensor pipe) ----
+          tmem_ld_32x32b_x16(tS + (hh ? 0 : 48), ra);
+          *my_x = my_tile_max;
+          if (tr) w_ld += clock64() - tt, tt = clock64();
+          named_bar_sync(pair_bar, 64);
+          if (tr) w_x += clock64() - tt, tt = clock64();
+          const float m_new = fmaxf(m_ref, fmaxf(my_tile_max, *other_x));
+          const bool need = (m_new - m_ref) * c > 8.0f;  // identical in both warps of the pair (same rows, same maxima)
           if (__any_sync(0xffffffffu, need)) {
-            const float f = ex2_approx((m_used - m_new) * c);
+            const float f = need ? ex2_approx((m_ref - m_new) * c) : 1.0f;
             l *= f;
 #pragma unroll 1
             for (int cc = 0; cc < 4; ++cc) {  // my half of the O columns
@@ -281,14 +289,16 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               tmem_st_32x32b_x16(tO + cc * 16, o);
             }
             tmem_st_wait();
-            m_used = m_new;
+            if (need) m_ref = m_new;
           }
         }
         if (pingpong) named_bar_sync(9 + t, 512);
         if (tr) w_pp += clock64() - tt, tt = clock64();
-        const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_used * c);
+        const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_ref * c);
         uint64_t la = 0, lb = 0;
-        // ---- pass 2: exp2((s - m) c) -> bf16 P, 16 columns at a time, next chunk's TMEM load in flight ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        // ---- one pass: exp2((s - m_ref) c) -> bf16 P, 16 columns at a time, next chunk's TMEM load in flight; the
+        // chunk's maximum is reduced on the side.  P is released to the MMA warp in two halves. ----
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           uint32_t* cur = (ch & 1) ? rb : ra;
@@ -304,13 +314,19 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           uint32_t pk[8];
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t x = fma_f32x2(pack_f32x2(cur[2 * kk], cur[2 * kk + 1]), c2, nmc2);
+            if (kk & 1) mx1 = max3_f32(mx1, __uint_as_float(cur[2 * kk]), __uint_as_float(cur[2 * kk + 1]));
+            else mx0 = max3_f32(mx0, __uint_as_float(cur[2 * kk]), __uint_as_float(cur[2 * kk + 1]));
+            uint64_t x = fma_f32x2(pack_f32x2(cur[2 * kk], cur[2 * kk + 1]), c2, nmc2);
+            uint32_t xl, xh;
+            unpack_f32x2(x, xl, xh);
+#ifndef QIMG_FMHA_NOCLAMP
+            xl = __float_as_uint(fminf(__uint_as_float(xl), 96.0f));  // see header: keeps l and O finite
+            xh = __float_as_uint(fminf(__uint_as_float(xh), 96.0f));
+#endif
             uint64_t p;
             if ((POLY_MASK >> kk) & 1u) {
-              p = exp2_poly_f32x2(x);
+              p = exp2_poly_f32x2(pack_f32x2(xl, xh));
             } else {
-              uint32_t xl, xh;
-              unpack_f32x2(x, xl, xh);
               p = pack_f32x2(__float_as_uint(ex2_approx(__uint_as_float(xl))), __float_as_uint(ex2_approx(__uint_as_float(xh))));
             }
             if (kk & 1) lb = add_f32x2(lb, p); else la = add_f32x2(la, p);
@@ -318,7 +334,17 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             unpack_f32x2(p, pl, ph);
             pk[kk] = pack_bf16x2(__uint_as_float(pl), __uint_as_float(ph));
           }
+          if (ch == 3) {  // release the first half (chunks of rounds 0 and 1): stored a whole round ago
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[t * 2 + 0]);
+          }
           tmem_st_32x32b_x8(tP + cidx * 8, pk);
+          if (ch == 1) {
+            // nothing to wait for yet: the release of this half is deferred to round 3 so that the store-completion
+            // wait never stalls the exponentials
+          }
         }
         if (tr) w_ex += clock64() - tt, tt = clock64();
         if (pingpong && !(t == 1 && j == n_kv - 1)) named_bar_arrive(9 + (t ^ 1), 512);
@@ -326,24 +352,25 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         unpack_f32x2(la, a0, a1);
         unpack_f32x2(lb, b0, b1);
         l += (__uint_as_float(a0) + __uint_as_float(a1)) + (__uint_as_float(b0) + __uint_as_float(b1));
+        my_tile_max = (j == 0) ? m_ref : fmaxf(mx0, mx1);
       };
       if (kv_valid < 64) softmax_tile(std::true_type{});
       else softmax_tile(std::false_type{});
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[t]);
+      if (lane == 0) mbar_arrive(&p_ready[t * 2 + 1]);
       if (tr) w_tl += clock64() - tt;
     }
     if (tr && lane == 0) {
       long long* o = prm.trace + 8 + t * 8;
       o[0] = clock64() - t_begin;
       o[1] = w_s;
-      o[2] = w_ld;   // pass 1: score loads + partial row maximum
-      o[3] = w_x;    // pair barrier (max exchange)
-      o[4] = w_pp;   // rescale check + ping-pong barrier
-      o[5] = w_ex;   // pass 2: exponentials, P stores
-      o[6] = w_tl;   // store wait, fence, arrive
+      o[2] = w_ld;   // first chunk load issue (+ two-pass maximum on tile 0)
+      o[3] = w_x;    // pair barrier (exchange of the previous tile's maxima)
+      o[4] = w_pp;   // rebase check + ping-pong barrier
+      o[5] = w_ex;   // exponentials, P stores, first-half release
+      o[6] = w_tl;   // store wait, fence, second-half release
     }
     // ---- final: combine the two partial row sums, O / l -> bf16 -> smem -> coalesced stores ----
     float* my_l = xch + ((t * 2 + 0) * 2 + hh) * 128 + row;           // xch is idle now (last use: max of tile n_kv-1,

@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "qimg_engine_workspace_bytes", "qimg_engine_forward", "qimg_engine_ws_offset_img", "qimg_engine_ws_offset_txt",
     "qimg_umma_probe", "qimg_prof_enable", "qimg_prof_collect", "qimg_set_gemm_mode", "qimg_get_gemm_mode", "qimg_set_fmha_mode", "qimg_get_fmha_mode", "qimg_gate_residual_bias", "qimg_engine_set_tp",
     "qimg_p2p_alloc", "qimg_p2p_free", "qimg_ipc_get_handle", "qimg_ipc_open_handle", "qimg_ipc_close_handle",
-    "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error",
+    "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error", "qimg_set_fmha_trace",
 ]
 
 
@@ -117,6 +117,7 @@ def load():
     lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.qimg_set_gemm_mode.argtypes = [i]
     lib.qimg_set_fmha_mode.argtypes = [i]
+    lib.qimg_set_fmha_trace.argtypes = [vp]
     lib.qimg_prof_enable.argtypes = [i]
     lib.qimg_prof_enable.restype = None
     lib.qimg_prof_collect.argtypes = [i, C.POINTER(C.c_double), C.POINTER(ll), C.POINTER(C.c_double)]
