@@ -31,6 +31,9 @@ CASES = {
     # depth: the reference's own bf16 path drifts from fp32 with depth (1.16e-2 at L=12), so at depth the
     # criterion is err(native, fp32) <= err(reference-bf16, fp32) + 1e-2 with both numbers recorded here
     "fullwidth_L12": dict(L=12, H=24, joint=3584, B=1, grid=(16, 16), T=32, seed=4),
+    # image-edit layout (pipeline_qwen_image_edit.py:602): noisy latents (8x6) followed by one condition image (4x6) on
+    # the sequence axis; two RoPE grids, text positions after the larger one
+    "tiny_edit_two_grids": dict(L=2, H=2, joint=256, B=2, grid=(8, 6), extra_grids=[(4, 6)], T=24, seed=5),
 }
 
 
@@ -46,7 +49,8 @@ def build_case(name: str, c: dict):
     wdict = dict(synthetic.synthetic_weights(c["L"], seed=c["seed"], dtype=torch.bfloat16, norm_jitter=0.1,
                                              num_heads=c["H"], joint_dim=c["joint"]))
     h, w_ = c["grid"]
-    S = h * w_
+    grids = [(1, h, w_)] + [(1, a, b) for a, b in c.get("extra_grids", [])]
+    S = sum(f * a * b for f, a, b in grids)
     g = torch.Generator().manual_seed(100 + c["seed"])
     hs = torch.randn((c["B"], S, 64), generator=g).bfloat16()
     eh = torch.randn((c["B"], c["T"], c["joint"]), generator=g).bfloat16()
@@ -63,8 +67,9 @@ def build_case(name: str, c: dict):
         ref = ref_shim.run_reference_model(
             model, od, hidden_states=hs.to(dt), encoder_hidden_states=eh.to(dt),
             encoder_hidden_states_mask=torch.ones(c["B"], c["T"], dtype=torch.long), timestep=timestep.to(dt),
-            img_shapes=[[(1, h, w_)]] * c["B"], txt_seq_lens=[c["T"]] * c["B"])
-        mine = O.model_forward(O.cast_weights(wdict, dt), dims, hs.to(dt), eh.to(dt), timestep.to(dt), (1, h, w_))
+            img_shapes=[list(grids)] * c["B"], txt_seq_lens=[c["T"]] * c["B"])
+        mine = O.model_forward(O.cast_weights(wdict, dt), dims, hs.to(dt), eh.to(dt), timestep.to(dt),
+                               grids if len(grids) > 1 else grids[0])
         err = O.rel_fro(mine, ref)
         print(f"[{name}] {dt_name}: restatement vs reference rel_fro = {err:.3e}  max|d| = {(mine.float()-ref.float()).abs().max():.3e}")
         assert err < (2e-6 if dt == torch.float32 else 2e-3), "oracle restatement deviates from the reference"

@@ -102,10 +102,17 @@ def ada_layer_norm(x: torch.Tensor, mod: torch.Tensor, eps: float):
     return y, gate.unsqueeze(1)
 
 
-def rope_tables(frame: int, height: int, width: int, txt_len: int, axes=(16, 56, 56), theta: float = 10000.0):
-    """QwenEmbedRope (qwen_image_transformer.py:179-285) with scale_rope=True for ONE
-    (frame,height,width) image: returns fp32 (img_cos, img_sin [F*H*W, 64], txt_cos, txt_sin [T, 64]).
-    cos/sin are the real/imag parts of torch.polar(1, angle) (:220)."""
+def rope_tables(frame, height: int = None, width: int = None, txt_len: int = None, axes=(16, 56, 56), theta: float = 10000.0):
+    """QwenEmbedRope (qwen_image_transformer.py:179-285) with scale_rope=True: returns fp32
+    (img_cos, img_sin [sum F*H*W, 64], txt_cos, txt_sin [T, 64]); cos/sin are the real/imag parts of
+    torch.polar(1, angle) (:220).  `frame, height, width` describe ONE image; alternatively pass a list of
+    (frame, height, width) grids as the first argument (image-edit pipelines: noisy latents followed by the condition
+    image(s), QwenEmbedRope.forward :222-260): the idx-th grid takes its frame positions from idx (:267), the tables are
+    concatenated along the sequence (:258) and the text positions start after the largest grid (:251-257)."""
+    if isinstance(frame, (list, tuple)) and len(frame) and isinstance(frame[0], (list, tuple)):
+        grids, txt_len = [tuple(g) for g in frame], (height if txt_len is None else txt_len)
+    else:
+        grids = [(frame, height, width)]
     def params(index, dim):
         freqs = torch.outer(index.float(), 1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float32).div(dim)))
         return freqs  # angles; polar(1, a) = cos a + i sin a
@@ -114,14 +121,17 @@ def rope_tables(frame: int, height: int, width: int, txt_len: int, axes=(16, 56,
     neg_index = torch.arange(4096).flip(0) * -1 - 1
     pos = [params(pos_index, d) for d in axes]
     neg = [params(neg_index, d) for d in axes]
-    # _compute_video_freqs (:262-285), idx = 0
-    f_frame = pos[0][0:frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
-    f_h = torch.cat([neg[1][-(height - height // 2):], pos[1][: height // 2]], dim=0)
-    f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
-    f_w = torch.cat([neg[2][-(width - width // 2):], pos[2][: width // 2]], dim=0)
-    f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
-    ang = torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1)
-    max_vid_index = max(height // 2, width // 2)  # (:251-254)
+    angs, max_vid_index = [], 0
+    for idx, (frame, height, width) in enumerate(grids):
+        # _compute_video_freqs (:262-285)
+        f_frame = pos[0][idx: idx + frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
+        f_h = torch.cat([neg[1][-(height - height // 2):], pos[1][: height // 2]], dim=0)
+        f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
+        f_w = torch.cat([neg[2][-(width - width // 2):], pos[2][: width // 2]], dim=0)
+        f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
+        angs.append(torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1))
+        max_vid_index = max(height // 2, width // 2, max_vid_index)  # (:251-254)
+    ang = torch.cat(angs, dim=0)
     txt_ang = torch.cat(pos, dim=1)[max_vid_index: max_vid_index + txt_len]  # (:257)
     # torch.polar(ones, a): real = cos a, imag = sin a in fp32
     return torch.cos(ang), torch.sin(ang), torch.cos(txt_ang), torch.sin(txt_ang)
@@ -215,7 +225,10 @@ def model_forward(w: dict, dims: DiTDims, hidden_states, encoder_hidden_states, 
     txt = F.linear(txt, w["txt_in.weight"], w["txt_in.bias"])
     temb = time_text_embed(w, timestep, dt)
     T = encoder_hidden_states.shape[1] if txt_len is None else txt_len
-    rope = rope_tables(*img_shape, T, axes=dims.axes_dims_rope)
+    if isinstance(img_shape[0], (list, tuple)):  # several grids per sample (edit pipelines)
+        rope = rope_tables([tuple(g) for g in img_shape], T, axes=dims.axes_dims_rope)
+    else:
+        rope = rope_tables(*img_shape, T, axes=dims.axes_dims_rope)
     inter = []
     for i in range(dims.num_layers):
         txt, img = block_forward(w, f"transformer_blocks.{i}.", dims, img, txt, temb, rope)
@@ -287,17 +300,21 @@ def euler_step(noise_pred: torch.Tensor, latents: torch.Tensor, sigma: torch.Ten
 
 
 def diffuse(w: dict, dims: DiTDims, latents, prompt_embeds, neg_prompt_embeds, sigmas: np.ndarray, img_shape,
-            true_cfg_scale: float = 4.0):
+            true_cfg_scale: float = 4.0, image_latents=None):
     """QwenImagePipeline.diffuse (pipeline_qwen_image.py:530-586).  `sigmas` has N+1 entries
-    (last = 0); timesteps = sigmas[:-1]*1000 in fp32."""
+    (last = 0); timesteps = sigmas[:-1]*1000 in fp32.  With `image_latents` [B,S2,64] it is
+    QwenImageEditPipeline.diffuse (pipeline_qwen_image_edit.py:574-639): the condition latents are appended on the
+    sequence axis every step (:600-602), `img_shape` lists both grids and only the first S1 rows of the prediction are
+    kept (:617,632)."""
     sig = torch.from_numpy(np.asarray(sigmas, dtype=np.float32))
     timesteps = sig[:-1] * 1000.0
     do_cfg = neg_prompt_embeds is not None
     for i, t in enumerate(timesteps):
         timestep = t.expand(latents.shape[0]).to(dtype=latents.dtype)  # (:552) rounds t to bf16 in bf16 mode
-        noise = model_forward(w, dims, latents, prompt_embeds, timestep / 1000, img_shape)
+        x_in = latents if image_latents is None else torch.cat([latents, image_latents], dim=1)
+        noise = model_forward(w, dims, x_in, prompt_embeds, timestep / 1000, img_shape)[:, : latents.shape[1]]
         if do_cfg:
-            neg = model_forward(w, dims, latents, neg_prompt_embeds, timestep / 1000, img_shape)
+            neg = model_forward(w, dims, x_in, neg_prompt_embeds, timestep / 1000, img_shape)[:, : latents.shape[1]]
             noise = cfg_combine(noise, neg, true_cfg_scale)
         latents = euler_step(noise, latents, sig[i], sig[i + 1])
     return latents

@@ -271,20 +271,21 @@ def test_fmha_large_scores_lazy_rescale(fmha_mode):
     assert not torch.isnan(got).any() and O.rel_fro(got, ref) < 2e-2
 
 
-@pytest.mark.parametrize("name", ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1"])
+@pytest.mark.parametrize("name", ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1", "tiny_edit_two_grids"])
 def test_model_forward_vs_reference_golden(golden_dir, name, gemm_mode, fmha_mode):
     fx = torch.load(os.path.join(golden_dir, name + ".pt"))
     c = fx["case"]
     m = make_model(c["L"], c["H"], c["joint"], c["seed"])
     h, w_ = c["grid"]
+    shapes = [[(1, h, w_)] + [(1, a, b) for a, b in c.get("extra_grids", [])]] * c["B"]  # edit layout: condition image appended
     args = (fx["hidden_states"].to(dev), fx["encoder_hidden_states"].to(dev), None)
-    out = m(*args, fx["timestep"].to(dev), [[(1, h, w_)]] * c["B"], [c["T"]] * c["B"], return_dict=False)[0].cpu()
+    out = m(*args, fx["timestep"].to(dev), shapes, [c["T"]] * c["B"], return_dict=False)[0].cpu()
     e_ref = O.rel_fro(out, fx["ref_bf16"])
     e_fp32 = O.rel_fro(out, fx["ref_fp32"])
     print(f"{name}: native vs ref-bf16 {e_ref:.3e}; native vs fp32 {e_fp32:.3e}; ref-bf16 vs fp32 {fx['ref_bf16_vs_fp32']:.3e}")
     assert e_ref <= 1e-2                                   # criterion (ii)
     assert e_fp32 <= fx["ref_bf16_vs_fp32"] + 1e-2         # criterion (iii)
-    out_u = m(*args, fx["timestep"][:1].to(dev), [[(1, h, w_)]] * c["B"], [c["T"]] * c["B"], return_dict=False,
+    out_u = m(*args, fx["timestep"][:1].to(dev), shapes, [c["T"]] * c["B"], return_dict=False,
               uniform_timestep=True)[0].cpu()
     assert torch.equal(out_u, out)                          # shared-timestep fast path is exact
 
@@ -349,6 +350,44 @@ def test_diffuse_trajectory_vs_oracle(cfg):
     assert out.error is None and out.output.shape == lat.shape
     assert np.array_equal(pipe.scheduler.sigmas.numpy(), sig)
     assert O.rel_fro(out.output.cpu(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("cfg", [False, True])
+def test_edit_diffuse_trajectory_vs_oracle(cfg):
+    """Image-edit layout (reference pipeline_qwen_image_edit.py:574-639): condition latents appended on the sequence
+    axis, two RoPE grids, noisy rows of the prediction kept; 4-step trajectory against the oracle."""
+    from vllm_omni_b200.diffusion.data import OmniDiffusionConfig, TransformerConfig
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image_edit import QwenImageEditPipeline
+    from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+    L, H, joint = 2, 2, 256
+    od = OmniDiffusionConfig(tf_model_config=TransformerConfig.from_dict({"num_layers": L}), model_class_name="QwenImageEditPipeline")
+    torch.set_default_dtype(bf)
+    try:
+        with torch.device(dev):
+            pipe = QwenImageEditPipeline(od_config=od, transformer_kwargs=dict(num_attention_heads=H, joint_attention_dim=joint))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    w = dict(synthetic.synthetic_weights(L, seed=15, norm_jitter=0.1, num_heads=H, joint_dim=joint))
+    pipe.transformer.load_weights(w.items())
+    g = gen(16)
+    B, hh, ww, T, h2, w2 = 2, 8, 6, 20, 4, 6
+    lat = torch.randn(B, hh * ww, 64, generator=g).bfloat16()
+    il = torch.randn(B, h2 * w2, 64, generator=g).bfloat16()
+    pe, ne = torch.randn(B, T, joint, generator=g).bfloat16(), torch.randn(B, T, joint, generator=g).bfloat16()
+    sig = O.flow_match_sigmas(4, hh * ww)
+    ref = O.diffuse(w, O.DiTDims(num_layers=L, num_heads=H, joint_dim=joint), lat, pe, ne if cfg else None, sig,
+                    [(1, hh, ww), (1, h2, w2)], 4.0, image_latents=il)
+    req = OmniDiffusionRequest(prompt_embeds=pe, negative_prompt_embeds=ne if cfg else None, latents=lat, height=hh * 16,
+                               width=ww * 16, num_inference_steps=4, true_cfg_scale=4.0 if cfg else 1.0, output_type="latent",
+                               extra={"image_latents": il, "image_latent_grid": (h2, w2)})
+    out = pipe.forward(req)
+    assert out.error is None and out.output.shape == lat.shape
+    assert O.rel_fro(out.output.cpu(), ref) < 1e-2
+    # without a condition image the edit pipeline is the text-to-image path
+    req2 = OmniDiffusionRequest(prompt_embeds=pe, latents=lat, height=hh * 16, width=ww * 16, num_inference_steps=2,
+                                true_cfg_scale=1.0, output_type="latent")
+    ref2 = O.diffuse(w, O.DiTDims(num_layers=L, num_heads=H, joint_dim=joint), lat, pe, None, O.flow_match_sigmas(2, hh * ww), (1, hh, ww))
+    assert O.rel_fro(pipe.forward(req2).output.cpu(), ref2) < 1e-2
 
 
 def test_full_size_properties_1024px():

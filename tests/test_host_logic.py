@@ -92,6 +92,25 @@ def test_rope_tables_match_oracle():
             assert torch.equal(a, b)
 
 
+def test_rope_tables_multi_grid_edit_layout():
+    """Edit pipelines: noisy latents + condition image(s); grid idx takes frame position idx (reference :267), text
+    positions start after the LARGEST grid (:251-257); img_shapes is read like the reference does (:231-234)."""
+    from vllm_omni_b200.diffusion.models.qwen_image.qwen_image_transformer import _grids
+    pe = QwenEmbedRope(10000, [16, 56, 56], True)
+    grids = ((1, 8, 6), (1, 4, 10))
+    got, ref = pe.tables(grids, 13), O.rope_tables(list(grids), 13)
+    assert got[0].shape == (8 * 6 + 4 * 10, 64) and got[2].shape == (13, 64)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    one = pe.tables(1, 8, 6, 13)
+    assert torch.equal(got[0][:48, 8:], one[0][:, 8:])      # h/w axes of the first grid unchanged
+    assert not torch.equal(got[2], one[2])                  # text offset moved: max(8//2, 6//2, 4//2, 10//2) = 5 vs 4
+    assert _grids([[(1, 8, 6), (1, 4, 10)]] * 3) == grids
+    assert _grids([[(1, 8, 6)]] * 2) == ((1, 8, 6),) and _grids((1, 8, 6)) == ((1, 8, 6),) and _grids([(1, 8, 6)] * 2) == ((1, 8, 6),)
+    with pytest.raises(NotImplementedError):
+        _grids([[(1, 8, 6)], [(1, 4, 6)]])
+
+
 def test_scheduler_matches_oracle_tables():
     od = OmniDiffusionConfig(tf_model_config=TransformerConfig.from_dict({"num_layers": 1}))
     sch = P.FlowMatchEulerDiscreteScheduler()
@@ -106,6 +125,9 @@ def test_scheduler_matches_oracle_tables():
 def test_registry_and_config():
     assert registry.DiffusionModelRegistry._try_load_model_cls("QwenImagePipeline") is P.QwenImagePipeline
     assert registry.DiffusionModelRegistry._try_load_model_cls("Nope") is None
+    edit = registry.DiffusionModelRegistry._try_load_model_cls("QwenImageEditPipeline")
+    assert issubclass(edit, P.QwenImagePipeline) and list(__import__("inspect").signature(edit.diffuse).parameters)[6] == "image_latents"
+    assert registry.get_diffusion_post_process_func(OmniDiffusionConfig(model_class_name="QwenImageEditPipeline")) is not None
     od = OmniDiffusionConfig(parallel_config={"data_parallel_size": 4, "tensor_parallel_size": 2})
     assert od.num_gpus == 8 and od.parallel_config.world_size == 8
     with pytest.raises(ValueError):

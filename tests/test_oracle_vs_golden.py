@@ -9,7 +9,13 @@ import torch
 from oracle import qwen_image_oracle as O
 from vllm_omni_b200 import synthetic
 
-CASES = ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1"]
+CASES = ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1", "tiny_edit_two_grids"]
+
+
+def case_grids(c):
+    """(1, h, w) for the T2I cases; a list of grids for the image-edit layout (condition image appended)."""
+    grids = [(1,) + tuple(c["grid"])] + [(1,) + tuple(g) for g in c.get("extra_grids", [])]
+    return grids if len(grids) > 1 else grids[0]
 
 
 def _weights(c):
@@ -25,7 +31,7 @@ def test_oracle_matches_reference_golden(golden_dir, name):
     chk = sum(float(w[k].double().abs().sum()) for k in sorted(w))
     assert abs(chk - fx["weights_checksum"]) <= 1e-9 * abs(fx["weights_checksum"]), "synthetic weight RNG drifted"
     dims = O.DiTDims(num_layers=c["L"], num_heads=c["H"], joint_dim=c["joint"])
-    grid = (1,) + tuple(c["grid"])
+    grid = case_grids(c)
     out = O.model_forward(w, dims, fx["hidden_states"], fx["encoder_hidden_states"], fx["timestep"], grid)
     assert out.dtype == torch.bfloat16
     assert O.rel_fro(out, fx["ref_bf16"]) <= 1e-6, "bf16 restatement must reproduce the reference bit-for-bit"

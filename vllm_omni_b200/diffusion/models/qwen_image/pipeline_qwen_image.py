@@ -190,9 +190,24 @@ class QwenImagePipeline(nn.Module):
     # ---- the hot loop: reference :530-586 ---------------------------------------------------------
     def diffuse(self, prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents,
                 img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale):
+        """Reference signature (pipeline_qwen_image.py:530-544)."""
+        return self._denoise(prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents,
+                             img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale)
+
+    def _denoise(self, prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents,
+                 img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale,
+                 image_latents=None):
+        """The denoise loop behind `diffuse`.  `image_latents` [B,S2,64] (image-edit pipelines, reference pipeline_qwen_image_edit.py:600-602,617): the
+        condition latents follow the noisy ones on the sequence axis in every forward, `img_shapes` lists both grids and
+        only the first S1 rows of the prediction feed the CFG / scheduler step."""
         self.scheduler.set_begin_index(0)
         dev = latents.device
         latents = latents.to(torch.bfloat16).contiguous().clone()
+        s1 = latents.shape[1]
+        model_in = latents
+        if image_latents is not None:
+            # one [B, S1+S2, 64] buffer: the condition rows are written once, the noisy rows refreshed per step
+            model_in = torch.cat([latents, image_latents.to(dev, torch.bfloat16)], dim=1).contiguous()
         sig = self.scheduler.sigmas  # host fp32 [N+1]
         # `timestep = t.expand(B).to(latents.dtype)` then `/ 1000` (reference :552,558): same two bf16 roundings,
         # computed once for all steps; one row per step, shared by the whole batch.
@@ -207,8 +222,10 @@ class QwenImagePipeline(nn.Module):
             if self.interrupt:
                 continue
             self._current_timestep = timesteps[i]
+            if image_latents is not None and i > 0:
+                model_in[:, :s1].copy_(latents)
             noise_pred = self.transformer(
-                hidden_states=latents, timestep=t_dev[i:i + 1], guidance=guidance,
+                hidden_states=model_in, timestep=t_dev[i:i + 1], guidance=guidance,
                 encoder_hidden_states_mask=prompt_embeds_mask, encoder_hidden_states=prompt_embeds, img_shapes=img_shapes,
                 txt_seq_lens=txt_seq_lens, attention_kwargs=self.attention_kwargs, return_dict=False, uniform_timestep=True)[0]
             neg_noise_pred = None
@@ -216,13 +233,21 @@ class QwenImagePipeline(nn.Module):
                 noise_pred, neg_noise_pred = _ps.cfg_all_gather(noise_pred)
             elif do_true_cfg:
                 neg_noise_pred = self.transformer(
-                    hidden_states=latents, timestep=t_dev[i:i + 1], guidance=guidance,
+                    hidden_states=model_in, timestep=t_dev[i:i + 1], guidance=guidance,
                     encoder_hidden_states_mask=negative_prompt_embeds_mask, encoder_hidden_states=negative_prompt_embeds,
                     img_shapes=img_shapes, txt_seq_lens=negative_txt_seq_lens, attention_kwargs=self.attention_kwargs,
                     return_dict=False, uniform_timestep=True)[0]
+            if image_latents is not None:  # keep the noisy rows only (:617,632)
+                noise_pred = noise_pred[:, :s1].contiguous()
+                if neg_noise_pred is not None:
+                    neg_noise_pred = neg_noise_pred[:, :s1].contiguous()
             # fused: comb = neg + s (pos - neg); rescale by ||pos|| / ||comb||; x += (sigma_{i+1} - sigma_i) v
             qlib.cfg_euler_step(noise_pred, neg_noise_pred, latents, float(true_cfg_scale), float(sig[i]), float(sig[i + 1]))
         return latents
+
+    def _condition_latents(self, req: OmniDiffusionRequest, batch: int, img_shapes):
+        """Text-to-image: no condition image.  Overridden by the edit pipeline."""
+        return None, img_shapes
 
     # ---- request entry point: reference :588-750 ----------------------------------------------------
     @torch.inference_mode()
@@ -281,13 +306,15 @@ class QwenImagePipeline(nn.Module):
                                        torch.bfloat16, dev, generator, latents)
         img_shapes = [[(1, height // self.vae_scale_factor // 2, width // self.vae_scale_factor // 2)]] * (
             batch_size * num_images_per_prompt)
+        image_latents, img_shapes = self._condition_latents(req, batch_size * num_images_per_prompt, img_shapes)
         timesteps, num_inference_steps = self.prepare_timesteps(num_inference_steps, sigmas, latents.shape[1])
         self._num_timesteps = len(timesteps)
         txt_seq_lens = prompt_embeds_mask.sum(dim=1).tolist()
         negative_txt_seq_lens = negative_prompt_embeds_mask.sum(dim=1).tolist() if do_true_cfg else None
-        latents = self.diffuse(prompt_embeds, prompt_embeds_mask, negative_prompt_embeds if do_true_cfg else None,
-                               negative_prompt_embeds_mask if do_true_cfg else None, latents, img_shapes, txt_seq_lens,
-                               negative_txt_seq_lens, timesteps, do_true_cfg, None, true_cfg_scale)
+        latents = self._denoise(prompt_embeds, prompt_embeds_mask, negative_prompt_embeds if do_true_cfg else None,
+                                negative_prompt_embeds_mask if do_true_cfg else None, latents, img_shapes, txt_seq_lens,
+                                negative_txt_seq_lens, timesteps, do_true_cfg, None, true_cfg_scale,
+                                image_latents=image_latents)
         self._current_timestep = None
         if output_type == "latent" or self.vae is None:
             return DiffusionOutput(output=latents)

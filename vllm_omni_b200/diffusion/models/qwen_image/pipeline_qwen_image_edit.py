@@ -1,0 +1,47 @@
+"""QwenImageEditPipeline — the image-conditioned sibling of QwenImagePipeline (reference
+vllm_omni/diffusion/models/qwen_image/pipeline_qwen_image_edit.py): same transformer, same denoise loop, but the packed
+VAE latents of the condition image are appended to the noisy latents on the sequence axis in every forward (:600-602),
+`img_shapes` carries two grids per sample (:753-758) so RoPE gives the condition image frame index 1, and only the noisy
+rows of the prediction are kept (:617,632).
+
+Scope: the DiT side.  The VAE encode of the input image (`_encode_vae_image` :455-480) and the
+Qwen2.5-VL prompt encode are outside the native engine; the request carries the already packed, already normalised
+condition latents:
+    req.extra["image_latents"]      [B or 1, S2, 64] bf16 (what `prepare_latents` returns as `image_latents`, :519-522)
+    req.extra["image_latent_grid"]  (h2, w2) latent-patch grid with h2 * w2 == S2
+"""
+from __future__ import annotations
+
+import torch
+
+from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image import (  # noqa: F401  (registry looks the func up here)
+    QwenImagePipeline, get_qwen_image_post_process_func)
+from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+
+
+class QwenImageEditPipeline(QwenImagePipeline):
+    def diffuse(self, prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents,
+                image_latents, img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance,
+                true_cfg_scale):
+        """Reference signature (:574-589): `image_latents` is the sixth positional argument."""
+        return self._denoise(prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents,
+                             img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale,
+                             image_latents=image_latents)
+
+    def _condition_latents(self, req: OmniDiffusionRequest, batch: int, img_shapes):
+        il = (req.extra or {}).get("image_latents")
+        if il is None:
+            return None, img_shapes  # behaves as text-to-image, like the reference when `image` is None (:600-602)
+        grid = (req.extra or {}).get("image_latent_grid")
+        if grid is None or int(grid[0]) * int(grid[1]) != il.shape[1]:
+            raise ValueError("req.extra['image_latent_grid'] = (h2, w2) with h2 * w2 == image_latents.shape[1] is required")
+        if il.shape[0] != batch:
+            if batch % il.shape[0]:
+                raise ValueError(f"Cannot duplicate `image` of batch size {il.shape[0]} to {batch} text prompts.")  # (:512-515)
+            il = torch.cat([il] * (batch // il.shape[0]), dim=0)
+        shapes = [[img_shapes[0][0], (1, int(grid[0]), int(grid[1]))]] * batch
+        return il, shapes
+
+
+def get_qwen_image_edit_post_process_func(od_config):
+    return get_qwen_image_post_process_func(od_config)

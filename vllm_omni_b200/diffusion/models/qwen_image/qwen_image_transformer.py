@@ -37,23 +37,28 @@ class Transformer2DModelOutput:
         return (self.sample,)[i]
 
 
-def _single_grid(img_shapes) -> tuple[int, int, int]:
-    """img_shapes is `[[(frame, h, w)]] * B` in the T2I pipeline (pipeline_qwen_image.py:688); accept that,
-    `[(f,h,w)]` or `(f,h,w)`; every sample must share one grid and hold one image (edit = §8f next)."""
+def _grids(img_shapes) -> tuple[tuple[int, int, int], ...]:
+    """The reference's reading of `img_shapes` (QwenEmbedRope.forward :231-234): a list is indexed by sample and sample 0
+    decides; its entry is a list of (frame, h, w) grids — `[[(1, h, w)]] * B` in the T2I pipeline
+    (pipeline_qwen_image.py:688), `[[(1, h, w), (1, h2, w2), ...]] * B` in the edit pipelines (noisy latents first, then
+    the condition image(s), pipeline_qwen_image_edit.py:602) — or a single grid tuple.  Unlike the reference, samples that
+    disagree with sample 0 are rejected instead of silently sharing its table."""
     def is_grid(x):
-        return isinstance(x, (list, tuple)) and len(x) == 3 and all(isinstance(v, int) for v in x)
+        return isinstance(x, tuple) and len(x) == 3 and all(isinstance(v, int) for v in x)
 
-    if is_grid(img_shapes):
-        return tuple(img_shapes)
-    per_sample = [s if not is_grid(s) else [s] for s in img_shapes]
-    grids = []
-    for s in per_sample:
-        if len(s) != 1 or not is_grid(s[0]):
-            raise NotImplementedError("one (frame, h, w) grid per sample is supported (multi-image edit is a 'next' item)")
-        grids.append(tuple(s[0]))
-    if any(g != grids[0] for g in grids):
-        raise NotImplementedError("all images in a batch must share one latent grid")
-    return grids[0]
+    v = img_shapes
+    if isinstance(v, list):
+        if not v:
+            raise ValueError("empty img_shapes")
+        if any(e != v[0] for e in v):
+            raise NotImplementedError("all samples of a batch must share the same image grids")
+        v = v[0]
+    if not isinstance(v, list):
+        v = [v]
+    grids = tuple(tuple(g) for g in v)
+    if not grids or not all(is_grid(g) for g in grids):
+        raise ValueError(f"bad img_shapes {img_shapes!r}")
+    return grids
 
 
 class _Linear(nn.Module):
@@ -157,39 +162,41 @@ class QwenEmbedRope(nn.Module):
     def _angles(self, index: torch.Tensor, dim: int) -> torch.Tensor:
         return torch.outer(index.float(), 1.0 / torch.pow(self.theta, torch.arange(0, dim, 2).to(torch.float32).div(dim)))
 
-    def tables(self, frame: int, height: int, width: int, txt_len: int):
-        key = (frame, height, width, txt_len)
+    def tables(self, frame, height: int = None, width: int = None, txt_len: int = None):
+        """One (frame, height, width) grid, or a sequence of grids as the first argument (then `height` is txt_len):
+        the idx-th grid takes its frame positions from idx (reference :267), tables are concatenated (:258)."""
+        if isinstance(frame, (list, tuple)) and len(frame) and isinstance(frame[0], (list, tuple)):
+            grids, txt_len = tuple(tuple(g) for g in frame), (height if txt_len is None else txt_len)
+        else:
+            grids = ((frame, height, width),)
+        key = (grids, txt_len)
         if key in self._cache:
             return self._cache[key]
         pos_index = torch.arange(4096)
         neg_index = torch.arange(4096).flip(0) * -1 - 1
         pos = [self._angles(pos_index, d) for d in self.axes_dim]
         neg = [self._angles(neg_index, d) for d in self.axes_dim]
-        f_frame = pos[0][0:frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
-        if self.scale_rope:
-            f_h = torch.cat([neg[1][-(height - height // 2):], pos[1][: height // 2]], dim=0)
-            f_w = torch.cat([neg[2][-(width - width // 2):], pos[2][: width // 2]], dim=0)
-            max_vid_index = max(height // 2, width // 2)
-        else:
-            f_h, f_w = pos[1][:height], pos[2][:width]
-            max_vid_index = max(height, width)
-        f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
-        f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
-        ang = torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1)
+        angs, max_vid_index = [], 0
+        for idx, (frame, height, width) in enumerate(grids):
+            f_frame = pos[0][idx: idx + frame].view(frame, 1, 1, -1).expand(frame, height, width, -1)
+            if self.scale_rope:
+                f_h = torch.cat([neg[1][-(height - height // 2):], pos[1][: height // 2]], dim=0)
+                f_w = torch.cat([neg[2][-(width - width // 2):], pos[2][: width // 2]], dim=0)
+                max_vid_index = max(height // 2, width // 2, max_vid_index)
+            else:
+                f_h, f_w = pos[1][:height], pos[2][:width]
+                max_vid_index = max(height, width, max_vid_index)
+            f_h = f_h.view(1, height, 1, -1).expand(frame, height, width, -1)
+            f_w = f_w.view(1, 1, width, -1).expand(frame, height, width, -1)
+            angs.append(torch.cat([f_frame, f_h, f_w], dim=-1).reshape(frame * height * width, -1))
+        ang = torch.cat(angs, dim=0)
         txt_ang = torch.cat(pos, dim=1)[max_vid_index: max_vid_index + txt_len]
         out = (torch.cos(ang), torch.sin(ang), torch.cos(txt_ang), torch.sin(txt_ang))
         self._cache[key] = out
         return out
 
     def forward(self, video_fhw, txt_seq_lens, device):
-        if isinstance(video_fhw, list):
-            video_fhw = video_fhw[0]
-        if isinstance(video_fhw, list):
-            if len(video_fhw) != 1:
-                raise NotImplementedError("multi-image (edit) RoPE is a SURVEY §8f 'next' item")
-            video_fhw = video_fhw[0]
-        frame, height, width = video_fhw
-        return tuple(t.to(device) for t in self.tables(frame, height, width, max(txt_seq_lens)))
+        return tuple(t.to(device) for t in self.tables(_grids(video_fhw), max(txt_seq_lens)))
 
 
 class _TimestepEmbedder(nn.Module):
@@ -483,13 +490,13 @@ class QwenImageTransformer2DModel(nn.Module):
         return self._ws[key]
 
     def _rope(self, img_shapes, txt_len: int, device):
-        frame, height, width = _single_grid(img_shapes)
-        key = (frame, height, width, txt_len, str(device))
+        grids = _grids(img_shapes)
+        key = (grids, txt_len, str(device))
         if key not in self._rope_dev:
-            ic, isn, tc, tsn = self.pos_embed.tables(frame, height, width, txt_len)
+            ic, isn, tc, tsn = self.pos_embed.tables(grids, txt_len)
             # cos/sin are cast to the activation dtype before use, as in the reference (:403-406)
             self._rope_dev[key] = tuple(t.to(torch.bfloat16).contiguous().to(device) for t in (ic, isn, tc, tsn))
-        return self._rope_dev[key], frame * height * width
+        return self._rope_dev[key], sum(f * h * w for f, h, w in grids)
 
     # ------------------------------------------------------------------ forward
     def forward(

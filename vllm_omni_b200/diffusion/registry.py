@@ -10,8 +10,10 @@ from vllm_omni_b200.diffusion.data import OmniDiffusionConfig
 _DIFFUSION_MODELS = {
     # arch: (mod_folder, mod_relname, cls_name)
     "QwenImagePipeline": ("qwen_image", "pipeline_qwen_image", "QwenImagePipeline"),
+    "QwenImageEditPipeline": ("qwen_image", "pipeline_qwen_image_edit", "QwenImageEditPipeline"),
 }
-_DIFFUSION_POST_PROCESS_FUNCS = {"QwenImagePipeline": "get_qwen_image_post_process_func"}
+_DIFFUSION_POST_PROCESS_FUNCS = {"QwenImagePipeline": "get_qwen_image_post_process_func",
+                                 "QwenImageEditPipeline": "get_qwen_image_edit_post_process_func"}
 
 
 class _Registry:
