@@ -214,6 +214,32 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
                         const void* img_cos, const void* img_sin, const void* txt_cos, const void* txt_sin, int B,
                         int S_img, int T, void* out, void* workspace, size_t workspace_bytes, qimg_stream_t stream);
 
+/* Staged forward for step caches (TeaCache, reference cache/teacache/hook.py:80-165 + extractors.py:184-246):
+ *   QIMG_STAGE_PRE     img_in, txt_norm + txt_in, temb, all modulations (extractor preprocessing :187-204); when the
+ *                      blocks are NOT part of the same call, block 0's modulated image stream (:206-209) is also left
+ *                      in the workspace at qimg_engine_ws_offset_mod()
+ *   QIMG_STAGE_BLOCKS  the L dual-stream blocks on the residual streams held in the workspace (run_transformer_blocks)
+ *   QIMG_STAGE_POST    norm_out + proj_out -> out (postprocess :230-236)
+ * The residual streams live at qimg_engine_ws_offset_img/_txt between calls; the workspace must not be reused by another
+ * shape in between.  qimg_engine_forward == all three stages. */
+#define QIMG_STAGE_PRE 1
+#define QIMG_STAGE_BLOCKS 2
+#define QIMG_STAGE_POST 4
+#define QIMG_STAGE_ALL 7
+int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, const void* enc, const void* timestep, int n_t,
+                               const void* img_cos, const void* img_sin, const void* txt_cos, const void* txt_sin, int B,
+                               int S_img, int T, void* out, void* workspace, size_t workspace_bytes, qimg_stream_t stream);
+size_t qimg_engine_ws_offset_mod(const qimg_engine* e, int B, int S_img, int T);
+
+/* Step-cache arithmetic on bf16 tensors of n elements (n % 8 == 0), each a single pass:
+ *   qimg_rel_l1_sums      sums2[0] = sum |bf16(a - b)|, sums2[1] = sum |b| (fp32, device memory; zeroed by the call):
+ *                         the two means of hook.py:198-203
+ *   qimg_bf16_sub         out = bf16(a - b)       (cached residual, hook.py:152-154)
+ *   qimg_bf16_add_inplace x   = bf16(x + r)       (residual reuse, hook.py:131-133) */
+int qimg_rel_l1_sums(const void* a, const void* b, long long n, float* sums2, qimg_stream_t stream);
+int qimg_bf16_sub(void* out, const void* a, const void* b, long long n, qimg_stream_t stream);
+int qimg_bf16_add_inplace(void* x, const void* r, long long n, qimg_stream_t stream);
+
 /* Debug/test access: copies of the image / text residual streams after the last forward live in the
  * workspace at these byte offsets ([B*S_img, D] and [B*T, D] bf16). */
 size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T);

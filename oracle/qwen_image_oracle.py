@@ -213,11 +213,9 @@ def block_forward(w: dict, p: str, dims: DiTDims, img, txt, temb, rope):
     return txt, img
 
 
-def model_forward(w: dict, dims: DiTDims, hidden_states, encoder_hidden_states, timestep, img_shape, txt_len=None,
-                  return_intermediates: bool = False):
-    """QwenImageTransformer2DModel.forward (qwen_image_transformer.py:692-802), SP off,
-    zero_cond_t off, guidance None.  hidden_states [B,S_img,64]; encoder_hidden_states
-    [B,T,joint]; timestep [B] (already /1000); img_shape = (frame, h, w) latent-patch grid."""
+def model_pre(w: dict, dims: DiTDims, hidden_states, encoder_hidden_states, timestep, img_shape, txt_len=None):
+    """Preprocessing part of QwenImageTransformer2DModel.forward (qwen_image_transformer.py:743-770; the same lines the
+    TeaCache extractor runs, cache/teacache/extractors.py:187-204): -> (img, txt, temb, rope)."""
     dt = hidden_states.dtype
     img = F.linear(hidden_states, w["img_in.weight"], w["img_in.bias"])
     timestep = timestep.to(dt)
@@ -229,16 +227,36 @@ def model_forward(w: dict, dims: DiTDims, hidden_states, encoder_hidden_states, 
         rope = rope_tables([tuple(g) for g in img_shape], T, axes=dims.axes_dims_rope)
     else:
         rope = rope_tables(*img_shape, T, axes=dims.axes_dims_rope)
-    inter = []
+    return img, txt, temb, rope
+
+
+def model_blocks(w: dict, dims: DiTDims, img, txt, temb, rope, inter: list | None = None):
+    """The transformer blocks (:783-792; extractor `run_transformer_blocks`, :214-227): -> (img, txt)."""
     for i in range(dims.num_layers):
         txt, img = block_forward(w, f"transformer_blocks.{i}.", dims, img, txt, temb, rope)
-        if return_intermediates:
+        if inter is not None:
             inter.append((txt, img))
-    # AdaLayerNormContinuous (:686,797): scale FIRST, then shift
+    return img, txt
+
+
+def model_post(w: dict, dims: DiTDims, img, temb):
+    """AdaLayerNormContinuous (:686,797; scale FIRST, then shift) + proj_out (:798); extractor `postprocess` :232-238."""
+    dt = img.dtype
     emb = F.linear(F.silu(temb).to(dt), w["norm_out.linear.weight"], w["norm_out.linear.bias"])
     scale, shift = torch.chunk(emb, 2, dim=1)
     img = F.layer_norm(img, (img.shape[-1],), None, None, dims.eps) * (1 + scale)[:, None, :] + shift[:, None, :]
-    out = F.linear(img, w["proj_out.weight"], w["proj_out.bias"])
+    return F.linear(img, w["proj_out.weight"], w["proj_out.bias"])
+
+
+def model_forward(w: dict, dims: DiTDims, hidden_states, encoder_hidden_states, timestep, img_shape, txt_len=None,
+                  return_intermediates: bool = False):
+    """QwenImageTransformer2DModel.forward (qwen_image_transformer.py:692-802), SP off,
+    zero_cond_t off, guidance None.  hidden_states [B,S_img,64]; encoder_hidden_states
+    [B,T,joint]; timestep [B] (already /1000); img_shape = (frame, h, w) latent-patch grid (or a list of grids)."""
+    img, txt, temb, rope = model_pre(w, dims, hidden_states, encoder_hidden_states, timestep, img_shape, txt_len)
+    inter = [] if return_intermediates else None
+    img, txt = model_blocks(w, dims, img, txt, temb, rope, inter)
+    out = model_post(w, dims, img, temb)
     if return_intermediates:
         return out, inter
     return out

@@ -390,6 +390,79 @@ def test_edit_diffuse_trajectory_vs_oracle(cfg):
     assert O.rel_fro(pipe.forward(req2).output.cpu(), ref2) < 1e-2
 
 
+def test_step_cache_kernels_bit_exact():
+    """rel-L1 sums, residual subtraction and residual add (reference cache/teacache/hook.py:131,152,198-203)."""
+    g = gen(30)
+    a = torch.randn(3, 77, 256, generator=g).bfloat16().to(dev)
+    b = (a.float() * 1.03 + 0.01 * torch.randn(3, 77, 256, generator=g).to(dev)).bfloat16()
+    sums = torch.zeros(2, dtype=torch.float32, device=dev)
+    q.rel_l1_sums(a, b, sums)
+    want0, want1 = (a - b).abs().float().sum().item(), b.abs().float().sum().item()
+    assert abs(sums[0].item() - want0) <= 1e-5 * want0 and abs(sums[1].item() - want1) <= 1e-5 * want1
+    out = torch.empty_like(a)
+    q.bf16_sub(out, a, b)
+    assert torch.equal(out, a - b)
+    x = a.clone()
+    q.bf16_add_inplace(x, b)
+    assert torch.equal(x, a + b)
+
+
+def test_staged_forward_equals_single_call(golden_dir):
+    """PRE -> BLOCKS -> POST through qimg_engine_forward_stages == qimg_engine_forward, bit for bit (the TeaCache
+    hook with a threshold that never reuses runs exactly this sequence)."""
+    from vllm_omni_b200.diffusion.cache.teacache import TeaCacheConfig, apply_teacache_hook
+    fx = torch.load(os.path.join(golden_dir, "tiny_L2_H2.pt"))
+    c = fx["case"]
+    m = make_model(c["L"], c["H"], c["joint"], c["seed"])
+    h, w_ = c["grid"]
+    args = (fx["hidden_states"].to(dev), fx["encoder_hidden_states"].to(dev), None, fx["timestep"].to(dev),
+            [[(1, h, w_)]] * c["B"], [c["T"]] * c["B"])
+    ref = m(*args, return_dict=False)[0].clone()
+    apply_teacache_hook(m, TeaCacheConfig(rel_l1_thresh=1e-30, coefficients=[0.0, 0.0, 0.0, 1.0, 0.0]))
+    for _ in range(3):
+        assert torch.equal(m(*args, return_dict=False)[0], ref)
+    assert [d[1] for d in m._teacache.decisions] == [True, True, True]
+
+
+@pytest.mark.parametrize("cfg", [False, True])
+def test_teacache_trajectory_vs_reference_hook(golden_dir, cfg):
+    """8-step denoise with the native TeaCache hook against the fixture produced by the UNMODIFIED reference hook
+    (tests/golden/teacache_tiny.pt): the same compute / reuse decisions (separate positive / negative states under CFG)
+    and latents within 1e-2."""
+    from vllm_omni_b200.diffusion.cache import get_cache_backend
+    from vllm_omni_b200.diffusion.data import OmniDiffusionConfig, TransformerConfig
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image import QwenImagePipeline
+    from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+    fx = torch.load(os.path.join(golden_dir, "teacache_tiny.pt"), weights_only=False)
+    c = fx["case"]
+    od = OmniDiffusionConfig(tf_model_config=TransformerConfig.from_dict({"num_layers": c["L"]}), cache_backend="tea_cache",
+                             cache_config={"rel_l1_thresh": c["thresh"], "coefficients": c["coefficients"]})
+    torch.set_default_dtype(bf)
+    try:
+        with torch.device(dev):
+            pipe = QwenImagePipeline(od_config=od, transformer_kwargs=dict(num_attention_heads=c["H"], joint_attention_dim=c["joint"]))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    pipe.transformer.load_weights(synthetic.synthetic_weights(c["L"], seed=c["seed"], norm_jitter=0.1, num_heads=c["H"],
+                                                              joint_dim=c["joint"]))
+    backend = get_cache_backend(od.cache_backend, od.cache_config)
+    backend.enable(pipe)
+    h, w_ = c["grid"]
+    want = fx["cfg" if cfg else "nocfg"]
+    for _ in range(2):  # the second run checks refresh()
+        backend.refresh(pipe, c["steps"])
+        req = OmniDiffusionRequest(prompt_embeds=fx["prompt_embeds"], negative_prompt_embeds=fx["negative_prompt_embeds"] if cfg else None,
+                                   latents=fx["latents0"], height=h * 16, width=w_ * 16, num_inference_steps=c["steps"],
+                                   sigmas=None, true_cfg_scale=4.0 if cfg else 1.0, output_type="latent")
+        out = pipe.forward(req)
+        assert out.error is None
+        assert np.array_equal(pipe.scheduler.sigmas.numpy(), fx["sigmas"])
+        got = [d[1] for d in pipe.transformer._teacache.decisions]
+        print("decisions", got, "rel", [round(d[2], 4) for d in pipe.transformer._teacache.decisions])
+        assert got == want["decisions"]
+        assert O.rel_fro(out.output.cpu(), want["latents"]) < 1e-2
+
+
 def test_full_size_properties_1024px():
     """BASELINE configs[1] sizes (1024px, S_img=4096, T=128, D=3072; depth cut to L=2 to bound memory/time):
     size-independent properties — batch rows are independent and deterministic; CFG with identical branches is the

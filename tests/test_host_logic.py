@@ -204,3 +204,66 @@ def test_tensor_parallel_weight_sharding():
     assert torch.equal(ps_[0][b + "img_mod.1.weight"], full[b + "img_mod.1.weight"])  # replicated
     with pytest.raises(ValueError):
         QwenImageTransformer2DModel(num_layers=1, num_attention_heads=3, joint_attention_dim=64, tp_size=2, tp_rank=0)
+
+
+def test_teacache_config_selector_and_decision_logic():
+    """Step-cache host logic (reference cache/teacache/{config,hook,backend}.py, cache/selector.py): config validation,
+    backend selection, and the accumulate / threshold / reset decision with the reference's bf16 roundings."""
+    from vllm_omni_b200.diffusion.cache import get_cache_backend
+    from vllm_omni_b200.diffusion.cache.teacache import TeaCacheBackend, TeaCacheConfig, TeaCacheHook, TeaCacheState
+    from vllm_omni_b200.diffusion.data import DiffusionCacheConfig
+    assert TeaCacheConfig().coefficients == [-450.0, 280.0, -45.0, 3.2, -0.02] and TeaCacheConfig().rel_l1_thresh == 0.2
+    with pytest.raises(ValueError):
+        TeaCacheConfig(rel_l1_thresh=0.0)
+    with pytest.raises(ValueError):
+        TeaCacheConfig(coefficients=[1.0, 2.0])
+    with pytest.raises(KeyError):
+        TeaCacheConfig(transformer_type="FluxTransformer2DModel")
+    assert get_cache_backend(None, None) is None and get_cache_backend("none", {}) is None
+    be = get_cache_backend("tea_cache", {"rel_l1_thresh": 0.3, "Fn_compute_blocks": 2})
+    assert isinstance(be, TeaCacheBackend) and be.config.rel_l1_thresh == 0.3 and not be.is_enabled()
+    with pytest.raises(ValueError):
+        get_cache_backend("cache_dit", DiffusionCacheConfig())
+    with pytest.raises(ValueError):
+        get_cache_backend("deep_cache", {})
+
+    class FakeTransformer:
+        _teacache = None
+        do_true_cfg = False
+
+    class QwenImageTransformer2DModel(FakeTransformer):
+        pass
+
+    class Pipe:
+        transformer = QwenImageTransformer2DModel()
+
+    be.enable(Pipe)
+    hook = Pipe.transformer._teacache
+    assert be.is_enabled() and isinstance(hook, TeaCacheHook) and hook.config.rel_l1_thresh == 0.3
+
+    class FakeLib:  # the reduction kernel's contract, on CPU tensors
+        @staticmethod
+        def rel_l1_sums(a, b, sums):
+            sums[0] = (a - b).abs().float().sum()
+            sums[1] = b.abs().float().sum()
+
+    g = torch.Generator().manual_seed(0)
+    hook = TeaCacheHook(TeaCacheConfig(rel_l1_thresh=0.05, coefficients=[0.0, 0.0, 0.0, 1.0, 0.0]))
+    st = TeaCacheState()
+    prev = torch.randn(4, 64, generator=g).bfloat16()
+    assert hook._should_compute(st, prev, FakeLib) == (True, pytest.approx(float("nan"), nan_ok=True))  # first step
+    st.cnt, st.has_mod, st.previous_modulated_input = 1, True, prev
+    acc, seen = 0.0, []
+    for k in range(6):
+        cur = (prev.float() * (1 + 0.02 * (k + 1))).bfloat16()
+        want = ((cur - prev).abs().mean() / (prev.abs().mean() + 1e-8)).item()  # reference expression, hook.py:198-205
+        compute, rel = hook._should_compute(st, cur, FakeLib)
+        assert rel == want
+        acc += abs(want)
+        assert compute == (acc >= 0.05)
+        if compute:
+            acc = 0.0
+        seen.append(compute)
+    assert any(seen) and not all(seen)
+    hook.reset_state()
+    assert hook._forward_cnt == 0 and hook.decisions == []

@@ -87,3 +87,21 @@ def test_rope_tables_shape_and_text_offset():
     # text positions start at max(h//2, w//2) on every axis (reference :251-257)
     ang = torch.atan2(tsn[0, 0], tc[0, 0])
     assert abs(float(ang) - 3.0) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [False, True])
+def test_teacache_oracle_matches_reference_hook(golden_dir, cfg):
+    """oracle/teacache_oracle.py against the fixture produced by the UNMODIFIED reference TeaCache hook
+    (oracle/make_golden_teacache.py): same compute / reuse decisions, bit-identical bf16 latents after 8 steps."""
+    from oracle import teacache_oracle as TO
+    fx = torch.load(os.path.join(golden_dir, "teacache_tiny.pt"), weights_only=False)
+    c = fx["case"]
+    w = _weights(c)
+    dims = O.DiTDims(num_layers=c["L"], num_heads=c["H"], joint_dim=c["joint"])
+    tc = TO.TeaCacheOracle(w, dims, c["thresh"], c["coefficients"])
+    out = TO.diffuse(tc, fx["latents0"].clone(), fx["prompt_embeds"], fx["negative_prompt_embeds"] if cfg else None,
+                     fx["sigmas"], (1,) + tuple(c["grid"]), 4.0)
+    want = fx["cfg" if cfg else "nocfg"]
+    assert [d[1] for d in tc.decisions] == want["decisions"]
+    assert any(want["decisions"][1:]) and not all(want["decisions"])  # both paths exercised
+    assert torch.equal(out, want["latents"])

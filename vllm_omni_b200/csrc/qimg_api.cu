@@ -509,6 +509,37 @@ int qimg_gate_residual_bias(void* x, const void* y, const void* bias, const void
   return 0;
 }
 
+static int ew_grid(long long n_vec) {
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 16;
+  return (int)(blocks > cap ? cap : blocks);
+}
+
+int qimg_rel_l1_sums(const void* a, const void* b, long long n, float* sums2, qimg_stream_t stream) {
+  if (n <= 0) return fail("qimg_rel_l1_sums: empty input");
+  if (n % 8) return fail("qimg_rel_l1_sums: n must be a multiple of 8");
+  QIMG_CUDA_CHECK(cudaMemsetAsync(sums2, 0, 2 * sizeof(float), (cudaStream_t)stream));
+  rel_l1_sums_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, n / 8, sums2);
+  QIMG_LAUNCH_CHECK("rel_l1_sums_kernel");
+  return 0;
+}
+
+int qimg_bf16_sub(void* out, const void* a, const void* b, long long n, qimg_stream_t stream) {
+  if (n <= 0) return 0;
+  if (n % 8) return fail("qimg_bf16_sub: n must be a multiple of 8");
+  bf16_sub_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((bf16*)out, (const bf16*)a, (const bf16*)b, n / 8);
+  QIMG_LAUNCH_CHECK("bf16_sub_kernel");
+  return 0;
+}
+
+int qimg_bf16_add_inplace(void* x, const void* r, long long n, qimg_stream_t stream) {
+  if (n <= 0) return 0;
+  if (n % 8) return fail("qimg_bf16_add_inplace: n must be a multiple of 8");
+  bf16_add_inplace_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((bf16*)x, (const bf16*)r, n / 8);
+  QIMG_LAUNCH_CHECK("bf16_add_inplace_kernel");
+  return 0;
+}
+
 int qimg_linear_small_m(const void* x, const void* W, const void* bias, void* y, int M, long long N, int K,
                         long long ldy, int act_silu, qimg_stream_t stream) {
   if (M <= 0 || N <= 0) return 0;

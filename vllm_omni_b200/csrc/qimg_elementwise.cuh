@@ -244,6 +244,72 @@ __global__ void __launch_bounds__(256) gate_residual_bias_kernel(bf16* __restric
   }
 }
 
+// ---- step-cache (TeaCache) helpers: reference cache/teacache/hook.py:124-160,196-206 ------------------------------
+// sums[0] += sum |bf16(a - b)|, sums[1] += sum |b|  (fp32): the two means of
+//   rel = (mod - prev).abs().mean() / (prev.abs().mean() + 1e-8)      (hook.py:198-203; the subtraction is a bf16 op)
+// Each byte is read once; one atomicAdd pair per block.
+__global__ void __launch_bounds__(256) rel_l1_sums_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                          long long n_vec, float* __restrict__ sums) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float sd = 0.f, sb = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const uint4 av = ldg_nc_v4(a + i * 8), bv = ldg_nc_v4(b + i * 8);
+    const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t d = bsub2(aw[k], bw[k]);
+      sd += fabsf(bf16lo(d)) + fabsf(bf16hi(d));
+      sb += fabsf(bf16lo(bw[k])) + fabsf(bf16hi(bw[k]));
+    }
+  }
+  sd = warp_sum(sd);
+  sb = warp_sum(sb);
+  __shared__ float red[2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = sd;
+    red[1][warp] = sb;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    sd = lane < 8 ? red[0][lane] : 0.f;
+    sb = lane < 8 ? red[1][lane] : 0.f;
+    sd = warp_sum(sd);
+    sb = warp_sum(sb);
+    if (lane == 0) {
+      atomicAdd(sums, sd);
+      atomicAdd(sums + 1, sb);
+    }
+  }
+}
+
+// out = bf16(a - b)  (cached residual, hook.py:152)   /   x = bf16(x + r)  (residual reuse, hook.py:131)
+__global__ void __launch_bounds__(256) bf16_sub_kernel(bf16* __restrict__ out, const bf16* __restrict__ a,
+                                                       const bf16* __restrict__ b, long long n_vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const uint4 av = ldg_nc_v4(a + i * 8), bv = ldg_nc_v4(b + i * 8);
+    uint4 o;
+    o.x = bsub2(av.x, bv.x);
+    o.y = bsub2(av.y, bv.y);
+    o.z = bsub2(av.z, bv.z);
+    o.w = bsub2(av.w, bv.w);
+    stg_v4(out + i * 8, o);
+  }
+}
+__global__ void __launch_bounds__(256) bf16_add_inplace_kernel(bf16* __restrict__ x, const bf16* __restrict__ r, long long n_vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const uint4 xv = ldg_v4(x + i * 8), rv = ldg_nc_v4(r + i * 8);
+    uint4 o;
+    o.x = badd2(xv.x, rv.x);
+    o.y = badd2(xv.y, rv.y);
+    o.z = badd2(xv.z, rv.z);
+    o.w = badd2(xv.w, rv.w);
+    stg_v4(x + i * 8, o);
+  }
+}
+
 // Small-M linear ("GEMV"): y[m, n] = bf16( sum_k act(x[m,k]) * W[n,k] + bias[n] ), M <= 8 per pass.
 // HBM-bound on W (read exactly once).  Used for the timestep MLP (qwen_image_transformer.py:50-62),
 // all 2*L modulation projections img_mod/txt_mod (:552-557, batched into ONE launch over the

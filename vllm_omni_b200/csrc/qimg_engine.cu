@@ -148,7 +148,17 @@ size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T) 
 int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, const void* timestep, int n_t,
                         const void* img_cos, const void* img_sin, const void* txt_cos, const void* txt_sin, int B,
                         int S_img, int T, void* out, void* workspace, size_t workspace_bytes, qimg_stream_t st) {
+  return qimg_engine_forward_stages(e, QIMG_STAGE_ALL, hidden, enc, timestep, n_t, img_cos, img_sin, txt_cos, txt_sin, B, S_img, T,
+                                    out, workspace, workspace_bytes, st);
+}
+
+size_t qimg_engine_ws_offset_mod(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size).xm_img; }
+
+int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, const void* enc, const void* timestep, int n_t,
+                               const void* img_cos, const void* img_sin, const void* txt_cos, const void* txt_sin, int B,
+                               int S_img, int T, void* out, void* workspace, size_t workspace_bytes, qimg_stream_t st) {
   if (!e) return fail("qimg_engine_forward: null engine");
+  if (stages <= 0 || stages > QIMG_STAGE_ALL) return fail("qimg_engine_forward_stages: bad stage mask");
   if (B <= 0 || S_img <= 0 || T <= 0) return fail("qimg_engine_forward: bad shape");
   if (n_t != 1 && n_t != B) return fail("qimg_engine_forward: n_t must be 1 or B");
   const qimg_dims& d = e->dims;
@@ -200,6 +210,7 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
   const long long emb_stride = (n_t == 1) ? 0 : 2LL * D;
 
   // ---- prologue: temb, all modulations, img_in, txt_norm + txt_in -------------------------
+  if (stages & QIMG_STAGE_PRE) {
   QIMG_TRY(qimg_timestep_sinusoid(timestep, tsin, n_t, st));
   QIMG_TRY(qimg_linear_small_m(tsin, e->g.t_lin1_w, e->g.t_lin1_b, t1, n_t, D, 256, D, 0, st));
   QIMG_TRY(qimg_linear_small_m(t1, e->g.t_lin2_w, e->g.t_lin2_b, temb, n_t, D, D, D, 1, st));
@@ -223,10 +234,17 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
     p[1].M = Mt; p[1].N = D; p[1].K = d.joint_dim; p[1].rows_per_batch = T; p[1].out = x_txt; p[1].ldo = D;
     QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS, st));
   }
+  if (!(stages & QIMG_STAGE_BLOCKS)) {
+    // staged call (step caches): leave block 0's modulated image stream in the workspace — the quantity TeaCache
+    // compares between steps (reference cache/teacache/extractors.py:206-209)
+    const char* mi0 = mod_all;
+    QIMG_TRY(qimg_ln_modulate(x_img, mi0, mi0 + (size_t)D * 2, xm_img, Mi, D, S_img, mod_stride, d.eps, st));
+  }
+  }  // QIMG_STAGE_PRE
 
   // ---- 60 dual-stream blocks -----------------------------------------------------------------
   const float sm_scale = 1.0f / sqrtf(128.0f);
-  for (int l = 0; l < L; ++l) {
+  for (int l = 0; (stages & QIMG_STAGE_BLOCKS) && l < L; ++l) {
     const qimg_block_weights& bw = e->blocks[l];
     // modulation layout per stream: [shift1, scale1, gate1, shift2, scale2, gate2] x D  (chunk(2) then chunk(3))
     const char* mi = mod_all + ((size_t)l * 12 * D) * 2;
@@ -301,6 +319,7 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
   }
 
   // ---- epilogue: AdaLayerNormContinuous (scale first, then shift) + proj_out -------------------
+  if (stages & QIMG_STAGE_POST) {
   QIMG_TRY(qimg_ln_modulate(x_img, (const char*)emb_out + (size_t)D * 2, emb_out, xm_img, Mi, D, S_img, emb_stride, d.eps, st));
   {
     qimg_gemm_problem p;
@@ -309,6 +328,7 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
     p.rows_per_batch = S_img; p.out = out; p.ldo = d.out_dim;
     QIMG_TRY(qimg_gemm(&p, 1, QIMG_EPI_BIAS, st));
   }
+  }  // QIMG_STAGE_POST
   return 0;
 }
 

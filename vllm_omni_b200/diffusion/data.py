@@ -6,6 +6,8 @@ entrypoints above the worker stay the reference's own and are out of scope.
 """
 from __future__ import annotations
 
+import os
+
 from contextlib import contextmanager
 from dataclasses import dataclass, field
 from typing import Any
@@ -64,6 +66,23 @@ class TransformerConfig:
 
 
 @dataclass
+class DiffusionCacheConfig:
+    """Cache-adapter parameters (reference data.py:120-200); only the TeaCache ones have a native consumer, unknown keys
+    (cache-dit's Fn_compute_blocks, ...) are accepted and kept for interface compatibility."""
+
+    rel_l1_thresh: float = 0.2
+    coefficients: list[float] | None = None
+    extra: dict[str, Any] = field(default_factory=dict)
+
+    @classmethod
+    def from_dict(cls, data: dict[str, Any]) -> "DiffusionCacheConfig":
+        if not isinstance(data, dict):
+            raise TypeError(f"Expected cache config dict, got {type(data)!r}")
+        known = {k: v for k, v in data.items() if k in ("rel_l1_thresh", "coefficients")}
+        return cls(**known, extra={k: v for k, v in data.items() if k not in known})
+
+
+@dataclass
 class OmniDiffusionConfig:
     model: str = ""
     model_class_name: str = "QwenImagePipeline"
@@ -74,7 +93,7 @@ class OmniDiffusionConfig:
     master_port: int | None = None
     vae_use_slicing: bool = False
     vae_use_tiling: bool = False
-    cache_backend: str | None = None
+    cache_backend: str | None = "none"  # "tea_cache" (reference data.py:261; env DIFFUSION_CACHE_BACKEND in from_kwargs)
     cache_config: Any = None
     # B200 engine extras (not in the reference): synthetic random weights instead of a checkpoint
     synthetic_weights_seed: int | None = None
@@ -86,9 +105,16 @@ class OmniDiffusionConfig:
             self.tf_model_config = TransformerConfig.from_dict(self.tf_model_config)
         if self.num_gpus is None:
             self.num_gpus = self.parallel_config.world_size
+        if isinstance(self.cache_config, dict):  # reference :438-443
+            self.cache_config = DiffusionCacheConfig.from_dict(self.cache_config)
+        elif not isinstance(self.cache_config, DiffusionCacheConfig):
+            self.cache_config = DiffusionCacheConfig()
 
     @classmethod
     def from_kwargs(cls, **kwargs) -> "OmniDiffusionConfig":
+        if "cache_backend" not in kwargs:  # reference :450-454
+            cb = os.environ.get("DIFFUSION_CACHE_BACKEND") or os.environ.get("DIFFUSION_CACHE_ADAPTER")
+            kwargs["cache_backend"] = cb.lower() if cb else "none"
         known = {f for f in cls.__dataclass_fields__}
         return cls(**{k: v for k, v in kwargs.items() if k in known})
 

@@ -215,6 +215,8 @@ class QwenImagePipeline(nn.Module):
         self.transformer.do_true_cfg = do_true_cfg
         # CFG parallel: rank 0 of the CFG group runs the positive branch, rank 1 the negative one
         cfg_par = do_true_cfg and _ps.get_cfg_parallel_world_size() == 2
+        if cfg_par:
+            self.transformer.do_true_cfg = False  # one branch per rank: the step cache keeps a single state here
         cfg_rank = _ps.get_cfg_parallel_rank() if cfg_par else 0
         if cfg_par and cfg_rank == 1:
             prompt_embeds, prompt_embeds_mask, txt_seq_lens = negative_prompt_embeds, negative_prompt_embeds_mask, negative_txt_seq_lens

@@ -298,6 +298,7 @@ class QwenImageTransformer2DModel(nn.Module):
         self._p2p_flags = None   # (local ptr, [ptr per rank]) barrier flags, exchanged once
         self._p2p_ws: dict = {}  # shape key -> (local ptr, [ptr per rank], nbytes)
         self._p2p_key = None
+        self._teacache = None  # set by cache.teacache.apply_teacache_hook
 
     # ------------------------------------------------------------------ weights
     def load_weights(self, weights: Iterable[tuple[str, torch.Tensor]]) -> set[str]:
@@ -541,10 +542,29 @@ class QwenImageTransformer2DModel(nn.Module):
             self._ws_current = (buf, off, nbytes)
             ws_ptr = buf.data_ptr() + off
         out = torch.empty((B, S_img, self.proj_out.out_features), dtype=torch.bfloat16, device=dev)
-        rc = qlib.load().qimg_engine_forward(
-            self._engine, hs.data_ptr(), enc.data_ptr(), ts.data_ptr(), n_t, ic.data_ptr(), isn.data_ptr(), tc.data_ptr(),
-            tsn.data_ptr(), B, S_img, T, out.data_ptr(), ws_ptr, nbytes, qlib.stream_ptr())
-        qlib.check(rc, "qimg_engine_forward")
+
+        def run_stage(stages: int):
+            rc = qlib.load().qimg_engine_forward_stages(
+                self._engine, stages, hs.data_ptr(), enc.data_ptr(), ts.data_ptr(), n_t, ic.data_ptr(), isn.data_ptr(),
+                tc.data_ptr(), tsn.data_ptr(), B, S_img, T, out.data_ptr(), ws_ptr, nbytes, qlib.stream_ptr())
+            qlib.check(rc, "qimg_engine_forward")
+
+        if self._teacache is None:
+            run_stage(qlib.STAGE_ALL)
+        else:
+            # step cache: the hook decides between the blocks and the cached residual (cache/teacache/hook.py)
+            if self.tp_size > 1 and self.tp_comm == "p2p":
+                raise NotImplementedError("TeaCache with the peer-memory TP workspace is not wired (use tp_comm='nccl')")
+            D = self.inner_dim
+            lib = qlib.load()
+
+            def view(o, rows):
+                o += off
+                return buf[o: o + rows * D * 2].view(torch.bfloat16).view(rows, D)
+
+            mod = view(lib.qimg_engine_ws_offset_mod(self._engine, B, S_img, T), B * S_img)
+            x_img = view(lib.qimg_engine_ws_offset_img(self._engine, B, S_img, T), B * S_img)
+            self._teacache.run(self, run_stage, mod, x_img, qlib)
         return Transformer2DModelOutput(sample=out)
 
     def debug_streams(self, B: int, S_img: int, T: int, device):

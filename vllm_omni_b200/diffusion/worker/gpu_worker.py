@@ -97,6 +97,11 @@ class GPUWorker:
                     self.pipeline.transformer.num_layers, seed=self.od_config.synthetic_weights_seed, device=device,
                     device_generate=True))
             logger.info("Worker %d: model ready in %.2fs", self.rank, time.perf_counter() - t0)
+            # step cache (reference gpu_worker.py:103-107)
+            from vllm_omni_b200.diffusion.cache.selector import get_cache_backend
+            self.cache_backend = get_cache_backend(self.od_config.cache_backend, self.od_config.cache_config)
+            if self.cache_backend is not None:
+                self.cache_backend.enable(self.pipeline)
 
     def generate(self, requests: list[OmniDiffusionRequest]) -> DiffusionOutput:
         return self.execute_model(requests, self.od_config)
@@ -107,6 +112,8 @@ class GPUWorker:
         if not reqs:
             raise ValueError("Cannot execute model with empty request list")
         req = reqs[0]  # one request at a time, as the reference scheduler sends them (scheduler.py:51-72)
+        if self.cache_backend is not None and self.cache_backend.is_enabled():  # reference :132-134
+            self.cache_backend.refresh(self.pipeline, req.num_inference_steps)
         dp = ps.get_data_parallel_world_size()
         if dp == 1:
             return self.pipeline.forward(req)

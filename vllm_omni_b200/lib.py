@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "qimg_umma_probe", "qimg_prof_enable", "qimg_prof_collect", "qimg_set_gemm_mode", "qimg_get_gemm_mode", "qimg_set_fmha_mode", "qimg_get_fmha_mode", "qimg_gate_residual_bias", "qimg_engine_set_tp",
     "qimg_p2p_alloc", "qimg_p2p_free", "qimg_ipc_get_handle", "qimg_ipc_open_handle", "qimg_ipc_close_handle",
     "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error", "qimg_set_fmha_trace",
+    "qimg_engine_forward_stages", "qimg_engine_ws_offset_mod", "qimg_rel_l1_sums", "qimg_bf16_sub", "qimg_bf16_add_inplace",
 ]
 
 
@@ -114,6 +115,12 @@ def load():
     lib.qimg_engine_ws_offset_txt.argtypes = [vp, i, i, i]
     lib.qimg_engine_ws_offset_txt.restype = sz
     lib.qimg_engine_forward.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp, sz, vp]
+    lib.qimg_engine_forward_stages.argtypes = [vp, i, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp, sz, vp]
+    lib.qimg_engine_ws_offset_mod.argtypes = [vp, i, i, i]
+    lib.qimg_engine_ws_offset_mod.restype = sz
+    lib.qimg_rel_l1_sums.argtypes = [vp, vp, ll, vp, vp]
+    lib.qimg_bf16_sub.argtypes = [vp, vp, vp, ll, vp]
+    lib.qimg_bf16_add_inplace.argtypes = [vp, vp, ll, vp]
     lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.qimg_set_gemm_mode.argtypes = [i]
     lib.qimg_set_fmha_mode.argtypes = [i]
@@ -314,3 +321,24 @@ def ipc_open_handle(handle: bytes) -> int:
 
 def ipc_close_handle(ptr: int):
     check(load().qimg_ipc_close_handle(C.c_void_p(ptr)), "qimg_ipc_close_handle")
+
+
+# ---- step-cache helpers (TeaCache) ---------------------------------------------------------------------------------
+STAGE_PRE, STAGE_BLOCKS, STAGE_POST, STAGE_ALL = 1, 2, 4, 7
+
+
+def rel_l1_sums(a: torch.Tensor, b: torch.Tensor, sums2: torch.Tensor):
+    """sums2 (fp32 [2], device) <- [sum |bf16(a - b)|, sum |b|]."""
+    _bf16c(a), _bf16c(b)
+    assert a.numel() == b.numel() and sums2.dtype == torch.float32 and sums2.numel() >= 2
+    check(load().qimg_rel_l1_sums(_p(a), _p(b), a.numel(), _p(sums2), stream_ptr()), "qimg_rel_l1_sums")
+
+
+def bf16_sub(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
+    _bf16c(out), _bf16c(a), _bf16c(b)
+    check(load().qimg_bf16_sub(_p(out), _p(a), _p(b), a.numel(), stream_ptr()), "qimg_bf16_sub")
+
+
+def bf16_add_inplace(x: torch.Tensor, r: torch.Tensor):
+    _bf16c(x), _bf16c(r)
+    check(load().qimg_bf16_add_inplace(_p(x), _p(r), x.numel(), stream_ptr()), "qimg_bf16_add_inplace")
