@@ -418,7 +418,8 @@ def test_staged_forward_equals_single_call(golden_dir):
     args = (fx["hidden_states"].to(dev), fx["encoder_hidden_states"].to(dev), None, fx["timestep"].to(dev),
             [[(1, h, w_)]] * c["B"], [c["T"]] * c["B"])
     ref = m(*args, return_dict=False)[0].clone()
-    apply_teacache_hook(m, TeaCacheConfig(rel_l1_thresh=1e-30, coefficients=[0.0, 0.0, 0.0, 1.0, 0.0]))
+    # constant polynomial 1.0 >= threshold: every step recomputes, i.e. the hook runs exactly PRE -> BLOCKS -> POST
+    apply_teacache_hook(m, TeaCacheConfig(rel_l1_thresh=0.5, coefficients=[0.0, 0.0, 0.0, 0.0, 1.0]))
     for _ in range(3):
         assert torch.equal(m(*args, return_dict=False)[0], ref)
     assert [d[1] for d in m._teacache.decisions] == [True, True, True]
