@@ -267,3 +267,48 @@ def test_teacache_config_selector_and_decision_logic():
     assert any(seen) and not all(seen)
     hook.reset_state()
     assert hook._forward_cnt == 0 and hook.decisions == []
+
+
+def test_edit_pipeline_condition_latents_host_logic():
+    """QwenImageEditPipeline._condition_latents: grid bookkeeping and the batch-replication rule of the reference's
+    prepare_latents (pipeline_qwen_image_edit.py:508-517), without touching the GPU."""
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image_edit import QwenImageEditPipeline
+    from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+    f = QwenImageEditPipeline._condition_latents
+    shapes = [[(1, 8, 6)]] * 4
+    assert f(None, OmniDiffusionRequest(), 4, shapes) == (None, shapes)            # no image: text-to-image path
+    il = torch.zeros(2, 24, 64, dtype=torch.bfloat16)
+    out, sh = f(None, OmniDiffusionRequest(extra={"image_latents": il, "image_latent_grid": (4, 6)}), 4, shapes)
+    assert out.shape == (4, 24, 64) and sh == [[(1, 8, 6), (1, 4, 6)]] * 4
+    with pytest.raises(ValueError):   # 3 condition images cannot be spread over 4 prompts
+        f(None, OmniDiffusionRequest(extra={"image_latents": torch.zeros(3, 24, 64), "image_latent_grid": (4, 6)}), 4, shapes)
+    with pytest.raises(ValueError):   # grid does not describe the latents
+        f(None, OmniDiffusionRequest(extra={"image_latents": il, "image_latent_grid": (5, 6)}), 4, shapes)
+    with pytest.raises(ValueError):
+        f(None, OmniDiffusionRequest(extra={"image_latents": il}), 4, shapes)
+
+
+def test_c_abi_argument_checks_without_gpu():
+    """Entry points validate their arguments before any CUDA call: exercised on the CPU-only build host (no compute)."""
+    import ctypes as C
+    lib = qlib.load()
+    dims = qlib.Dims(2, 24, 128, 64, 64, 3584, 1e-6)
+    g, blocks, h = qlib.GlobalWeights(), (qlib.BlockWeights * 2)(), C.c_void_p()
+    assert lib.qimg_engine_create(C.byref(dims), C.byref(g), blocks, C.byref(h)) == 0
+    try:
+        two = (C.c_void_p * 2)(1024, 2048)
+        assert lib.qimg_engine_set_tp_p2p(h, 3, 0, two, two) != 0 and b"tp_size" in lib.qimg_last_error()
+        assert lib.qimg_engine_set_tp_p2p(h, 2, 2, two, two) != 0 and b"rank" in lib.qimg_last_error()
+        assert lib.qimg_engine_set_tp_p2p(h, 2, 0, (C.c_void_p * 2)(1024, None), two) != 0
+        assert lib.qimg_engine_set_tp(h, 5, qlib.ALLREDUCE_FN(lambda *a: 0), None) != 0   # 5 does not divide 24 heads
+        assert lib.qimg_engine_set_tp(h, 2, C.cast(None, qlib.ALLREDUCE_FN), None) != 0   # TP needs a callback
+        assert lib.qimg_engine_forward_stages(h, 0, *([None] * 3), 1, *([None] * 4), 1, 64, 8, None, None, 0, None) != 0
+        assert b"stage" in lib.qimg_last_error()
+        assert lib.qimg_engine_workspace_bytes(h, 1, 4096, 128) > 4096 * 3072 * 2 * 4
+        assert lib.qimg_engine_ws_offset_mod(h, 1, 4096, 128) > lib.qimg_engine_ws_offset_txt(h, 1, 4096, 128) > 0
+    finally:
+        lib.qimg_engine_destroy(h)
+    bad = qlib.Dims(2, 24, 64, 64, 64, 3584, 1e-6)
+    assert lib.qimg_engine_create(C.byref(bad), C.byref(g), blocks, C.byref(h)) != 0 and b"head_dim" in lib.qimg_last_error()
+    assert lib.qimg_set_fmha_mode(7) != 0 and lib.qimg_set_gemm_mode(2) != 0
+    assert lib.qimg_rel_l1_sums(None, None, 12, None, None) != 0 and b"multiple of 8" in lib.qimg_last_error()

@@ -1,22 +1,23 @@
-"""reference vllm_omni/diffusion/cache/teacache/state.py:9-38.  The tensors are device buffers owned by the state and
-reused across steps (no per-step allocation)."""
+"""Per-branch TeaCache state (what reference cache/teacache/state.py:9-38 tracks), with device buffers that are
+allocated once and overwritten in place instead of re-created every step."""
 from __future__ import annotations
 
 import torch
 
 
 class TeaCacheState:
-    def __init__(self):
-        self.cnt = 0
-        self.accumulated_rel_l1_distance = 0.0
-        self.previous_modulated_input: torch.Tensor | None = None
-        self.previous_residual: torch.Tensor | None = None
-        self.previous_residual_encoder: torch.Tensor | None = None  # not kept: the text stream never reaches the output
-        self.has_mod = False
-        self.has_residual = False
+    __slots__ = ("cnt", "accumulated_rel_l1_distance", "previous_modulated_input", "previous_residual",
+                 "previous_residual_encoder", "has_mod", "has_residual")
+
+    def __init__(self) -> None:
+        self.previous_modulated_input: torch.Tensor | None = None  # block 0's modulated image stream of the last step
+        self.previous_residual: torch.Tensor | None = None          # x_img(after blocks) - x_img(before), last computed step
+        self.previous_residual_encoder: torch.Tensor | None = None  # never filled: the text stream does not reach the output
+        self.reset()
 
     def reset(self) -> None:
-        self.cnt = 0
+        """New generation: forget the validity of the buffers (the storage itself is kept for reuse)."""
+        self.cnt = 0                              # forwards seen by this branch
         self.accumulated_rel_l1_distance = 0.0
         self.has_mod = False
         self.has_residual = False
