@@ -312,3 +312,24 @@ def test_c_abi_argument_checks_without_gpu():
     assert lib.qimg_engine_create(C.byref(bad), C.byref(g), blocks, C.byref(h)) != 0 and b"head_dim" in lib.qimg_last_error()
     assert lib.qimg_set_fmha_mode(7) != 0 and lib.qimg_set_gemm_mode(2) != 0
     assert lib.qimg_rel_l1_sums(None, None, 12, None, None) != 0 and b"multiple of 8" in lib.qimg_last_error()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one): one JSON line with the contract's
+    keys; run here at a reduced resolution so that it takes seconds."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--res", "256", "--txt-len", "32"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0 and line["vs_baseline"] is None
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and 1 <= cb["cores"] <= (os.cpu_count() or 1) and cb["value"] == line["value"] and "probe" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
