@@ -48,9 +48,13 @@ int qimg_get_gemm_mode(void);
  *            2 = 80-row KV tiles, P in its own TMEM region: softmax and tensor pipes fully decoupled, the MMA
  *                warp issues whatever is ready; half-empty query-tile pairs skip the empty tile and run last;
  *            3 = like 2 with 64-row KV tiles;
- *            4 = like 0 with TWO softmax threads per query row (16 softmax warps).
+ *            4 = like 0 with TWO softmax threads per query row (16 softmax warps);
+ *            5 = like 0 with the DELAYED reference maximum (tile j is exponentiated against the maximum over tiles < j;
+ *                exponents clamped at 2^96) and P handed over in four quarters;
+ *            6 = like 4 with the delayed reference maximum, one pass over the scores and P handed over in two halves
+ *                (DEFAULT: mode 6).  Pipelines 0-4 reduce every tile's maximum first and are exact for any input.
  *   poly 0..3 = 0 / 25 / 37.5 / 50 % of the softmax exponentials on a degree-3 FMA-pipe polynomial.
- *   pingpong  = strict alternation of the two softmax warpgroups' exp phases (pipelines 0 and 4).
+ *   pingpong  = strict alternation of the two softmax warpgroups' exp phases (pipelines 0, 4, 5, 6).
  * Env QIMG_FMHA_MODE overrides the default. */
 int qimg_set_fmha_mode(int mode);
 int qimg_get_fmha_mode(void);
