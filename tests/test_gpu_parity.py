@@ -464,6 +464,33 @@ def test_teacache_trajectory_vs_reference_hook(golden_dir, cfg):
         assert O.rel_fro(out.output.cpu(), want["latents"]) < 1e-2
 
 
+@pytest.mark.parametrize("cfg", [False, True])
+def test_diffuse_vs_reference_loop_golden(golden_dir, cfg):
+    """Native denoise loop (engine forwards + fused CFG / Euler kernel) against the latents the reference's OWN
+    `QwenImagePipeline.diffuse` produced on CPU (tests/golden/diffuse_tiny.pt; negative prompt of a different length)."""
+    from vllm_omni_b200.diffusion.data import OmniDiffusionConfig, TransformerConfig
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image import QwenImagePipeline
+    from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+    fx = torch.load(os.path.join(golden_dir, "diffuse_tiny.pt"), weights_only=False)
+    c = fx["case"]
+    od = OmniDiffusionConfig(tf_model_config=TransformerConfig.from_dict({"num_layers": c["L"]}))
+    torch.set_default_dtype(bf)
+    try:
+        with torch.device(dev):
+            pipe = QwenImagePipeline(od_config=od, transformer_kwargs=dict(num_attention_heads=c["H"], joint_attention_dim=c["joint"]))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    pipe.transformer.load_weights(synthetic.synthetic_weights(c["L"], seed=c["seed"], norm_jitter=0.1, num_heads=c["H"],
+                                                              joint_dim=c["joint"]))
+    h, w_ = c["grid"]
+    req = OmniDiffusionRequest(prompt_embeds=fx["prompt_embeds"], negative_prompt_embeds=fx["negative_prompt_embeds"] if cfg else None,
+                               latents=fx["latents0"], height=h * 16, width=w_ * 16, num_inference_steps=c["steps"],
+                               true_cfg_scale=c["true_cfg_scale"] if cfg else 1.0, output_type="latent")
+    out = pipe.forward(req)
+    assert out.error is None and np.array_equal(pipe.scheduler.sigmas.numpy(), fx["sigmas"])
+    assert O.rel_fro(out.output.cpu(), fx["cfg" if cfg else "nocfg"]) < 1e-2
+
+
 def test_full_size_properties_1024px():
     """BASELINE configs[1] sizes (1024px, S_img=4096, T=128, D=3072; depth cut to L=2 to bound memory/time):
     size-independent properties — batch rows are independent and deterministic; CFG with identical branches is the

@@ -105,3 +105,17 @@ def test_teacache_oracle_matches_reference_hook(golden_dir, cfg):
     assert [d[1] for d in tc.decisions] == want["decisions"]
     assert any(want["decisions"][1:]) and not all(want["decisions"])  # both paths exercised
     assert torch.equal(out, want["latents"])
+
+
+@pytest.mark.parametrize("cfg", [False, True])
+def test_oracle_diffuse_matches_reference_loop(golden_dir, cfg):
+    """oracle.diffuse against the fixture produced by executing the reference's own `QwenImagePipeline.diffuse`
+    (pipeline_qwen_image.py:530-586: timestep handling, both forwards, true-CFG combine + norm rescale) on CPU
+    (oracle/make_golden_diffuse.py; only the diffusers scheduler object is an adapter): bit-identical latents."""
+    fx = torch.load(os.path.join(golden_dir, "diffuse_tiny.pt"), weights_only=False)
+    c = fx["case"]
+    w = _weights(c)
+    dims = O.DiTDims(num_layers=c["L"], num_heads=c["H"], joint_dim=c["joint"])
+    out = O.diffuse(w, dims, fx["latents0"].clone(), fx["prompt_embeds"], fx["negative_prompt_embeds"] if cfg else None,
+                    fx["sigmas"], (1,) + tuple(c["grid"]), c["true_cfg_scale"])
+    assert torch.equal(out, fx["cfg" if cfg else "nocfg"])
