@@ -333,3 +333,75 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and 1 <= cb["cores"] <= (os.cpu_count() or 1) and cb["value"] == line["value"] and "probe" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_worker_proc_message_protocol(monkeypatch):
+    """The runner protocol of the reference WorkerProc (gpu_worker.py:143-314): rpc dicts (output_rank /
+    exec_all_ranks), request lists -> execute_model, exceptions -> DiffusionOutput(error=...), shutdown, ready handshake.
+    The GPU worker itself is replaced by a recorder: this is host logic only."""
+    from vllm_omni_b200.diffusion.data import DiffusionOutput
+    from vllm_omni_b200.diffusion.worker import gpu_worker as gw
+
+    class Recorder:
+        def __init__(self):
+            self.calls, self.shut = [], False
+
+        def generate(self, reqs):
+            self.calls.append(("generate", reqs))
+            return DiffusionOutput(output=torch.zeros(1))
+
+        def execute_model(self, reqs, od):
+            self.calls.append(("execute_model", reqs))
+            if reqs == ["boom"]:
+                raise RuntimeError("kernel launch failed")
+            return DiffusionOutput(output=torch.ones(1))
+
+        def ping(self, x, y=0):
+            return x + y
+
+        def shutdown(self):
+            self.shut = True
+
+    class Queue:
+        def __init__(self, items=()):
+            self.items = list(items)
+            self.out = []
+
+        def dequeue(self, indefinite=True):
+            return self.items.pop(0)
+
+        def enqueue(self, x):
+            self.out.append(x)
+
+    class Pipe:
+        sent = None
+
+        def send(self, m):
+            Pipe.sent = m
+
+    monkeypatch.setattr(gw.WorkerProc, "_create_worker", lambda self, gpu_id, od: Recorder())
+    od = OmniDiffusionConfig()
+    msgs = [
+        {"type": "rpc", "method": "ping", "args": (2,), "kwargs": {"y": 3}, "output_rank": 0},
+        {"type": "rpc", "method": "ping", "args": (1,), "output_rank": 1},                  # not for this rank: ignored
+        {"type": "rpc", "method": "ping", "args": (5,), "output_rank": 1, "exec_all_ranks": True},  # executed, no reply
+        {"type": "rpc", "method": "nope", "output_rank": None},                              # error reply, loop survives
+        [],                                                                                  # empty message: skipped
+        ["req"],
+        ["boom"],
+        {"type": "shutdown"},
+    ]
+    res = Queue()
+    gw.WorkerProc.worker_main(0, od, Pipe(), Queue(msgs), result_queue=res)
+    assert Pipe.sent == {"status": "ready", "result_handle": None}
+    assert res.out[0] == 5
+    assert isinstance(res.out[1], dict) and res.out[1]["status"] == "error" and "nope" in res.out[1]["error"]
+    assert isinstance(res.out[2], DiffusionOutput) and res.out[2].error is None
+    assert isinstance(res.out[3], DiffusionOutput) and res.out[3].error == "kernel launch failed"
+    assert len(res.out) == 4
+    # a non-zero rank never owns the result queue (reference :165-170)
+    p1 = gw.WorkerProc(od, gpu_id=1, broadcast_queue=Queue([{"type": "shutdown"}]), result_queue=Queue())
+    assert p1.result_mq is None
+    p1.worker_busy_loop()
+    assert p1.worker.shut
+    assert gw.get_diffusion_worker_class() is gw.WorkerProc
