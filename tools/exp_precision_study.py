@@ -7,7 +7,8 @@ kernels.  Output: relative Frobenius error of softmax(QK^T)V against float64.
 
 Result on 2026-09 (S=4224, d=128): fp32 1.6e-3 / f16x2 1.7e-3 / bf16x2 3.6e-3 at |s|max~5; 4.4e-4 / 4.5e-4 / 6.6e-4 at
 |s|max~46; f16x2 with delta=8: 1.8e-3 / 4.7e-4.  The error is dominated by the bf16 rounding of P; f16x2 exponentials
-(half the XU instructions) are essentially free in accuracy, but fp16's 2^16 range needs the clamp at 15 instead of 96."""
+are essentially free in accuracy, but fp16's 2^16 range needs the clamp at 15 instead of 96 - and on sm_100a ptxas lowers
+`ex2.approx.f16x2` to two MUFU.EX2.F16 per pair, so it saves XU work only if that form issues faster (unmeasured)."""
 import math
 
 import torch
