@@ -340,9 +340,12 @@ def main():
             line["e2e"] = {"value": n_img / (ms_e2e_max / 1e3), "unit": UNIT,
                            "h2d_bytes_per_step": (lat_h.numel() + txt_h.numel() * (2 if args.cfg else 1)) * 2 * world,
                            "d2h_bytes_per_step": out_h.numel() * 2 * world}
-        if not args.no_cpu_baseline:
-            v, s, desc = cpu_reference_sample(res, T, NS, L, cfg=args.cfg)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": desc}
+        if not args.no_cpu_baseline and world == 1:  # the CPU leg is reported on rank 0 at N=1 only
+            try:
+                v, s, desc = cpu_reference_sample(res, T, NS, L, cfg=args.cfg)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": desc}
+            except Exception as exc:  # never lose the measured line to a host-side failure
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc!r}"}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
