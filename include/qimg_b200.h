@@ -42,20 +42,16 @@ int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* f
 int qimg_set_gemm_mode(int mode);
 int qimg_get_gemm_mode(void);
 
-/* Attention pipeline tuning, mode = pipeline | (poly << 3) | (pingpong << 5):
- *   pipeline 0 = 128-row KV tiles, P aliases S in TMEM (fixed issue order QK0 PV1 QK1 PV0);
- *            1 = 64-row KV tiles, double-buffered S;
- *            2 = 80-row KV tiles, P in its own TMEM region: softmax and tensor pipes fully decoupled, the MMA
- *                warp issues whatever is ready; half-empty query-tile pairs skip the empty tile and run last;
- *            3 = like 2 with 64-row KV tiles;
- *            4 = like 0 with TWO softmax threads per query row (16 softmax warps);
- *            5 = like 0 with the DELAYED reference maximum (tile j is exponentiated against the maximum over tiles < j;
- *                exponents clamped at 2^96) and P handed over in four quarters;
- *            6 = like 4 with the delayed reference maximum, one pass over the scores and P handed over in two halves
- *                (DEFAULT: mode 6).  Pipelines 0-4 reduce every tile's maximum first and are exact for any input.
- *   poly 0..3 = 0 / 25 / 37.5 / 50 % of the softmax exponentials on a degree-3 FMA-pipe polynomial.
- *   pingpong  = strict alternation of the two softmax warpgroups' exp phases (pipelines 0, 4, 5, 6).
- * Env QIMG_FMHA_MODE overrides the default. */
+/* Attention pipeline, mode = pipeline | (poly << 3):
+ *   pipeline 4 = EXACT: every KV tile's row maximum is reduced (and exchanged between the two threads of a row) before
+ *                the tile is exponentiated; correct for any input;
+ *            6 = FAST (default): tile j >= 1 is exponentiated in one pass against the running reference maximum the row
+ *                already has, the tile's own maximum only decides the lazy rebase of O / l afterwards, P is handed to the
+ *                tensor pipe in two halves.  Exact as long as no score exceeds the reference by more than 2^100 (a jump
+ *                of > 69 nats inside one 128-key tile); such a launch sets a device-side flag — see qimg_fmha_overflow —
+ *                and the caller must recompute with pipeline 4 (the native denoise loop does, once per 50 steps).
+ *   poly 1 = 25 % of the softmax exponentials on a degree-3 FMA-pipe polynomial instead of MUFU.EX2.
+ * Env QIMG_FMHA_MODE overrides the default.  (Round 1 shipped seven pipelines; five lost and were deleted.) */
 int qimg_set_fmha_mode(int mode);
 int qimg_get_fmha_mode(void);
 
@@ -138,10 +134,18 @@ int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_s
  * backends/sdpa.py:46-66) and the cat/split around it (qwen_image_transformer.py:414-416,448-449). */
 int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
                     int T, float softmax_scale, qimg_stream_t stream);
-/* Diagnostics: when set to a device buffer of 32 int64, attention pipelines 0 and 4 (fmha mode & 7) record the cycle
+/* Same with an explicit pipeline (`mode` as in qimg_set_fmha_mode; < 0 = the process default).  The layer-level
+ * AttentionImpl plug-in passes 4 (exact): it has no end-of-denoise point at which to consult the overflow flag. */
+int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
+                         int T, float softmax_scale, int mode, qimg_stream_t stream);
+/* Overflow flag of the fast pipeline on the current device: *out = 1 if any launch since the last reset saw a score more
+ * than 2^100 above its row's reference maximum (results of that launch are then not trustworthy).  Synchronising 4-byte
+ * read; reset != 0 clears the flag.  Reference semantics being guarded: exact softmax, attention/backends/sdpa.py:56-64. */
+int qimg_fmha_overflow(int* out, int reset);
+/* Diagnostics: when set to a device buffer of 32 int64, the attention kernels record the cycle
  * counters of CTA 200: [0] MMA-warp loop, [1..4] its waits on K, P1, V, P0, [5] KV tiles; [8..14] / [16..22] tile-0 /
- * tile-1 softmax warp: loop, wait on S, score load (+ max in pipeline 4), max (pair barrier in 4), ping-pong barrier,
- * exponentials + P stores, tail (store wait, fence, arrive).  NULL disables. */
+ * tile-1 softmax warp: loop, wait on S, score load (+ max in pipeline 4), pair barrier, rebase check,
+ * exponentials + P stores, tail (store wait, fence, arrive).  NULL disables.  Needs a -DQIMG_FMHA_TRACE build. */
 int qimg_set_fmha_trace(void* dev_buf_32_i64);
 
 /* ---- whole-model engine ------------------------------------------------------------- */

@@ -34,6 +34,12 @@ CASES = {
     # image-edit layout (pipeline_qwen_image_edit.py:602): noisy latents (8x6) followed by one condition image (4x6) on
     # the sequence axis; two RoPE grids, text positions after the larger one
     "tiny_edit_two_grids": dict(L=2, H=2, joint=256, B=2, grid=(8, 6), extra_grids=[(4, 6)], T=24, seed=5),
+    # the headline shape of BASELINE configs[1] (1024 px: 64x64 latent grid, T=128, D=3072, H=24, S=4224: 33 KV tiles,
+    # 17 query-tile pairs, 8-band GEMM raster), depth cut to 2 so the fp32 reference fits the build container
+    "fullwidth_1024px_L2": dict(L=2, H=24, joint=3584, B=1, grid=(64, 64), T=128, seed=6),
+    # FULL DEPTH (L=60) for criterion (iii) at a reduced width (H=8, D=1024) and grid so that the unmodified reference
+    # runs in bf16 AND fp32 on the CPU (60 full-width fp32 blocks = 81 GB do not fit the 62 GB container)
+    "narrow_L60_H8": dict(L=60, H=8, joint=1024, B=1, grid=(16, 16), T=32, seed=7),
 }
 
 

@@ -13,8 +13,14 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libqimg_b200.so")
 SOURCES = ["qimg_api.cu", "qimg_engine.cu", "qimg_tp_p2p.cu"]
-HEADERS = ["qimg_common.cuh", "qimg_elementwise.cuh", "qimg_gemm.cuh", "qimg_gemm2.cuh", "qimg_fmha.cuh", "qimg_fmha2.cuh", "qimg_fmha3.cuh", "qimg_fmha4.cuh", "qimg_fmha5.cuh", "qimg_fmha6.cuh", "qimg_host.cuh",
-           os.path.join("..", "..", "include", "qimg_b200.h")]
+HEADERS = ["qimg_common.cuh", "qimg_elementwise.cuh", "qimg_gemm.cuh", "qimg_gemm2.cuh", "qimg_fmha.cuh", "qimg_fmha4.cuh",
+           "qimg_fmha6.cuh", "qimg_host.cuh", os.path.join("..", "..", "include", "qimg_b200.h")]
+FLAGS_STAMP = LIB_PATH + ".flags"  # the optional build flags the existing .so was compiled with
+
+
+def _opt_flags() -> list[str]:
+    return ["--use_fast_math" if os.environ.get("QIMG_FAST_MATH") else "-DQIMG_NO_FAST_MATH",
+            *(["-DQIMG_FMHA_TRACE"] if os.environ.get("QIMG_FMHA_TRACE") else [])]
 
 
 def _nvcc() -> str:
@@ -27,6 +33,12 @@ def _nvcc() -> str:
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
+    try:  # a .so built with other optional flags (trace counters, fast math) is stale for this environment
+        with open(FLAGS_STAMP) as f:
+            if f.read().split() != _opt_flags():
+                return True
+    except OSError:
+        return True
     t = os.path.getmtime(LIB_PATH)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
     return any(os.path.exists(p) and os.path.getmtime(p) > t for p in deps)
@@ -36,10 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "--use_fast_math" if os.environ.get("QIMG_FAST_MATH") else "-DQIMG_NO_FAST_MATH",
-           *(["-DQIMG_FMHA_TRACE"] if os.environ.get("QIMG_FMHA_TRACE") else []),
-           *(["-DQIMG_FMHA_NOCLAMP"] if os.environ.get("QIMG_FMHA_NOCLAMP") else []),  # experiment only
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+           *_opt_flags(), "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -48,6 +57,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    with open(FLAGS_STAMP, "w") as f:
+        f.write(" ".join(_opt_flags()))
     return LIB_PATH
 
 

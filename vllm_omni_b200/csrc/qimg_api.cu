@@ -7,10 +7,7 @@
 
 #include "qimg_elementwise.cuh"
 #include "qimg_fmha.cuh"
-#include "qimg_fmha2.cuh"
-#include "qimg_fmha3.cuh"
 #include "qimg_fmha4.cuh"
-#include "qimg_fmha5.cuh"
 #include "qimg_fmha6.cuh"
 #include "qimg_gemm.cuh"
 #include "qimg_gemm2.cuh"
@@ -21,14 +18,36 @@ namespace qimg {
 thread_local std::string g_last_error;
 std::atomic<long long> g_launch_count{0};
 
+constexpr int kMaxDevices = 64;
+
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
 int device_sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0) return -1;
+  if (cached[dev] > 0) return cached[dev];
+  int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  cached = n;
+  cached[dev] = n;
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): set it once for each device this process
+// launches on (`done` is the launcher's own static table)
+template <typename K>
+static int ensure_smem_attr(K kernel, int smem_bytes, bool (&done)[kMaxDevices]) {
+  const int dev = current_device();
+  if (dev < 0) return fail("no CUDA device");
+  if (!done[dev]) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    done[dev] = true;
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -38,11 +57,13 @@ struct ProfRec {
   cudaEvent_t a, b;
   double flops;
 };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;                      // guards g_prof / g_event_pool (launches may come from several host threads)
 static std::vector<ProfRec> g_prof[2];            // 0 = gemm, 1 = fmha
 static std::vector<cudaEvent_t> g_event_pool;
 
 static cudaEvent_t prof_event() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   if (!g_event_pool.empty()) {
     cudaEvent_t e = g_event_pool.back();
     g_event_pool.pop_back();
@@ -57,7 +78,7 @@ struct ProfScope {
   cudaStream_t st;
   ProfRec rec;
   bool on;
-  ProfScope(int kind_, double flops, cudaStream_t st_) : kind(kind_), st(st_), on(g_prof_on) {
+  ProfScope(int kind_, double flops, cudaStream_t st_) : kind(kind_), st(st_), on(g_prof_on.load()) {
     if (on) {
       rec.a = prof_event();
       rec.b = prof_event();
@@ -68,6 +89,7 @@ struct ProfScope {
   ~ProfScope() {
     if (on) {
       cudaEventRecord(rec.b, st);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
       g_prof[kind].push_back(rec);
     }
   }
@@ -147,6 +169,13 @@ static const CUtensorMap* get_tmap(const void* ptr, uint64_t cols, uint64_t rows
   auto ins = g_tmaps.emplace(key, tm);
   return &ins.first->second;
 }
+// Bounded cache: descriptors are keyed by raw pointer and activation buffers come and go with the caller's allocator.
+// Called at the START of a launcher (never between two get_tmap calls of one launch, whose returned pointers must stay
+// valid until the kernel is enqueued — the descriptor is copied into the kernel's parameter space at launch).
+void tmap_cache_trim() {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmaps.size() >= 4096) g_tmaps.clear();
+}
 const CUtensorMap* get_tmap_2d(const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
   return get_tmap(ptr, cols, rows, 0, box_rows);
 }
@@ -159,12 +188,9 @@ const CUtensorMap* get_tmap_3d(const void* ptr, uint64_t cols, uint64_t rows, ui
 // ------------------------------------------------------------------------------------------
 template <int BN, int EPI>
 static int launch_gemm_inst(const CUtensorMap* tA[2], const CUtensorMap* tB[2], const GemmParams& prm, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_done[kMaxDevices] = {};
   constexpr int smem = gemm_smem_bytes<BN>();
-  if (!attr_set) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  if (ensure_smem_attr(gemm_umma_kernel<BN, EPI>, smem, attr_done)) return 1;
   int sms = device_sm_count();
   if (sms <= 0) return fail("no CUDA device");
   int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
@@ -175,11 +201,8 @@ static int launch_gemm_inst(const CUtensorMap* tA[2], const CUtensorMap* tB[2], 
 
 template <int EPI>
 static int launch_gemm2_inst(const CUtensorMap* tA[2], const CUtensorMap* tB[2], const GemmParams& prm, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
-    attr_set = true;
-  }
+  static bool attr_done[kMaxDevices] = {};
+  if (ensure_smem_attr(gemm_umma2_kernel<EPI>, GEMM2_SMEM_BYTES, attr_done)) return 1;
   int sms = device_sm_count();
   if (sms <= 0) return fail("no CUDA device");
   int clusters = sms / 2;
@@ -201,6 +224,7 @@ static int gemm_mode() {
 
 static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStream_t st) {
   if (nprob < 1 || nprob > 2) return fail("qimg_gemm: nprob must be 1 or 2");
+  tmap_cache_trim();
   int maxN = 0;
   for (int i = 0; i < nprob; ++i) maxN = pr[i].N > maxN ? pr[i].N : maxN;
   const int BN = (maxN <= 64 && epi == QIMG_EPI_BIAS) ? 64 : 256;
@@ -366,40 +390,31 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 static long long* g_fmha_trace = nullptr;  // qimg_set_fmha_trace (diagnostics)
 using namespace qimg;
 
-template <uint32_t MASK>
-static int launch_fmha_inst(int pipeline, bool pingpong, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
-                            const FmhaParams& prm, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v7<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v7<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v8<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v8<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v9<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v9<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA4_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v5<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA2_SMEM_BYTES));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmha3_smem_bytes<80>()));
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(fmha_joint_kernel_v6<MASK, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, fmha3_smem_bytes<64>()));
-    attr_set = true;
+// Overflow flag of the fast attention pipeline: one int per device, owned by the library (4 bytes, allocated on first use)
+static int* g_fmha_ovf[qimg::kMaxDevices] = {};
+static int* fmha_overflow_flag() {
+  const int dev = current_device();
+  if (dev < 0) return nullptr;
+  if (!g_fmha_ovf[dev]) {
+    if (cudaMalloc(&g_fmha_ovf[dev], sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(g_fmha_ovf[dev], 0, sizeof(int));
   }
+  return g_fmha_ovf[dev];
+}
+
+template <uint32_t MASK>
+static int launch_fmha_inst(int pipeline, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
+                            const FmhaParams& prm, cudaStream_t st) {
+  static bool done7[kMaxDevices] = {}, done9[kMaxDevices] = {};
   const int pairs = (prm.S + 255) / 256;
-  const dim3 grid2(pairs, prm.B * prm.H);
+  const int grid = pairs * prm.B * prm.H;
   if (pipeline == 6) {
-    if (pingpong) fmha_joint_kernel_v9<MASK, true><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-    else fmha_joint_kernel_v9<MASK, false><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  } else if (pipeline == 5) {
-    if (pingpong) fmha_joint_kernel_v8<MASK, true><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-    else fmha_joint_kernel_v8<MASK, false><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  } else if (pipeline == 4) {
-    if (pingpong) fmha_joint_kernel_v7<MASK, true><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-    else fmha_joint_kernel_v7<MASK, false><<<pairs * prm.B * prm.H, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  } else if (pipeline == 2) fmha_joint_kernel_v6<MASK, 80><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<80>(), st>>>(*tq, *tk, *tv, prm);
-  else if (pipeline == 3) fmha_joint_kernel_v6<MASK, 64><<<pairs * prm.B * prm.H, FMHA_THREADS, fmha3_smem_bytes<64>(), st>>>(*tq, *tk, *tv, prm);
-  else if (pipeline == 1) fmha_joint_kernel_v5<MASK><<<grid2, FMHA_THREADS, FMHA2_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else if (pingpong) fmha_joint_kernel<MASK, true><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  else fmha_joint_kernel<MASK, false><<<pairs * prm.B * prm.H, FMHA_THREADS, FMHA_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+    if (ensure_smem_attr(fmha_joint_kernel_v9<MASK>, FMHA4_SMEM_BYTES, done9)) return 1;
+    fmha_joint_kernel_v9<MASK><<<grid, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  } else {
+    if (ensure_smem_attr(fmha_joint_kernel_v7<MASK>, FMHA4_SMEM_BYTES, done7)) return 1;
+    fmha_joint_kernel_v7<MASK><<<grid, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  }
   QIMG_LAUNCH_CHECK("fmha_joint_kernel");
   return 0;
 }
@@ -411,7 +426,7 @@ const char* qimg_last_error(void) { return g_last_error.c_str(); }
 long long qimg_launch_count(void) { return g_launch_count.load(); }
 void qimg_reset_launch_count(void) { g_launch_count.store(0); }
 
-void qimg_prof_enable(int on) { g_prof_on = on != 0; }
+void qimg_prof_enable(int on) { g_prof_on.store(on != 0); }
 
 int qimg_set_gemm_mode(int mode) {
   if (mode != 0 && mode != 1) return fail("qimg_set_gemm_mode: mode must be 0 (cta_group::1) or 1 (cta_group::2 pair)");
@@ -423,6 +438,7 @@ int qimg_get_gemm_mode(void) { return gemm_mode(); }
 int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* flops_total) {
   if (kind < 0 || kind > 1) return fail("qimg_prof_collect: kind");
   double ms = 0, fl = 0;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (ProfRec& r : g_prof[kind]) {
     QIMG_CUDA_CHECK(cudaEventSynchronize(r.b));
     float t = 0;
@@ -545,11 +561,8 @@ int qimg_linear_small_m(const void* x, const void* W, const void* bias, void* y,
   if (M <= 0 || N <= 0) return 0;
   if (K % 8) return fail("qimg_linear_small_m: K must be a multiple of 8");
   if (M > 64) return fail("qimg_linear_small_m: M > 64 (use qimg_gemm)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(linear_small_m_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * 2));
-    attr_set = true;
-  }
+  static bool attr_done[kMaxDevices] = {};
+  if (ensure_smem_attr(linear_small_m_kernel<8>, 8 * 4096 * 2, attr_done)) return 1;
   if (K > 4096) return fail("qimg_linear_small_m: K > 4096");
   const int sms = device_sm_count();
   for (int m0 = 0; m0 < M; m0 += 8) {
@@ -588,17 +601,20 @@ int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_s
   return launch_gemm(problems, nprob, epilogue, (cudaStream_t)stream);
 }
 
-// 0 = first-generation pipeline (128-row KV tiles), 1 = double-buffered-S pipeline (64-row KV tiles)
+// mode = pipeline | (poly << 3): pipeline 6 = fast (delayed reference maximum, guarded by the overflow flag; DEFAULT),
+// pipeline 4 = exact (every tile's maximum reduced first); poly 1 = 25 % of the exponentials on the FMA-pipe polynomial
 static int g_fmha_mode = -1;
 static int fmha_mode() {
   if (g_fmha_mode < 0) {
     const char* e = getenv("QIMG_FMHA_MODE");
-    g_fmha_mode = e ? atoi(e) : 6;  // two threads per row, delayed reference maximum, half-tile P hand-off (best of the sweep, profiles/)
+    g_fmha_mode = e ? atoi(e) : 6;
+    if ((g_fmha_mode & 7) != 4 && (g_fmha_mode & 7) != 6) g_fmha_mode = 6;
   }
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode < 0 || mode > 63 || (mode & 7) > 6) return fail("qimg_set_fmha_mode: bad mode");
+  if (mode < 0 || mode > 15 || ((mode & 7) != 4 && (mode & 7) != 6))
+    return fail("qimg_set_fmha_mode: mode must be 4 (exact) or 6 (fast), optionally | 8 (25 % polynomial exponentials)");
   g_fmha_mode = mode;
   return 0;
 }
@@ -610,15 +626,26 @@ int qimg_set_fmha_trace(void* dev_buf_32_i64) {
   return 0;
 }
 
-int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
-                    int T, float softmax_scale, qimg_stream_t stream) {
+int qimg_fmha_overflow(int* out, int reset) {
+  int* flag = fmha_overflow_flag();
+  if (!flag) return fail("qimg_fmha_overflow: no CUDA device / allocation failed");
+  int v = 0;
+  QIMG_CUDA_CHECK(cudaMemcpy(&v, flag, sizeof(int), cudaMemcpyDeviceToHost));  // synchronises with prior launches
+  if (reset && v) QIMG_CUDA_CHECK(cudaMemset(flag, 0, sizeof(int)));
+  if (out) *out = v;
+  return 0;
+}
+
+int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
+                         int T, float softmax_scale, int mode, qimg_stream_t stream) {
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
-  const int mode = fmha_mode();
-  const int pipeline = mode & 7;  // 0: 128-row KV tiles; 1: 64-row dbuf S; 2/3: decoupled P (80/64 rows); 4: 2 threads per row
-  const uint32_t kv_rows = pipeline == 2 ? 80 : (pipeline == 3 ? 64 : (pipeline == 1 ? FMHA2_KV : 128));
+  if (mode < 0) mode = fmha_mode();
+  const int pipeline = mode & 7;
+  if (mode > 15 || (pipeline != 4 && pipeline != 6)) return fail("qimg_fmha_joint: mode must be 4 (exact) or 6 (fast) [| 8]");
+  tmap_cache_trim();
   const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
-  const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
-  const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, kv_rows);
+  const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, 128);
+  const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, 128);
   if (!tq || !tk || !tv) return 1;
   FmhaParams prm;
   prm.out_txt = (bf16*)out_txt;
@@ -626,14 +653,16 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
   prm.B = B; prm.H = H; prm.S = S; prm.T = T;
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
   prm.trace = g_fmha_trace;
+  prm.overflow = fmha_overflow_flag();
+  if (!prm.overflow) return fail("qimg_fmha_joint: could not allocate the overflow flag");
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
-  const bool pp = (mode & 32) != 0;  // strict alternation of the two softmax warpgroups' exp phases (pipeline 0)
-  switch ((mode >> 3) & 3) {         // share of the exponentials on the FMA-pipe polynomial: 0 / 25 / 37.5 / 50 %
-    case 0: return launch_fmha_inst<0x00u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
-    case 1: return launch_fmha_inst<0x11u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
-    case 2: return launch_fmha_inst<0x52u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
-    default: return launch_fmha_inst<0x55u>(pipeline, pp, tq, tk, tv, prm, (cudaStream_t)stream);
-  }
+  if (mode & 8) return launch_fmha_inst<0x11u>(pipeline, tq, tk, tv, prm, (cudaStream_t)stream);
+  return launch_fmha_inst<0x00u>(pipeline, tq, tk, tv, prm, (cudaStream_t)stream);
+}
+
+int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
+                    int T, float softmax_scale, qimg_stream_t stream) {
+  return qimg_fmha_joint_mode(q, k, v, out_txt, out_img, B, H, S, T, softmax_scale, -1, stream);
 }
 
 int qimg_umma_probe(const void* A, const void* B, float* D, int N, int K, int mode, qimg_stream_t stream) {
@@ -643,11 +672,8 @@ int qimg_umma_probe(const void* A, const void* B, float* D, int N, int K, int mo
   const CUtensorMap* ta = get_tmap_2d(A, 128, 128, 128);
   const CUtensorMap* tb = get_tmap_2d(B, 128, 128, 128);
   if (!ta || !tb) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024 + 256));
-    attr_set = true;
-  }
+  static bool attr_done[kMaxDevices] = {};
+  if (ensure_smem_attr(umma_probe_kernel, 65536 + 1024 + 256, attr_done)) return 1;
   umma_probe_kernel<<<1, 192, 65536 + 1024 + 256, (cudaStream_t)stream>>>(*ta, *tb, (const bf16*)A, D, mode);
   QIMG_LAUNCH_CHECK("umma_probe_kernel");
   return 0;

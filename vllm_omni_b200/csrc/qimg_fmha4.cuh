@@ -15,7 +15,7 @@ namespace qimg {
 constexpr int FMHA4_THREADS = 32 * (2 + 16);
 constexpr int FMHA4_SMEM_BYTES = FMHA_SMEM_BYTES + 4096;
 
-template <uint32_t POLY_MASK, bool PINGPONG>
+template <uint32_t POLY_MASK>
 __global__ void __launch_bounds__(FMHA4_THREADS, 1)
 fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
@@ -38,19 +38,9 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // 1-D grid, remapped so that the query-tile pairs whose SECOND tile lies completely beyond S run last and
-  // skip that tile (S = 4224 -> 16 full pairs + 1 half pair per head; 1536 full + 96 half CTAs fill 148 SMs in
-  // ~11.1 instead of 12 CTA-times)
-  const int full_pairs = prm.S / 256 + ((prm.S % 256) > 128 ? 1 : 0);
   const int n_bh = prm.B * prm.H;
-  int bh, pair_idx;
-  if ((int)blockIdx.x < full_pairs * n_bh) {
-    bh = blockIdx.x / full_pairs;
-    pair_idx = blockIdx.x - bh * full_pairs;
-  } else {
-    bh = blockIdx.x - full_pairs * n_bh;
-    pair_idx = full_pairs;
-  }
+  const FmhaWork work = fmha_decode_cta(blockIdx.x, prm.S, n_bh);  // head-major, half pairs lagged (qimg_fmha.cuh)
+  const int bh = work.bh, pair_idx = work.pair_idx;
   const int q_row0 = pair_idx * 256;
   const bool two = q_row0 + 128 < prm.S;  // is the second query tile (partly) in range?
   const int n_kv = (prm.S + 127) / 128;
@@ -202,7 +192,6 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // row sums stay private until the end.
     const int t = (warp - 2) >> 3;
     if (t == 0 || two) {
-    const bool pingpong = PINGPONG && two;
     const int hh = ((warp - 2) >> 2) & 1;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -218,7 +207,6 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float c = prm.scale_log2;
     float m_used = -INFINITY;
     float l = 0.f;  // partial row sum over my column half
-    if (pingpong && t == 1) named_bar_arrive(9, 512);
     const bool tr = kFmhaTrace && prm.trace != nullptr && blockIdx.x == 200 && hh == 0 && q == 0;
     long long w_s = 0, w_ld = 0, w_x = 0, w_pp = 0, w_ex = 0, w_tl = 0, tt = 0;
     const long long t_begin = kFmhaTrace ? clock64() : 0;
@@ -284,7 +272,6 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             m_used = m_new;
           }
         }
-        if (pingpong) named_bar_sync(9 + t, 512);
         if (tr) w_pp += clock64() - tt, tt = clock64();
         const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_used * c);
         uint64_t la = 0, lb = 0;
@@ -321,7 +308,6 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_st_32x32b_x8(tP + cidx * 8, pk);
         }
         if (tr) w_ex += clock64() - tt, tt = clock64();
-        if (pingpong && !(t == 1 && j == n_kv - 1)) named_bar_arrive(9 + (t ^ 1), 512);
         uint32_t a0, a1, b0, b1;
         unpack_f32x2(la, a0, a1);
         unpack_f32x2(lb, b0, b1);

@@ -8,9 +8,10 @@
 //      updated maximum over tiles < j) in ONE pass over the scores, 16 columns at a time; the tile's own maximum is
 //      reduced on the side (FMNMX3 under the MUFU-bound exponentials) and only decides, at the start of tile j+1 and
 //      after the two threads of a row have exchanged their halves' maxima, whether O and l are rebased (threshold 2^8).
-//      Tile 0 still reduces its maximum first (two passes, as v7).  Exponents are clamped at 2^96 so l and O stay finite
-//      when a tile's maximum jumps far above the reference (a jump of more than 66 nats inside one tile loses the
-//      relative weights of the clamped entries; pipelines 0-4 remain exact for such inputs).
+//      Tile 0 still reduces its maximum first (two passes, as v7).  No clamp in the loop: fp32 / bf16 hold exp2 arguments
+//      up to 2^100 without losing relative weights; a tile whose maximum exceeds the reference by more than that sets the
+//      device flag prm.overflow (qimg_fmha_overflow) and the caller recomputes with the exact pipeline v7 — round 1
+//      clamped at 2^96 inside the loop (2 FMNMX per pair, 5.8 % of the issue samples) and was silently inexact beyond it.
 //   2. Each thread releases its P in two halves (mbarrier per (tile, half)); P*V of the first 4 k-steps runs while the
 //      second half is exponentiated, so only half a P*V stays on the chain.
 #pragma once
@@ -22,7 +23,7 @@
 namespace qimg {
 
 
-template <uint32_t POLY_MASK, bool PINGPONG>
+template <uint32_t POLY_MASK>
 __global__ void __launch_bounds__(FMHA4_THREADS, 1)
 fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FmhaParams prm) {
@@ -45,19 +46,9 @@ fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // 1-D grid, remapped so that the query-tile pairs whose SECOND tile lies completely beyond S run last and
-  // skip that tile (S = 4224 -> 16 full pairs + 1 half pair per head; 1536 full + 96 half CTAs fill 148 SMs in
-  // ~11.1 instead of 12 CTA-times)
-  const int full_pairs = prm.S / 256 + ((prm.S % 256) > 128 ? 1 : 0);
   const int n_bh = prm.B * prm.H;
-  int bh, pair_idx;
-  if ((int)blockIdx.x < full_pairs * n_bh) {
-    bh = blockIdx.x / full_pairs;
-    pair_idx = blockIdx.x - bh * full_pairs;
-  } else {
-    bh = blockIdx.x - full_pairs * n_bh;
-    pair_idx = full_pairs;
-  }
+  const FmhaWork work = fmha_decode_cta(blockIdx.x, prm.S, n_bh);  // head-major, half pairs lagged (qimg_fmha.cuh)
+  const int bh = work.bh, pair_idx = work.pair_idx;
   const int q_row0 = pair_idx * 256;
   const bool two = q_row0 + 128 < prm.S;  // is the second query tile (partly) in range?
   const int n_kv = (prm.S + 127) / 128;
@@ -206,7 +197,6 @@ fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // row sums stay private until the end.
     const int t = (warp - 2) >> 3;
     if (t == 0 || two) {
-    const bool pingpong = PINGPONG && two;
     const int hh = ((warp - 2) >> 2) & 1;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -223,7 +213,6 @@ fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float m_ref = 0.f;  // reference (raw score units) the exponentials of the current tile are taken against
     float l = 0.f;      // partial row sum over my column half, relative to m_ref
     float my_tile_max = -INFINITY;  // maximum of my 64 columns of the previous tile (exchanged at the next tile's start)
-    if (pingpong && t == 1) named_bar_arrive(9, 512);
     const bool tr = kFmhaTrace && prm.trace != nullptr && blockIdx.x == 200 && hh == 0 && q == 0;
     long long w_s = 0, w_ld = 0, w_x = 0, w_pp = 0, w_ex = 0, w_tl = 0, tt = 0;
     const long long t_begin = kFmhaTrace ? clock64() : 0;
@@ -292,7 +281,6 @@ fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (need) m_ref = m_new;
           }
         }
-        if (pingpong) named_bar_sync(9 + t, 512);
         if (tr) w_pp += clock64() - tt, tt = clock64();
         const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_ref * c);
         uint64_t la = 0, lb = 0;
@@ -317,16 +305,12 @@ fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (kk & 1) mx1 = max3_f32(mx1, __uint_as_float(cur[2 * kk]), __uint_as_float(cur[2 * kk + 1]));
             else mx0 = max3_f32(mx0, __uint_as_float(cur[2 * kk]), __uint_as_float(cur[2 * kk + 1]));
             uint64_t x = fma_f32x2(pack_f32x2(cur[2 * kk], cur[2 * kk + 1]), c2, nmc2);
-            uint32_t xl, xh;
-            unpack_f32x2(x, xl, xh);
-#ifndef QIMG_FMHA_NOCLAMP
-            xl = __float_as_uint(fminf(__uint_as_float(xl), 96.0f));  // see header: keeps l and O finite
-            xh = __float_as_uint(fminf(__uint_as_float(xh), 96.0f));
-#endif
             uint64_t p;
             if ((POLY_MASK >> kk) & 1u) {
-              p = exp2_poly_f32x2(pack_f32x2(xl, xh));
+              p = exp2_poly_f32x2(x);
             } else {
+              uint32_t xl, xh;
+              unpack_f32x2(x, xl, xh);
               p = pack_f32x2(__float_as_uint(ex2_approx(__uint_as_float(xl))), __float_as_uint(ex2_approx(__uint_as_float(xh))));
             }
             if (kk & 1) lb = add_f32x2(lb, p); else la = add_f32x2(la, p);
@@ -347,12 +331,15 @@ fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         if (tr) w_ex += clock64() - tt, tt = clock64();
-        if (pingpong && !(t == 1 && j == n_kv - 1)) named_bar_arrive(9 + (t ^ 1), 512);
         uint32_t a0, a1, b0, b1;
         unpack_f32x2(la, a0, a1);
         unpack_f32x2(lb, b0, b1);
         l += (__uint_as_float(a0) + __uint_as_float(a1)) + (__uint_as_float(b0) + __uint_as_float(b1));
         my_tile_max = (j == 0) ? m_ref : fmaxf(mx0, mx1);
+        // guard: the exponentials above are exact (floating point) as long as no argument exceeded 2^FMHA_OVF_LOG2;
+        // a score that far above the reference (a jump of > 69 nats inside ONE KV tile) flags the launch instead of being
+        // clamped inside the loop — the caller re-runs with the exact pipeline (one predicated store, off the XU chain)
+        if (j > 0 && (my_tile_max - m_ref) * c > FMHA_OVF_LOG2) *prm.overflow = 1;
       };
       if (kv_valid < 64) softmax_tile(std::true_type{});
       else softmax_tile(std::false_type{});

@@ -45,6 +45,7 @@ int device_sm_count();  // cached; <= 0 on error
 // bf16 row-major matrix view [dim1 = rows][dim0 = cols] (optionally x dim2 batches), SWIZZLE_128B,
 // inner box = 64 elements (128 B).  Returns nullptr on failure (error recorded).
 const CUtensorMap* get_tmap_2d(const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows);
+void tmap_cache_trim();  // drop the descriptor cache when it has grown large; call only at the start of a launcher
 const CUtensorMap* get_tmap_3d(const void* ptr, uint64_t cols, uint64_t rows, uint64_t batches, uint32_t box_rows);
 
 }  // namespace qimg

@@ -36,7 +36,9 @@ class B200FMHAImpl(AttentionImpl):
                 attn_metadata.joint_value, value)
         B, S, H, hd = query.shape
         q, k, v = (t.to(torch.bfloat16).permute(0, 2, 1, 3).contiguous() for t in (query, key, value))
-        out_txt, out_img = qlib.fmha_joint(q, k, v, T=0, softmax_scale=self.softmax_scale)
+        # exact pipeline: a per-layer call has no end-of-denoise point at which the fast pipeline's overflow flag could
+        # be consulted (the whole-model engine uses the fast one and checks once per denoise)
+        out_txt, out_img = qlib.fmha_joint(q, k, v, T=0, softmax_scale=self.softmax_scale, mode=qlib.FMHA_EXACT)
         return out_img.view(B, S, H, hd)
 
 

@@ -116,6 +116,19 @@ def cfg_all_gather(local: torch.Tensor) -> list[torch.Tensor]:
     return bufs
 
 
+def any_rank_in_model_group(flag: bool, device=None) -> bool:
+    """Logical OR of `flag` over the ranks that compute ONE trajectory together (the TP group and the CFG group; DP
+    replicas are independent and are not consulted).  Used for decisions every such rank must take identically."""
+    if _STATE.tp_size == 1 and _STATE.cfg_size == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device if dist.get_backend() == "nccl" else "cpu")
+    if _STATE.tp_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_STATE.tp_group)
+    if _STATE.cfg_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_STATE.cfg_group)
+    return bool(int(t.item()))
+
+
 def get_tensor_model_parallel_world_size() -> int:
     return _STATE.tp_size
 

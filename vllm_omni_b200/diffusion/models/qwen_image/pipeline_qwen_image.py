@@ -12,6 +12,7 @@ synchronisation (timesteps live on the device, sigmas are host floats).
 """
 from __future__ import annotations
 
+import logging
 import math
 from collections.abc import Iterable
 from dataclasses import dataclass
@@ -26,6 +27,8 @@ from vllm_omni_b200.diffusion.data import DiffusionOutput, OmniDiffusionConfig
 from vllm_omni_b200.diffusion.distributed import parallel_state as _ps
 from vllm_omni_b200.diffusion.models.qwen_image.qwen_image_transformer import QwenImageTransformer2DModel
 from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+
+logger = logging.getLogger(__name__)
 
 
 def calculate_shift(image_seq_len, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
@@ -197,6 +200,32 @@ class QwenImagePipeline(nn.Module):
     def _denoise(self, prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents,
                  img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale,
                  image_latents=None):
+        """`_denoise_once` under the attention guard: the default (fast) attention pipeline takes its exponentials against
+        a running reference maximum and is exact unless a score jumps more than 2^100 above it inside one KV tile; such a
+        launch raises a device flag (include/qimg_b200.h qimg_fmha_overflow).  The flag is read ONCE per denoise (4 bytes,
+        the only synchronisation of the loop); if it is set — on any rank that shares this trajectory — the process
+        switches to the exact pipeline for good and the trajectory is recomputed from the same initial latents, so the
+        caller always receives exact-softmax results (reference semantics: attention/backends/sdpa.py:56-64)."""
+        args = (prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents, img_shapes,
+                txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale)
+        mode = qlib.get_fmha_mode()
+        if (mode & 7) != qlib.FMHA_FAST:
+            return self._denoise_once(*args, image_latents=image_latents)
+        qlib.fmha_overflow(reset=True)  # launches of other callers (layer-level plug-ins) must not leak into this decision
+        out = self._denoise_once(*args, image_latents=image_latents)
+        if not _ps.any_rank_in_model_group(qlib.fmha_overflow(reset=True), latents.device):
+            return out
+        logger.warning("attention scores left the fast pipeline's exact range (jump > 2^100 inside one KV tile); "
+                       "switching to the exact attention pipeline and recomputing the denoise")
+        qlib.set_fmha_mode(qlib.FMHA_EXACT | (mode & 8))
+        hook = getattr(self.transformer, "_teacache", None)
+        if hook is not None:
+            hook.reset_state()
+        return self._denoise_once(*args, image_latents=image_latents)
+
+    def _denoise_once(self, prompt_embeds, prompt_embeds_mask, negative_prompt_embeds, negative_prompt_embeds_mask, latents,
+                      img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale,
+                      image_latents=None):
         """The denoise loop behind `diffuse`.  `image_latents` [B,S2,64] (image-edit pipelines, reference pipeline_qwen_image_edit.py:600-602,617): the
         condition latents follow the noisy ones on the sequence axis in every forward, `img_shapes` lists both grids and
         only the first S1 rows of the prediction feed the CFG / scheduler step."""

@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = [
     "qimg_p2p_alloc", "qimg_p2p_free", "qimg_ipc_get_handle", "qimg_ipc_open_handle", "qimg_ipc_close_handle",
     "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error", "qimg_set_fmha_trace",
     "qimg_engine_forward_stages", "qimg_engine_ws_offset_mod", "qimg_rel_l1_sums", "qimg_bf16_sub", "qimg_bf16_add_inplace",
+    "qimg_fmha_joint_mode", "qimg_fmha_overflow",
 ]
 
 
@@ -105,6 +106,8 @@ def load():
     lib.qimg_cfg_euler_step.argtypes = [vp, vp, vp, ll, i, f, f, f, vp]
     lib.qimg_gemm.argtypes = [C.POINTER(GemmProblem), i, i, vp]
     lib.qimg_fmha_joint.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, f, vp]
+    lib.qimg_fmha_joint_mode.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, f, i, vp]
+    lib.qimg_fmha_overflow.argtypes = [C.POINTER(i), i]
     lib.qimg_engine_create.argtypes = [C.POINTER(Dims), C.POINTER(GlobalWeights), C.POINTER(BlockWeights), C.POINTER(vp)]
     lib.qimg_engine_destroy.argtypes = [vp]
     lib.qimg_engine_destroy.restype = None
@@ -187,6 +190,17 @@ def set_fmha_mode(mode: int):
 
 def get_fmha_mode() -> int:
     return int(load().qimg_get_fmha_mode())
+
+
+FMHA_EXACT, FMHA_FAST = 4, 6
+
+
+def fmha_overflow(reset: bool = True) -> bool:
+    """True if a fast-pipeline attention launch on the current device flagged an out-of-range score since the last reset
+    (synchronising 4-byte read, qimg_fmha_overflow)."""
+    v = C.c_int(0)
+    check(load().qimg_fmha_overflow(C.byref(v), int(reset)), "qimg_fmha_overflow")
+    return v.value != 0
 
 
 def prof_enable(on: bool):
@@ -273,8 +287,9 @@ def linear(x, W, bias, epilogue: int = EPI_BIAS, out=None):
     return out
 
 
-def fmha_joint(q, k, v, T: int, softmax_scale: float, out_txt=None, out_img=None):
-    """q,k,v [B,H,S,128] head-major -> (out_txt [B*T, H*128], out_img [B*(S-T), H*128])."""
+def fmha_joint(q, k, v, T: int, softmax_scale: float, out_txt=None, out_img=None, mode: int = -1):
+    """q,k,v [B,H,S,128] head-major -> (out_txt [B*T, H*128], out_img [B*(S-T), H*128]).
+    mode: FMHA_EXACT / FMHA_FAST (fast = guarded by `fmha_overflow`), -1 = process default."""
     for t in (q, k, v):
         _bf16c(t)
     B, H, S, hd = q.shape
@@ -283,8 +298,8 @@ def fmha_joint(q, k, v, T: int, softmax_scale: float, out_txt=None, out_img=None
         out_txt = torch.empty((B * T, H * 128), dtype=torch.bfloat16, device=q.device)
     if out_img is None:
         out_img = torch.empty((B * (S - T), H * 128), dtype=torch.bfloat16, device=q.device)
-    check(load().qimg_fmha_joint(_p(q), _p(k), _p(v), _p(out_txt), _p(out_img), B, H, S, T, softmax_scale, stream_ptr()),
-          "qimg_fmha_joint")
+    check(load().qimg_fmha_joint_mode(_p(q), _p(k), _p(v), _p(out_txt), _p(out_img), B, H, S, T, softmax_scale, int(mode),
+                                      stream_ptr()), "qimg_fmha_joint")
     return out_txt, out_img
 
 
