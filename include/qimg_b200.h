@@ -94,7 +94,7 @@ int qimg_cfg_euler_step(const void* pos, const void* neg, void* latents, long lo
                         float sigma, float sigma_next, qimg_stream_t stream);
 
 /* ---- tcgen05 GEMM family ------------------------------------------------------------ */
-enum { QIMG_EPI_BIAS = 0, QIMG_EPI_BIAS_GELU = 1, QIMG_EPI_BIAS_GATE_RES = 2, QIMG_EPI_QKV = 3 };
+enum { QIMG_EPI_BIAS = 0, QIMG_EPI_BIAS_GELU = 1, QIMG_EPI_BIAS_GATE_RES = 2, QIMG_EPI_QKV = 3, QIMG_EPI_PARTIAL_F32 = 4 };
 
 /* One linear problem out = A[M,K] @ W[N,K]^T (+ epilogue).  Up to two problems (image stream,
  * text stream) are grouped in one launch.  Replaces vLLM QKVParallelLinear/ReplicatedLinear and
@@ -123,6 +123,14 @@ typedef struct qimg_gemm_problem {
   const void* rope_sin;
   int S_joint, pos_off, H;
   float eps;
+  /* QIMG_EPI_PARTIAL_F32 (tensor-parallel row-parallel linear, K sharded over tp_size ranks; bias is NOT applied):
+   * the fp32 partial sums of row m are stored into the receive buffer of the rank that owns m — rows are split
+   * contiguously and balanced (the first M % tp_size owners get one more) — at
+   *   (float*)tp_recv[owner] + ((tp_rank * tp_recv_rows + tp_recv_row_off + (m - first_row(owner))) * N + n).
+   * tp_recv[] are device pointers valid in THIS process (peer mappings opened with qimg_ipc_open_handle, the own
+   * buffer at index tp_rank).  The reduction itself is qimg_tp_reduce_ln_push. */
+  void* tp_recv[8];
+  int tp_size, tp_rank, tp_recv_rows, tp_recv_row_off;
 } qimg_gemm_problem;
 
 int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_stream_t stream);

@@ -1,12 +1,15 @@
 """Tensor-parallel check (torchrun --nproc-per-node P, P GPUs): every rank holds the head / FFN shards of the same
-synthetic checkpoint and runs the TP engine (TP_COMM=nccl: NCCL all-reduce of the row-parallel partial sums; TP_COMM=p2p: the fused
-peer-memory reduce + epilogue + all-gather kernel); rank 0 compares the
-output with the single-GPU engine on the same inputs (tolerance 1e-2, the reference's SP-vs-baseline convention,
-tests/diffusion/attention/test_ulysses_sequence_parallel.py:332-343), and times both.
+synthetic checkpoint and runs the TP engine; rank 0 compares the output with the single-GPU engine on the same inputs
+(tolerance 1e-2, the reference's SP-vs-baseline convention, tests/diffusion/attention/test_ulysses_sequence_parallel.py:332-343)
+and times both (CUDA events, max over ranks).
+
+  TP_COMM=p2p   (default) GEMM epilogue pushes fp32 partial tiles to the row owners over NVLink peer memory; one fused
+                kernel reduces, applies bias + gate + residual + the next AdaLN and all-gathers the rows (qimg_tp_p2p.cu)
+  TP_COMM=nccl  bf16 partial sums + NCCL all-reduce + epilogue kernel (comparison baseline)
+  TP_CASES="comm,L,res,B;..." runs several cases in one launch (overrides TP_COMM / TP_LAYERS / TP_RES / TP_BATCH).
 """
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist
@@ -26,55 +29,70 @@ def build(L, dev, **kw):
             m = QwenImageTransformer2DModel(num_layers=L, **kw)
     finally:
         torch.set_default_dtype(torch.float32)
-    m.load_weights(synthetic.synthetic_weights(L, seed=0, norm_jitter=0.1))
+    m.load_weights(synthetic.synthetic_weights(L, seed=0, norm_jitter=0.1, device=dev, device_generate=True))
     return m
+
+
+def timed(fn, n, dev):
+    fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return out, float(t)
 
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    L = int(os.environ.get("TP_LAYERS", "4"))
-    res = int(os.environ.get("TP_RES", "512"))
-    B = int(os.environ.get("TP_BATCH", "1"))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     torch.cuda.set_device(dev)
     ps.init_distributed_environment(world_size=world, rank=rank, backend="nccl")
     ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=world, backend="nccl")
-    comm = os.environ.get("TP_COMM", "nccl")  # "nccl": all-reduce callback; "p2p": fused peer-memory reduction kernel
-    m = build(L, dev, tp_size=world, tp_rank=ps.get_tensor_model_parallel_rank(), tp_group=ps.get_tp_group(), tp_comm=comm)
-    lat, txt = synthetic.synthetic_inputs(B, res, res, 64)
-    t = torch.tensor([0.5], dtype=torch.bfloat16, device=dev)
-    grid = [[(1, res // 16, res // 16)]] * B
-    args = (lat.to(dev), txt.to(dev), None, t, grid, [64] * B)
-
-    def run(model, n=3):
-        out = model(*args, return_dict=False, uniform_timestep=True)[0]
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(n):
-            out = model(*args, return_dict=False, uniform_timestep=True)[0]
-        torch.cuda.synchronize()
-        return out, (time.perf_counter() - t0) / n * 1e3
-
-    out_tp, ms_tp = run(m)
+    cases = os.environ.get("TP_CASES") or "{},{},{},{}".format(os.environ.get("TP_COMM", "p2p"), os.environ.get("TP_LAYERS", "4"),
+                                                               os.environ.get("TP_RES", "512"), os.environ.get("TP_BATCH", "1"))
+    tol = float(os.environ.get("TP_TOL", "1e-2"))
     ok = True
-    if comm == "p2p" and not m.p2p_healthy():
-        print(f"rank {rank}: peer-memory barrier timed out", flush=True)
-        ok = False
-    if rank == 0:
-        m1 = build(L, dev, tp_size=1)
-        out_1 = m1(*args, return_dict=False, uniform_timestep=True)[0]
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            out_1 = m1(*args, return_dict=False, uniform_timestep=True)[0]
-        torch.cuda.synchronize()
-        ms_1 = (time.perf_counter() - t0) / 3 * 1e3
-        err = float((out_tp.float() - out_1.float()).norm() / out_1.float().norm())
-        print(f"tp_check tp={world} comm={comm} L={L} {res}px B={B}: rel_fro(TP, single GPU) = {err:.3e}; "
-              f"forward {ms_tp:.2f} ms (TP{world}) vs {ms_1:.2f} ms (1 GPU) -> speed-up {ms_1 / ms_tp:.2f}x")
-        ok = ok and err <= 1e-2 and not torch.isnan(out_tp).any()
-    dist.barrier()
+    for case in cases.split(";"):
+        comm, L, res, B = case.split(",")
+        L, res, B = int(L), int(res), int(B)
+        m = build(L, dev, tp_size=world, tp_rank=ps.get_tensor_model_parallel_rank(), tp_group=ps.get_tp_group(), tp_comm=comm)
+        lat, txt = synthetic.synthetic_inputs(B, res, res, 128)
+        t = torch.tensor([0.5], dtype=torch.bfloat16, device=dev)
+        grid = [[(1, res // 16, res // 16)]] * B
+        args = (lat.to(dev), txt.to(dev), None, t, grid, [128] * B)
+        out_tp, ms_tp = timed(lambda: m(*args, return_dict=False, uniform_timestep=True)[0], 3, dev)
+        if comm == "p2p" and not m.p2p_healthy():
+            print(f"rank {rank}: peer-memory barrier timed out", flush=True)
+            ok = False
+        if rank == 0:
+            m1 = build(L, dev, tp_size=1)
+            fn1 = lambda: m1(*args, return_dict=False, uniform_timestep=True)[0]  # noqa: E731
+            out_1 = fn1()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                out_1 = fn1()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_1 = e0.elapsed_time(e1) / 3
+            err = float((out_tp.float() - out_1.float()).norm() / out_1.float().norm())
+            rows, D, P = B * ((res // 16) ** 2 + 128), 3072, world
+            nvl = 2 * L * (P - 1) / P * rows * D * ((4 + 2) if comm == "p2p" else 2 * 2)  # bytes sent per rank per forward
+            print(f"tp_check tp={world} comm={comm} L={L} {res}px B={B}: rel_fro(TP, single GPU) = {err:.3e}; forward {ms_tp:.2f} ms "
+                  f"(TP{world}) vs {ms_1:.2f} ms (1 GPU) -> speed-up {ms_1 / ms_tp:.2f}x; NVLink bytes sent per rank per forward "
+                  f"{nvl / 1e6:.0f} MB (algorithmic)", flush=True)
+            ok = ok and err <= tol and not torch.isnan(out_tp).any()
+            del m1
+        dist.barrier()
+        del m
+        torch.cuda.empty_cache()
     ps.destroy_distributed_env()
     sys.exit(0 if ok else 1)
 

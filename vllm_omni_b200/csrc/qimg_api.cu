@@ -253,12 +253,23 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
     d.nq_w = (const bf16*)s.norm_q_w; d.nk_w = (const bf16*)s.norm_k_w;
     d.cos = (const bf16*)s.rope_cos; d.sin = (const bf16*)s.rope_sin;
     d.S_joint = s.S_joint; d.pos_off = s.pos_off; d.H = s.H; d.eps = s.eps;
-    if (!s.bias) return fail("qimg_gemm: bias is required");
+    if (epi == QIMG_EPI_PARTIAL_F32) {
+      if (s.tp_size < 1 || s.tp_size > 8 || s.tp_rank < 0 || s.tp_rank >= s.tp_size)
+        return fail("qimg_gemm: partial-sum epilogue needs 1 <= tp_size <= 8 and 0 <= tp_rank < tp_size");
+      if (s.tp_recv_rows <= 0 || s.tp_recv_row_off < 0) return fail("qimg_gemm: bad tp_recv_rows / tp_recv_row_off");
+      for (int r = 0; r < s.tp_size; ++r) {
+        if (!s.tp_recv[r]) return fail("qimg_gemm: null tp_recv pointer");
+        d.tp_recv[r] = (float*)s.tp_recv[r];
+      }
+      d.tp_size = s.tp_size; d.tp_rank = s.tp_rank; d.tp_recv_rows = s.tp_recv_rows; d.tp_recv_row_off = s.tp_recv_row_off;
+    } else if (!s.bias) {
+      return fail("qimg_gemm: bias is required");
+    }
     if (epi == QIMG_EPI_QKV) {
       if (s.N != 3 * s.H * 128) return fail("qimg_gemm: QKV epilogue needs N == 3*H*128");
       if (!s.q || !s.k || !s.v || !s.norm_q_w || !s.norm_k_w || !s.rope_cos || !s.rope_sin)
         return fail("qimg_gemm: QKV epilogue pointers missing");
-    } else if (!s.out || s.ldo % 8) {
+    } else if (epi != QIMG_EPI_PARTIAL_F32 && (!s.out || s.ldo % 8)) {
       return fail("qimg_gemm: out missing or ldo not a multiple of 8");
     }
     if (epi == QIMG_EPI_BIAS_GATE_RES && !s.gate) return fail("qimg_gemm: gate missing");
@@ -285,6 +296,7 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
       case QIMG_EPI_BIAS_GELU: return launch_gemm2_inst<EPI_BIAS_GELU>(tA, tB, prm, st);
       case QIMG_EPI_BIAS_GATE_RES: return launch_gemm2_inst<EPI_BIAS_GATE_RES>(tA, tB, prm, st);
       case QIMG_EPI_QKV: return launch_gemm2_inst<EPI_QKV>(tA, tB, prm, st);
+      case QIMG_EPI_PARTIAL_F32: return launch_gemm2_inst<EPI_PARTIAL_F32>(tA, tB, prm, st);
     }
     return fail("qimg_gemm: unknown epilogue");
   }
@@ -293,6 +305,7 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
     case QIMG_EPI_BIAS_GELU: return launch_gemm_inst<256, EPI_BIAS_GELU>(tA, tB, prm, st);
     case QIMG_EPI_BIAS_GATE_RES: return launch_gemm_inst<256, EPI_BIAS_GATE_RES>(tA, tB, prm, st);
     case QIMG_EPI_QKV: return launch_gemm_inst<256, EPI_QKV>(tA, tB, prm, st);
+    case QIMG_EPI_PARTIAL_F32: return launch_gemm_inst<256, EPI_PARTIAL_F32>(tA, tB, prm, st);
   }
   return fail("qimg_gemm: unknown epilogue");
 }

@@ -86,6 +86,32 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
   return v;
 }
 
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2) for the row kernels: ~5 instructions per element instead of ~15
+__device__ __forceinline__ uint64_t ew_pack2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void ew_unpack2(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ew_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t ew_add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ew_splat2(float v) { return ew_pack2(__float_as_uint(v), __float_as_uint(v)); }
+__device__ __forceinline__ float ew_hsum2(uint64_t v) {
+  uint32_t a, b;
+  ew_unpack2(v, a, b);
+  return __uint_as_float(a) + __uint_as_float(b);
+}
+
 // ---------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------

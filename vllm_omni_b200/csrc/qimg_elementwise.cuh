@@ -76,31 +76,6 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
 // unpacked once into packed fp32x2 registers and all three passes (mean, variance, normalise+modulate) run on
 // FADD2/FFMA2 + packed bf16 ops: ~5 instructions per element instead of ~15 (the generic kernel above is
 // issue-bound at 2.4 TB/s; profiles/r01_ln_modulate).
-__device__ __forceinline__ uint64_t ew_pack2(uint32_t lo, uint32_t hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
-}
-__device__ __forceinline__ void ew_unpack2(uint64_t v, uint32_t& lo, uint32_t& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ew_fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t ew_add2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t ew_splat2(float v) { return ew_pack2(__float_as_uint(v), __float_as_uint(v)); }
-__device__ __forceinline__ float ew_hsum2(uint64_t v) {
-  uint32_t a, b;
-  ew_unpack2(v, a, b);
-  return __uint_as_float(a) + __uint_as_float(b);
-}
-
 template <int NCH>
 __global__ void __launch_bounds__(128) ln_modulate_fast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
                                                                const bf16* __restrict__ scale, bf16* __restrict__ y,

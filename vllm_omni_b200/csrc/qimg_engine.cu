@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "qimg_host.cuh"
+#include "qimg_tp.h"
 
 using namespace qimg;
 
@@ -24,16 +25,11 @@ struct qimg_engine {
   void* allreduce_user = nullptr;
   // peer-memory TP (qimg_engine_set_tp_p2p): every rank's workspace and barrier flags, mapped into this process
   bool p2p = false;
+  bool p2p_ready = false;  // peer pointers registered (qimg_engine_set_tp_p2p with non-NULL arrays)
   int tp_rank = 0;
   void* peer_ws[8] = {};
   void* peer_flags[8] = {};
 };
-
-namespace qimg {
-int tp_p2p_barrier(void* const* flags, int P, int rank, cudaStream_t st);
-int tp_p2p_reduce(void* const* part, void* const* x, const void* bias, const void* gate, int rows, int D, int rows_per_batch,
-                  long long gate_stride, int P, int rank, cudaStream_t st);
-}  // namespace qimg
 
 namespace {
 
@@ -41,11 +37,12 @@ inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; 
 
 struct WsLayout {
   size_t x_img, x_txt, xm_img, xm_txt, q, k, v, at_img, at_txt, h_img, h_txt, txt_normed, tsin, t1, temb, mod_all, emb_out,
-      part, zero_bias, total;
+      part, zero_bias, recv, total;
+  int own_img, own_txt;  // peer-memory TP: largest owner slice of the image / text rows
 };
 
 // tp > 1: head-sharded q/k/v/attention-output and FF-sharded MLP hidden buffers are 1/tp of the full size
-WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max, int tp = 1) {
+WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max, int tp = 1, bool p2p = false) {
   const size_t D = (size_t)d.num_heads * d.head_dim, FF = 4 * D, S = (size_t)S_img + T;
   const size_t Mi = (size_t)B * S_img, Mt = (size_t)B * T;
   const size_t Hl = (size_t)d.num_heads / tp, Dl = D / tp, FFl = FF / tp;
@@ -73,8 +70,13 @@ WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max, int
   w.temb = take((size_t)n_t_max * D);
   w.mod_all = take((size_t)n_t_max * d.num_layers * 12 * D);
   w.emb_out = take((size_t)n_t_max * 2 * D);
-  w.part = take(tp > 1 ? (Mi + Mt) * D : 0);  // [img rows | txt rows] x D partial sums of the row-parallel linears
-  w.zero_bias = take(tp > 1 ? D : 0);
+  const bool nccl_tp = tp > 1 && !p2p;
+  w.part = take(nccl_tp ? (Mi + Mt) * D : 0);  // NCCL mode: [img rows | txt rows] x D bf16 partial sums of the row-parallel linears
+  w.zero_bias = take(nccl_tp ? D : 0);
+  // peer-memory mode: fp32 partial sums of MY rows from every source rank, [tp][own_img + own_txt][D]
+  w.own_img = tp > 1 ? (int)((Mi + tp - 1) / tp) : 0;
+  w.own_txt = tp > 1 ? (int)((Mt + tp - 1) / tp) : 0;
+  w.recv = take((tp > 1 && p2p) ? (size_t)tp * (w.own_img + w.own_txt) * D * 2 : 0);
   w.total = off;
   return w;
 }
@@ -112,14 +114,19 @@ int qimg_engine_set_tp(qimg_engine* e, int tp_size, qimg_allreduce_fn allreduce,
 }
 
 int qimg_engine_set_tp_p2p(qimg_engine* e, int tp_size, int tp_rank, void* const* peer_workspaces, void* const* peer_flags) {
-  if (!e || !peer_workspaces || !peer_flags) return fail("qimg_engine_set_tp_p2p: null argument");
+  if (!e) return fail("qimg_engine_set_tp_p2p: null engine");
   if (tp_size != 2 && tp_size != 4 && tp_size != 8) return fail("qimg_engine_set_tp_p2p: tp_size must be 2, 4 or 8");
   if (e->dims.num_heads % tp_size) return fail("qimg_engine_set_tp_p2p: tp_size must divide num_heads");
   if (tp_rank < 0 || tp_rank >= tp_size) return fail("qimg_engine_set_tp_p2p: bad rank");
-  for (int p = 0; p < tp_size; ++p) {
-    if (!peer_workspaces[p] || !peer_flags[p]) return fail("qimg_engine_set_tp_p2p: null peer pointer");
-    e->peer_ws[p] = peer_workspaces[p];
-    e->peer_flags[p] = peer_flags[p];
+  if ((peer_workspaces == nullptr) != (peer_flags == nullptr)) return fail("qimg_engine_set_tp_p2p: pass both pointer arrays or neither");
+  e->p2p_ready = false;
+  if (peer_workspaces) {
+    for (int p = 0; p < tp_size; ++p) {
+      if (!peer_workspaces[p] || !peer_flags[p]) return fail("qimg_engine_set_tp_p2p: null peer pointer");
+      e->peer_ws[p] = peer_workspaces[p];
+      e->peer_flags[p] = peer_flags[p];
+    }
+    e->p2p_ready = true;
   }
   e->tp_size = tp_size;
   e->tp_rank = tp_rank;
@@ -128,16 +135,16 @@ int qimg_engine_set_tp_p2p(qimg_engine* e, int tp_size, int tp_rank, void* const
 }
 
 int qimg_engine_p2p_error(qimg_engine* e, int* out) {
-  if (!e || !e->p2p || !out) return fail("qimg_engine_p2p_error: engine is not in peer-memory TP mode");
+  if (!e || !e->p2p || !e->p2p_ready || !out) return fail("qimg_engine_p2p_error: engine is not in peer-memory TP mode");
   QIMG_CUDA_CHECK(cudaMemcpy(out, (char*)e->peer_flags[e->tp_rank] + 64, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 
 size_t qimg_engine_workspace_bytes(const qimg_engine* e, int B, int S_img, int T) {
-  return ws_layout(e->dims, B, S_img, T, B, e->tp_size).total;
+  return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p).total;
 }
-size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size).x_img; }
-size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size).x_txt; }
+size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p).x_img; }
+size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p).x_txt; }
 
 #define QIMG_TRY(expr)      \
   do {                      \
@@ -152,7 +159,7 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
                                     out, workspace, workspace_bytes, st);
 }
 
-size_t qimg_engine_ws_offset_mod(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size).xm_img; }
+size_t qimg_engine_ws_offset_mod(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p).xm_img; }
 
 int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, const void* enc, const void* timestep, int n_t,
                                const void* img_cos, const void* img_sin, const void* txt_cos, const void* txt_sin, int B,
@@ -163,7 +170,7 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
   if (n_t != 1 && n_t != B) return fail("qimg_engine_forward: n_t must be 1 or B");
   const qimg_dims& d = e->dims;
   const int tp = e->tp_size;
-  const WsLayout w = ws_layout(d, B, S_img, T, B, tp);
+  const WsLayout w = ws_layout(d, B, S_img, T, B, tp, e->p2p);
   if (workspace_bytes < w.total) return fail("qimg_engine_forward: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail("qimg_engine_forward: workspace must be 1024-byte aligned");
   char* ws = static_cast<char*>(workspace);
@@ -171,33 +178,53 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
   const int Hl = H / tp, Dl = D / tp, FFl = FF / tp;  // local heads / widths under tensor parallelism
   void *part = ws + w.part, *zero_bias = ws + w.zero_bias;
   char* part_txt = (char*)part + (size_t)B * S_img * D * 2;
-  if (tp > 1) QIMG_CUDA_CHECK(cudaMemsetAsync(zero_bias, 0, (size_t)D * 2, (cudaStream_t)st));
-  if (e->p2p && workspace != e->peer_ws[e->tp_rank]) return fail("qimg_engine_forward: peer-memory TP needs the registered workspace");
-  // partial sums -> (sum over ranks) -> x += gate * (sum + bias), either through the caller's all-reduce (NCCL) followed by
-  // the epilogue kernel, or in one peer-memory kernel bracketed by two cross-GPU barriers (qimg_tp_p2p.cu)
+  if (tp > 1 && !e->p2p) QIMG_CUDA_CHECK(cudaMemsetAsync(zero_bias, 0, (size_t)D * 2, (cudaStream_t)st));
+  if (e->p2p) {
+    if (!e->p2p_ready) return fail("qimg_engine_forward: peer-memory TP declared but no peer workspaces registered");
+    if (workspace != e->peer_ws[e->tp_rank]) return fail("qimg_engine_forward: peer-memory TP needs the registered workspace");
+    if (stages != QIMG_STAGE_ALL) return fail("qimg_engine_forward_stages: staged forwards are not available in peer-memory TP mode");
+  }
+  // NCCL mode: bf16 partial sums -> caller's all-reduce -> x += gate * (sum + bias)   (comparison baseline)
   auto tp_reduce = [&](const void* b_img, const void* g_img, const void* b_txt, const void* g_txt, long long gstride) -> int {
-    void* x_img_l = ws + w.x_img;
-    void* x_txt_l = ws + w.x_txt;
-    if (!e->p2p) {
-      if (!e->allreduce) return fail("TP: no all-reduce registered");
-      if (e->allreduce(part, (long long)(B * S_img + B * T) * D, e->allreduce_user, st)) return fail("TP all-reduce callback failed");
-      QIMG_TRY(qimg_gate_residual_bias(x_img_l, part, b_img, g_img, B * S_img, D, S_img, gstride, st));
-      QIMG_TRY(qimg_gate_residual_bias(x_txt_l, part_txt, b_txt, g_txt, B * T, D, T, gstride, st));
-      return 0;
-    }
-    void *pi[8], *pt[8], *xi[8], *xt[8];
-    for (int p = 0; p < tp; ++p) {
-      char* base = (char*)e->peer_ws[p];
-      pi[p] = base + w.part;
-      pt[p] = base + w.part + (size_t)B * S_img * D * 2;
-      xi[p] = base + w.x_img;
-      xt[p] = base + w.x_txt;
-    }
-    QIMG_TRY(tp_p2p_barrier(e->peer_flags, tp, e->tp_rank, (cudaStream_t)st));
-    QIMG_TRY(tp_p2p_reduce(pi, xi, b_img, g_img, B * S_img, D, S_img, gstride, tp, e->tp_rank, (cudaStream_t)st));
-    QIMG_TRY(tp_p2p_reduce(pt, xt, b_txt, g_txt, B * T, D, T, gstride, tp, e->tp_rank, (cudaStream_t)st));
-    QIMG_TRY(tp_p2p_barrier(e->peer_flags, tp, e->tp_rank, (cudaStream_t)st));
+    if (!e->allreduce) return fail("TP: no all-reduce registered");
+    if (e->allreduce(part, (long long)(B * S_img + B * T) * D, e->allreduce_user, st)) return fail("TP all-reduce callback failed");
+    QIMG_TRY(qimg_gate_residual_bias(ws + w.x_img, part, b_img, g_img, B * S_img, D, S_img, gstride, st));
+    QIMG_TRY(qimg_gate_residual_bias(ws + w.x_txt, part_txt, b_txt, g_txt, B * T, D, T, gstride, st));
     return 0;
+  };
+  // peer-memory mode (csrc/qimg_tp_p2p.cu): the row-parallel GEMM pushed fp32 partial sums to the row owners; each rank
+  // now reduces ITS rows, applies bias + gate + residual, runs the NEXT AdaLayerNorm on the row in registers and stores
+  // the modulated row into every rank's xm buffer; two cross-GPU barriers order pushes / reads
+  auto tp_reduce_ln = [&](const void* b_img, const void* g_img, const void* b_txt, const void* g_txt, long long gstride,
+                          const void* sh_img, const void* sc_img, const void* sh_txt, const void* sc_txt,
+                          long long mstride) -> int {
+    TpReduceArgs a;
+    memset(&a, 0, sizeof a);
+    a.P = tp; a.rank = e->tp_rank; a.D = D; a.eps = d.eps;
+    a.recv_local = ws + w.recv;
+    a.recv_rows = w.own_img + w.own_txt;
+    a.row_off[0] = 0; a.row_off[1] = w.own_img;
+    a.x[0] = ws + w.x_img; a.x[1] = ws + w.x_txt;
+    a.rows[0] = B * S_img; a.rows[1] = B * T;
+    a.rows_per_batch[0] = S_img; a.rows_per_batch[1] = T;
+    a.bias[0] = b_img; a.bias[1] = b_txt;
+    a.gate[0] = g_img; a.gate[1] = g_txt;
+    a.shift[0] = sh_img; a.shift[1] = sh_txt;
+    a.scale[0] = sc_img; a.scale[1] = sc_txt;
+    a.gate_stride[0] = a.gate_stride[1] = gstride;
+    a.mod_stride[0] = a.mod_stride[1] = mstride;
+    for (int p = 0; p < tp; ++p) {
+      a.xm[0][p] = (char*)e->peer_ws[p] + w.xm_img;
+      a.xm[1][p] = (char*)e->peer_ws[p] + w.xm_txt;
+    }
+    QIMG_TRY(tp_p2p_barrier(e->peer_flags, tp, e->tp_rank, (cudaStream_t)st));   // every rank's pushes have landed
+    QIMG_TRY(tp_p2p_reduce_ln_push(a, (cudaStream_t)st));
+    QIMG_TRY(tp_p2p_barrier(e->peer_flags, tp, e->tp_rank, (cudaStream_t)st));   // every rank's xm rows have landed
+    return 0;
+  };
+  auto partial_problem = [&](qimg_gemm_problem& p, int row_off) {
+    p.tp_size = tp; p.tp_rank = e->tp_rank; p.tp_recv_rows = w.own_img + w.own_txt; p.tp_recv_row_off = row_off;
+    for (int r = 0; r < tp; ++r) p.tp_recv[r] = (char*)e->peer_ws[r] + w.recv;
   };
   const int Mi = B * S_img, Mt = B * T;
   void *x_img = ws + w.x_img, *x_txt = ws + w.x_txt, *xm_img = ws + w.xm_img, *xm_txt = ws + w.xm_txt;
@@ -251,8 +278,11 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
     const char* mt = mi + (size_t)6 * D * 2;
     auto seg = [&](const char* base, int i) { return (const void*)(base + (size_t)i * D * 2); };
 
-    QIMG_TRY(qimg_ln_modulate(x_img, seg(mi, 0), seg(mi, 1), xm_img, Mi, D, S_img, mod_stride, d.eps, st));
-    QIMG_TRY(qimg_ln_modulate(x_txt, seg(mt, 0), seg(mt, 1), xm_txt, Mt, D, T, mod_stride, d.eps, st));
+    const bool p2p = tp > 1 && e->p2p;
+    if (!p2p || l == 0) {  // peer-memory TP: blocks > 0 receive their LN1 output from the previous block's fused reduction
+      QIMG_TRY(qimg_ln_modulate(x_img, seg(mi, 0), seg(mi, 1), xm_img, Mi, D, S_img, mod_stride, d.eps, st));
+      QIMG_TRY(qimg_ln_modulate(x_txt, seg(mt, 0), seg(mt, 1), xm_txt, Mt, D, T, mod_stride, d.eps, st));
+    }
     {
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
@@ -275,6 +305,18 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
       p[1].A = at_txt; p[1].W = bw.to_add_out_w; p[1].bias = bw.to_add_out_b; p[1].M = Mt; p[1].rows_per_batch = T;
       p[1].out = x_txt; p[1].gate = seg(mt, 2);
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS_GATE_RES, st));
+    } else if (p2p) {
+      // row-parallel out-projection fused with the reduce-scatter: fp32 partial tiles go straight to the row owners
+      qimg_gemm_problem p[2];
+      memset(p, 0, sizeof p);
+      p[0].A = at_img; p[0].W = bw.to_out_w; p[0].M = Mi; p[0].N = D; p[0].K = Dl; p[0].rows_per_batch = S_img;
+      partial_problem(p[0], 0);
+      p[1] = p[0];
+      p[1].A = at_txt; p[1].W = bw.to_add_out_w; p[1].M = Mt; p[1].rows_per_batch = T;
+      partial_problem(p[1], w.own_img);
+      QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_PARTIAL_F32, st));
+      QIMG_TRY(tp_reduce_ln(bw.to_out_b, seg(mi, 2), bw.to_add_out_b, seg(mt, 2), mod_stride, seg(mi, 3), seg(mi, 4), seg(mt, 3),
+                            seg(mt, 4), mod_stride));
     } else {
       // row-parallel out-projection: partial sums over the local heads -> all-reduce -> bias + gate + residual
       qimg_gemm_problem p[2];
@@ -286,8 +328,10 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS, st));
       QIMG_TRY(tp_reduce(bw.to_out_b, seg(mi, 2), bw.to_add_out_b, seg(mt, 2), mod_stride));
     }
-    QIMG_TRY(qimg_ln_modulate(x_img, seg(mi, 3), seg(mi, 4), xm_img, Mi, D, S_img, mod_stride, d.eps, st));
-    QIMG_TRY(qimg_ln_modulate(x_txt, seg(mt, 3), seg(mt, 4), xm_txt, Mt, D, T, mod_stride, d.eps, st));
+    if (!p2p) {
+      QIMG_TRY(qimg_ln_modulate(x_img, seg(mi, 3), seg(mi, 4), xm_img, Mi, D, S_img, mod_stride, d.eps, st));
+      QIMG_TRY(qimg_ln_modulate(x_txt, seg(mt, 3), seg(mt, 4), xm_txt, Mt, D, T, mod_stride, d.eps, st));
+    }
     {
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
@@ -306,6 +350,25 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
       p[1].A = h_txt; p[1].W = bw.txt_mlp_w2; p[1].bias = bw.txt_mlp_b2; p[1].M = Mt; p[1].rows_per_batch = T;
       p[1].out = x_txt; p[1].gate = seg(mt, 5);
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_BIAS_GATE_RES, st));
+    } else if (p2p) {
+      qimg_gemm_problem p[2];
+      memset(p, 0, sizeof p);
+      p[0].A = h_img; p[0].W = bw.img_mlp_w2; p[0].M = Mi; p[0].N = D; p[0].K = FFl; p[0].rows_per_batch = S_img;
+      partial_problem(p[0], 0);
+      p[1] = p[0];
+      p[1].A = h_txt; p[1].W = bw.txt_mlp_w2; p[1].M = Mt; p[1].rows_per_batch = T;
+      partial_problem(p[1], w.own_img);
+      QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_PARTIAL_F32, st));
+      if (l + 1 < L) {  // the LayerNorm that follows is block l+1's first one
+        const char* ni = mod_all + ((size_t)(l + 1) * 12 * D) * 2;
+        const char* nt = ni + (size_t)6 * D * 2;
+        QIMG_TRY(tp_reduce_ln(bw.img_mlp_b2, seg(mi, 5), bw.txt_mlp_b2, seg(mt, 5), mod_stride, seg(ni, 0), seg(ni, 1), seg(nt, 0),
+                              seg(nt, 1), mod_stride));
+      } else {  // ... or norm_out (AdaLayerNormContinuous: scale first, then shift); the text stream ends here
+        const void* sc = emb_out;
+        const void* sh = (const char*)emb_out + (size_t)D * 2;
+        QIMG_TRY(tp_reduce_ln(bw.img_mlp_b2, seg(mi, 5), bw.txt_mlp_b2, seg(mt, 5), mod_stride, sh, sc, sh, sc, emb_stride));
+      }
     } else {
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
@@ -320,7 +383,8 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
 
   // ---- epilogue: AdaLayerNormContinuous (scale first, then shift) + proj_out -------------------
   if (stages & QIMG_STAGE_POST) {
-  QIMG_TRY(qimg_ln_modulate(x_img, (const char*)emb_out + (size_t)D * 2, emb_out, xm_img, Mi, D, S_img, emb_stride, d.eps, st));
+  if (!(tp > 1 && e->p2p))  // peer-memory TP: the last block's fused reduction already produced norm_out's rows in xm_img
+    QIMG_TRY(qimg_ln_modulate(x_img, (const char*)emb_out + (size_t)D * 2, emb_out, xm_img, Mi, D, S_img, emb_stride, d.eps, st));
   {
     qimg_gemm_problem p;
     memset(&p, 0, sizeof p);

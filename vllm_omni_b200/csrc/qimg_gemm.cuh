@@ -8,6 +8,7 @@
 //   img_mlp/txt_mlp net.0.proj + gelu(tanh)       :491,501,591,596                    -> EPI_BIAS_GELU
 //   net.2 + gate*x + residual                     :592,597                            -> EPI_BIAS_GATE_RES
 //   img_in / txt_in / proj_out                    :743,759,798                        -> EPI_BIAS
+//   tensor-parallel to_out / net.2 (K sharded): fp32 partial sums pushed to the row owner's peer buffer -> EPI_PARTIAL_F32
 // The image and text streams (different weights, M_txt << M_img) are GROUPED in one
 // launch so the small text GEMM fills the tail instead of starving 140 SMs.
 //
@@ -26,7 +27,7 @@
 
 namespace qimg {
 
-enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_GATE_RES = 2, EPI_QKV = 3 };
+enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_GATE_RES = 2, EPI_QKV = 3, EPI_PARTIAL_F32 = 4 };
 
 struct GemmProblem {
   int M, N, K;
@@ -46,6 +47,11 @@ struct GemmProblem {
   const bf16* sin;
   int S_joint, pos_off, H;
   float eps;
+  // EPI_PARTIAL_F32 (tensor-parallel row-parallel linear): fp32 partial sums are PUSHED to the receive buffer of the rank
+  // that owns the row (peer memory over NVLink).  Rows are split contiguously and balanced over tp_size owners; owner o
+  // keeps the rows of source rank s at tp_recv[o] + ((s * tp_recv_rows + tp_recv_row_off + local_row) * N) floats.
+  float* tp_recv[8];
+  int tp_size, tp_rank, tp_recv_rows, tp_recv_row_off;
   // tile bookkeeping (filled by the host launcher)
   int m_tiles, n_tiles, tile_begin;
 };
@@ -89,9 +95,73 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& prm, int tile
 
 // One accumulator tile (128 rows x BN columns, rows [m_blk*128, +128)) -> global memory.  Executed by the 8
 // epilogue warps of a CTA; warp (q = lane quarter, chunk range) owns 32 rows x (chunk_hi-chunk_lo)*64 columns.
+// EPI_PARTIAL_F32: the compute + collective fusion of the tensor-parallel row-parallel linears.  The accumulator tile
+// leaves TMEM as fp32 and goes straight over NVLink into the receive buffer of the rank that owns each row (the
+// reduce-scatter half of the all-reduce), tile by tile, under the main loop of the next tile (two TMEM accumulator
+// stages) — no bf16 rounding of partial sums, no local round trip through HBM, no separate reduction-input pass.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_partial(const GemmProblem& P, int m_blk, int n_blk, uint32_t t_row, uint32_t stg,
+                                                      int lane, int q, int chunk_lo, int chunk_hi) {
+  // destination row pointers of this lane's 8 store rows (gm0 + 4 it), computed once per tile: owner o of a row and its
+  // index within o's slice advance incrementally (one division per tile, none in the store loop)
+  const int gm0 = m_blk * GEMM_BM + q * 32 + (lane >> 3);
+  const int base = P.M / P.tp_size, extra = P.M % P.tp_size;
+  float* dst_row[8];
+  {
+    int o, start;
+    const int cut = extra * (base + 1);
+    if (gm0 < cut) {
+      o = gm0 / (base + 1);
+      start = o * (base + 1);
+    } else {
+      o = base > 0 ? extra + (gm0 - cut) / base : P.tp_size - 1;
+      start = cut + (o - extra) * base;
+    }
+    int size = base + (o < extra ? 1 : 0);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int gm = gm0 + it * 4;
+      while (gm >= start + size && o + 1 < P.tp_size) {
+        start += size;
+        ++o;
+        size = base + (o < extra ? 1 : 0);
+      }
+      dst_row[it] = P.tp_recv[o] + ((size_t)P.tp_rank * P.tp_recv_rows + P.tp_recv_row_off + (gm - start)) * (size_t)P.N;
+    }
+  }
+#pragma unroll 1
+  for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int n0 = n_blk * BN + chunk * 64 + half * 32;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_row + chunk * 64 + half * 32, r);
+      tmem_ld_wait();
+      // this thread's row: 32 fp32 = 128 B -> staging (16 B chunk index XOR row&7), then 128 B-per-row coalesced stores
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(r[j * 4], r[j * 4 + 1], r[j * 4 + 2], r[j * 4 + 3]));
+      __syncwarp();
+      const int c16 = lane & 7;
+      const int gn = n0 + c16 * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        const uint4 v = lds_v4(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+        if (gm0 + it * 4 < P.M && gn < P.N) stg_v4(dst_row[it] + gn, v);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmProblem& P, int m_blk, int n_blk, uint32_t t_row, uint32_t stg,
                                               int lane, int q, int chunk_lo, int chunk_hi) {
+  if (EPI == EPI_PARTIAL_F32) {
+    epilogue_tile_partial<BN>(P, m_blk, n_blk, t_row, stg, lane, q, chunk_lo, chunk_hi);
+    return;
+  }
   const int m_own = m_blk * GEMM_BM + q * 32 + lane;  // this thread's accumulator row
 
   // batch / in-batch index of the first row of this warp's 32-row slab: one division per tile, rows

@@ -32,6 +32,7 @@ class TeaCacheHook:
         self._sums = None       # fp32 [2] device scratch of the reduction kernel
         self._ori = None        # image residual stream before the blocks
         self.decisions: list[tuple[str, bool, float]] = []  # (branch, computed?, rel distance) of the current run
+        self._tp_group = None   # set in run() when the transformer is tensor parallel
 
     # ---- state -------------------------------------------------------------------------------------------------
     def reset_state(self) -> None:
@@ -61,6 +62,12 @@ class TeaCacheHook:
         if self._sums is None or self._sums.device != mod.device:
             self._sums = torch.zeros(2, dtype=torch.float32, device=mod.device)
         qlib.rel_l1_sums(mod, state.previous_modulated_input, self._sums)
+        if self._tp_group is not None:
+            # tensor parallel: the sums come from fp32 atomics in a non-deterministic order, so two ranks could land on
+            # different sides of the threshold and one would skip the blocks (and their collectives) while the other runs
+            # them.  TP rank 0 decides for the group.
+            import torch.distributed as dist
+            dist.broadcast(self._sums, src=dist.get_global_rank(self._tp_group, 0), group=self._tp_group)
         s = self._sums.cpu()  # the reference's host sync (hook.py:204-205)
         n = float(mod.numel())
         num = (s[0] / n).to(torch.bfloat16)   # .abs().mean() of a bf16 tensor: fp32 accumulation, bf16 result
@@ -76,6 +83,7 @@ class TeaCacheHook:
     def run(self, module, run_stage, mod: torch.Tensor, x_img: torch.Tensor, qlib):
         """`run_stage(mask)` launches engine stages on the current inputs; `mod` / `x_img` are views of the workspace
         (block 0's modulated image stream and the image residual stream)."""
+        self._tp_group = getattr(module, "tp_group", None) if getattr(module, "tp_size", 1) > 1 else None
         run_stage(qlib.STAGE_PRE)
         branch = "negative" if (module.do_true_cfg and self._forward_cnt % 2 == 1) else "positive"
         state = self._state(branch)

@@ -257,9 +257,11 @@ class QwenImageTransformer2DModel(nn.Module):
             from vllm_omni_b200.diffusion.distributed import parallel_state as _ps
             tp_rank, tp_group = _ps.get_tensor_model_parallel_rank(), _ps.get_tp_group()
         self.tp_size, self.tp_rank, self.tp_group = int(tp_size), int(tp_rank or 0), tp_group
-        # how the row-parallel partial sums are reduced: "nccl" = all-reduce callback + epilogue kernel; "p2p" = one
-        # peer-memory kernel per rank (reduce-scatter + bias/gate/residual + all-gather over NVLink, csrc/qimg_tp_p2p.cu)
-        self.tp_comm = (tp_comm or os.environ.get("QIMG_TP_COMM", "nccl")).lower()
+        # how the row-parallel partial sums are reduced: "p2p" (default) = the GEMM epilogue pushes fp32 partial tiles to
+        # the row owners over NVLink peer memory, one fused kernel reduces + applies bias/gate/residual + the next AdaLN and
+        # all-gathers the modulated rows (csrc/qimg_tp_p2p.cu); "nccl" = bf16 partial sums + all-reduce callback + epilogue
+        # kernel (comparison baseline)
+        self.tp_comm = (tp_comm or os.environ.get("QIMG_TP_COMM", "p2p")).lower()
         if self.tp_comm not in ("nccl", "p2p"):
             raise ValueError(f"tp_comm must be 'nccl' or 'p2p', got {self.tp_comm!r}")
         if num_attention_heads % self.tp_size:
@@ -407,6 +409,10 @@ class QwenImageTransformer2DModel(nn.Module):
         qlib.check(qlib.load().qimg_engine_create(C.byref(dims), C.byref(g), blocks, C.byref(handle)), "qimg_engine_create")
         self._engine = handle
         self._engine_keepalive = (dims, g, blocks)
+        if self.tp_size > 1 and self.tp_comm == "p2p":
+            # declare the mode (workspace layout depends on it); the peer pointers follow in _p2p_workspace
+            qlib.check(qlib.load().qimg_engine_set_tp_p2p(self._engine, self.tp_size, self.tp_rank, None, None),
+                       "qimg_engine_set_tp_p2p")
         if self.tp_size > 1 and self.tp_comm == "nccl":
             import torch.distributed as dist
 

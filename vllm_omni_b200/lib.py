@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libqimg_b200.so")
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_QKV = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_QKV, EPI_PARTIAL_F32 = 0, 1, 2, 3, 4
 
 # every symbol declared in include/qimg_b200.h (tests check the .so exports all of them)
 EXPORTED_SYMBOLS = [
@@ -39,6 +39,8 @@ class GemmProblem(C.Structure):
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
         ("norm_q_w", C.c_void_p), ("norm_k_w", C.c_void_p), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("S_joint", C.c_int), ("pos_off", C.c_int), ("H", C.c_int), ("eps", C.c_float),
+        ("tp_recv", C.c_void_p * 8), ("tp_size", C.c_int), ("tp_rank", C.c_int), ("tp_recv_rows", C.c_int),
+        ("tp_recv_row_off", C.c_int),
     ]
 
 
