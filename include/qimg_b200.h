@@ -37,6 +37,10 @@ void qimg_reset_launch_count(void);
 void qimg_prof_enable(int on);
 int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* flops_total);
 
+/* NVTX ranges around the engine's launch families ("qimg.forward" > "qimg.pre" / "qimg.block" > "gemm.qkv+qknorm+rope",
+ * "fmha.joint", ... / "qimg.post"); default off, env QIMG_NVTX=1 turns them on.  Header-only NVTX3: free without a profiler. */
+void qimg_set_nvtx(int on);
+
 /* GEMM tile mode: 0 = one CTA per 128x256 tile (tcgen05 cta_group::1), 1 = CTA pair per 256x256 tile
  * (cta_group::2, cluster of 2).  Default 1; env QIMG_GEMM_MODE overrides. */
 int qimg_set_gemm_mode(int mode);
@@ -92,6 +96,15 @@ int qimg_timestep_sinusoid(const void* t, void* out, int B, qimg_stream_t stream
  * (torch promotes the 0-dim fp32 dt to the bf16 operand dtype). */
 int qimg_cfg_euler_step(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale,
                         float sigma, float sigma_next, qimg_stream_t stream);
+/* Same step with (sigma_i, sigma_{i+1}) read from DEVICE memory (fp32 [2]): the launch has no per-timestep host argument,
+ * so one captured CUDA graph of a denoise step can be replayed for all timesteps (pipeline `enable_cuda_graph`). */
+int qimg_cfg_euler_step_dev(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale,
+                            const float* sigma_pair, qimg_stream_t stream);
+/* How `dt * model_output` treats dt: 0 (default) = rounded to bf16 first — torch's result for a 0-dim fp32 DEVICE tensor
+ * times a bf16 tensor, which is what diffusers' FlowMatchEulerDiscreteScheduler.step computes with its sigmas on the
+ * device, and what torch computes on CPU; 1 = kept at fp32 (torch's result when dt is a 0-dim CPU tensor and the
+ * model output is on CUDA). */
+int qimg_set_euler_dt_fp32(int on);
 
 /* ---- tcgen05 GEMM family ------------------------------------------------------------ */
 enum { QIMG_EPI_BIAS = 0, QIMG_EPI_BIAS_GELU = 1, QIMG_EPI_BIAS_GATE_RES = 2, QIMG_EPI_QKV = 3, QIMG_EPI_PARTIAL_F32 = 4 };
@@ -255,6 +268,20 @@ size_t qimg_engine_ws_offset_mod(const qimg_engine* e, int B, int S_img, int T);
 int qimg_rel_l1_sums(const void* a, const void* b, long long n, float* sums2, qimg_stream_t stream);
 int qimg_bf16_sub(void* out, const void* a, const void* b, long long n, qimg_stream_t stream);
 int qimg_bf16_add_inplace(void* x, const void* r, long long n, qimg_stream_t stream);
+
+/* Step-cache decision ON THE DEVICE (no host synchronisation; the reference reads the distance back with .cpu().item(),
+ * cache/teacache/hook.py:204-205):
+ *   qimg_tea_decide     one thread: rel = bf16 arithmetic of hook.py:198-203 on sums2 / n, accum += |poly(rel)| (coef5: highest
+ *                       power first, fp64 Horner = numpy.poly1d), *flag = 1 (reuse) while accum < thresh, else 0 and accum = 0.
+ *                       force: 0 = decide from the data; 1 = first forward of a branch (accum = 0, compute); 2 = no previous
+ *                       input yet (compute, accum kept).  hist (optional, fp32 [2 * steps]) records (flag, rel) at hist_idx.
+ *   qimg_tea_residual   flag = 1: x += resid   /   flag = 0: resid = x - ori        (hook.py:131-133 / 152-154)
+ *   qimg_engine_set_blocks_predicate   every kernel of the engine's BLOCKS stage starts with `if (*skip_flag) return;`, so a
+ *                       reused step costs ~540 empty launches instead of 60 blocks; NULL removes the predicate. */
+int qimg_tea_decide(const float* sums2, long long n, const double* coef5, double thresh, double* accum, int* flag, float* hist,
+                    int hist_idx, int force, qimg_stream_t stream);
+int qimg_tea_residual(void* x, const void* ori, void* resid, long long n, const int* flag, qimg_stream_t stream);
+int qimg_engine_set_blocks_predicate(qimg_engine* e, const int* skip_flag);
 
 /* Debug/test access: copies of the image / text residual streams after the last forward live in the
  * workspace at these byte offsets ([B*S_img, D] and [B*T, D] bf16). */

@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           *_opt_flags(), "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+           *_opt_flags(), "-shared", "-Xcompiler", "-fPIC", "-ldl", "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -16,6 +16,9 @@
 namespace qimg {
 
 thread_local std::string g_last_error;
+static thread_local const int* g_launch_predicate = nullptr;
+void set_launch_predicate(const int* flag) { g_launch_predicate = flag; }
+const int* launch_predicate() { return g_launch_predicate; }
 std::atomic<long long> g_launch_count{0};
 
 constexpr int kMaxDevices = 64;
@@ -286,6 +289,7 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
     tB[1] = tB[0];
   }
   prm.total_tiles = tiles;
+  prm.skip = launch_predicate();
   double flops = 0;
   for (int i = 0; i < nprob; ++i) flops += 2.0 * pr[i].M * (double)pr[i].N * pr[i].K;
   ProfScope prof(0, flops, st);
@@ -492,11 +496,13 @@ int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* 
   cudaStream_t st = (cudaStream_t)stream;
   const bf16 *xp = (const bf16*)x, *shp = (const bf16*)shift, *scp = (const bf16*)scale;
   if (D == 3072) {  // Qwen-Image width: compile-time row length
-    ln_modulate_fast_kernel<12><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps);
+    ln_modulate_fast_kernel<12><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps, launch_predicate());
+  } else if (D == 1024) {
+    ln_modulate_fast_kernel<4><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps, launch_predicate());
   } else if (D == 256) {
-    ln_modulate_fast_kernel<1><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps);
+    ln_modulate_fast_kernel<1><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps, launch_predicate());
   } else {
-    ln_modulate_kernel<<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, D, rows_per_batch, mod_stride, eps);
+    ln_modulate_kernel<<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, D, rows_per_batch, mod_stride, eps, launch_predicate());
   }
   QIMG_LAUNCH_CHECK("ln_modulate_kernel");
   return 0;
@@ -561,6 +567,26 @@ int qimg_bf16_sub(void* out, const void* a, const void* b, long long n, qimg_str
   return 0;
 }
 
+int qimg_tea_decide(const float* sums2, long long n, const double* coef5, double thresh, double* accum, int* flag, float* hist,
+                    int hist_idx, int force, qimg_stream_t stream) {
+  if (!accum || !flag || !coef5) return fail("qimg_tea_decide: null argument");
+  if (force == 0 && (!sums2 || n <= 0)) return fail("qimg_tea_decide: sums / n missing");
+  TeaCoef c;
+  for (int i = 0; i < 5; ++i) c.c[i] = coef5[i];
+  tea_decide_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums2, (double)n, c, thresh, accum, flag, hist, hist_idx, force);
+  QIMG_LAUNCH_CHECK("tea_decide_kernel");
+  return 0;
+}
+
+int qimg_tea_residual(void* x, const void* ori, void* resid, long long n, const int* flag, qimg_stream_t stream) {
+  if (n <= 0) return 0;
+  if (n % 8) return fail("qimg_tea_residual: n must be a multiple of 8");
+  if (!flag) return fail("qimg_tea_residual: null flag");
+  tea_residual_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((bf16*)x, (const bf16*)ori, (bf16*)resid, n / 8, flag);
+  QIMG_LAUNCH_CHECK("tea_residual_kernel");
+  return 0;
+}
+
 int qimg_bf16_add_inplace(void* x, const void* r, long long n, qimg_stream_t stream) {
   if (n <= 0) return 0;
   if (n % 8) return fail("qimg_bf16_add_inplace: n must be a multiple of 8");
@@ -597,16 +623,34 @@ int qimg_timestep_sinusoid(const void* t, void* out, int B, qimg_stream_t stream
   return 0;
 }
 
-int qimg_cfg_euler_step(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale,
-                        float sigma, float sigma_next, qimg_stream_t stream) {
+static int g_euler_dt_fp32 = 0;
+int qimg_set_euler_dt_fp32(int on) {
+  g_euler_dt_fp32 = on != 0;
+  return 0;
+}
+
+static int launch_cfg_euler(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale, float dt,
+                            const float* sigma_pair, qimg_stream_t stream) {
   if (rows <= 0) return 0;
   if (C != 64) return fail("qimg_cfg_euler_step: C must be 64 (packed latent channels)");
   const long long vecs = rows * 8;
-  const float dt = sigma_next - sigma;  // fp32 subtraction, as the scheduler's 0-dim fp32 tensors
   cfg_euler_step_kernel<<<(int)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)pos, (const bf16*)neg,
-                                                                                     (bf16*)latents, rows, cfg_scale, dt);
+                                                                                     (bf16*)latents, rows, cfg_scale, dt,
+                                                                                     sigma_pair, g_euler_dt_fp32);
   QIMG_LAUNCH_CHECK("cfg_euler_step_kernel");
   return 0;
+}
+
+int qimg_cfg_euler_step(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale,
+                        float sigma, float sigma_next, qimg_stream_t stream) {
+  // fp32 subtraction, as the scheduler's 0-dim fp32 tensors
+  return launch_cfg_euler(pos, neg, latents, rows, C, cfg_scale, sigma_next - sigma, nullptr, stream);
+}
+
+int qimg_cfg_euler_step_dev(const void* pos, const void* neg, void* latents, long long rows, int C, float cfg_scale,
+                            const float* sigma_pair, qimg_stream_t stream) {
+  if (!sigma_pair) return fail("qimg_cfg_euler_step_dev: null sigma pair");
+  return launch_cfg_euler(pos, neg, latents, rows, C, cfg_scale, 0.f, sigma_pair, stream);
 }
 
 int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_stream_t stream) {
@@ -666,6 +710,7 @@ int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_
   prm.B = B; prm.H = H; prm.S = S; prm.T = T;
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
   prm.trace = g_fmha_trace;
+  prm.skip = launch_predicate();
   prm.overflow = fmha_overflow_flag();
   if (!prm.overflow) return fail("qimg_fmha_joint: could not allocate the overflow flag");
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);

@@ -16,7 +16,9 @@ constexpr int EW_MAX_CHUNKS = 16;  // 16 x 256 = 4096 elements per row max (D=30
 // shift/scale are [*, D] slices of the modulation buffer, row -> batch = row / rows_per_batch.
 __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
                                                           const bf16* __restrict__ scale, bf16* __restrict__ y, int rows,
-                                                          int D, int rows_per_batch, long long mod_stride, float eps) {
+                                                          int D, int rows_per_batch, long long mod_stride, float eps,
+                                                          const int* __restrict__ skip) {
+  if (skip && *skip) return;  // step cache: this forward reuses the cached residual (qimg_tea_decide)
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -80,7 +82,8 @@ template <int NCH>
 __global__ void __launch_bounds__(128) ln_modulate_fast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
                                                                const bf16* __restrict__ scale, bf16* __restrict__ y,
                                                                int rows, int rows_per_batch, long long mod_stride,
-                                                               float eps) {
+                                                               float eps, const int* __restrict__ skip) {
+  if (skip && *skip) return;
   constexpr int D = NCH * 256;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -285,6 +288,64 @@ __global__ void __launch_bounds__(256) bf16_add_inplace_kernel(bf16* __restrict_
   }
 }
 
+// ---- TeaCache decision on the DEVICE (reference cache/teacache/hook.py:170-217 takes it on the host after `.cpu().item()`) ----
+// One thread reproduces the host arithmetic bit for bit: the two means in fp32 rounded to bf16, the bf16 `+ 1e-8` and
+// division, the degree-4 rescale polynomial (numpy.poly1d = Horner) and the accumulation in fp64.  flag = 1: reuse the
+// cached residual (the engine's BLOCKS stage is launched predicated on it and exits at once), 0: compute.
+struct TeaCoef {
+  double c[5];  // highest power first
+};
+__global__ void tea_decide_kernel(const float* __restrict__ sums, double n, TeaCoef coef, double thresh, double* __restrict__ accum,
+                                  int* __restrict__ flag, float* __restrict__ hist, int hist_idx, int force) {
+  if (threadIdx.x || blockIdx.x) return;
+  float rel = __int_as_float(0x7fc00000);  // NaN: no distance on a forced step (as the host hook records)
+  int reuse = 0;
+  if (force == 1) {  // first forward of a branch: reset the accumulator and compute (hook.py:183-186)
+    *accum = 0.0;
+  } else if (force == 0) {
+    const float nf = (float)n;
+    const float num = rbf(__fdiv_rn(sums[0], nf));
+    const float den = rbf(__fdiv_rn(sums[1], nf));
+    rel = rbf(__fdiv_rn(num, rbf(den + 1e-8f)));
+    const double x = (double)rel;
+    double y = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) y = y * x + coef.c[i];
+    const double a = *accum + fabs(y);
+    if (a < thresh) {
+      *accum = a;
+      reuse = 1;
+    } else {
+      *accum = 0.0;
+    }
+  }  // force == 2: no previous modulated input yet -> compute, accumulator untouched
+  *flag = reuse;
+  if (hist) {
+    hist[2 * hist_idx] = (float)reuse;
+    hist[2 * hist_idx + 1] = rel;
+  }
+}
+
+// reuse (flag = 1): x += resid (hook.py:131-133);  compute (flag = 0): resid = x - ori (hook.py:152-154).  One pass either way.
+__global__ void __launch_bounds__(256) tea_residual_kernel(bf16* __restrict__ x, const bf16* __restrict__ ori, bf16* __restrict__ resid,
+                                                           long long n_vec, const int* __restrict__ flag) {
+  const bool reuse = *flag != 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const uint4 xv = ldg_v4(x + i * 8);
+    uint4 o;
+    if (reuse) {
+      const uint4 rv = ldg_nc_v4(resid + i * 8);
+      o.x = badd2(xv.x, rv.x); o.y = badd2(xv.y, rv.y); o.z = badd2(xv.z, rv.z); o.w = badd2(xv.w, rv.w);
+      stg_v4(x + i * 8, o);
+    } else {
+      const uint4 ov = ldg_nc_v4(ori + i * 8);
+      o.x = bsub2(xv.x, ov.x); o.y = bsub2(xv.y, ov.y); o.z = bsub2(xv.z, ov.z); o.w = bsub2(xv.w, ov.w);
+      stg_v4(resid + i * 8, o);
+    }
+  }
+}
+
 // Small-M linear ("GEMV"): y[m, n] = bf16( sum_k act(x[m,k]) * W[n,k] + bias[n] ), M <= 8 per pass.
 // HBM-bound on W (read exactly once).  Used for the timestep MLP (qwen_image_transformer.py:50-62),
 // all 2*L modulation projections img_mod/txt_mod (:552-557, batched into ONE launch over the
@@ -357,7 +418,10 @@ __global__ void timestep_sinusoid_kernel(const bf16* __restrict__ t, bf16* __res
 // neg == nullptr -> no CFG (noise = pos).
 __global__ void __launch_bounds__(256) cfg_euler_step_kernel(const bf16* __restrict__ pos, const bf16* __restrict__ neg,
                                                              bf16* __restrict__ x, long long rows, float cfg_scale,
-                                                             float dt) {
+                                                             float dt, const float* __restrict__ sigma_pair, int dt_fp32) {
+  // sigma_pair != nullptr: (sigma_i, sigma_{i+1}) live in device memory, so a CUDA graph of the step can be replayed
+  // for every timestep (the fp32 subtraction is the same one the host path does)
+  if (sigma_pair) dt = __ldg(sigma_pair + 1) - __ldg(sigma_pair);
   const long long vec = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte vector per thread
   const long long row = vec >> 3;
   const bool active = row < rows;
@@ -402,7 +466,10 @@ __global__ void __launch_bounds__(256) cfg_euler_step_kernel(const bf16* __restr
   }
   if (active) {
     uint32_t o[4];
-    const float dtb = rbf(dt);
+    // the scheduler's `dt * model_output` multiplies a 0-dim fp32 tensor with a bf16 tensor: type promotion keeps bf16,
+    // and a 0-dim DEVICE tensor (diffusers keeps sigmas on the device) is cast to bf16 inside the kernel before the
+    // multiply (dt_fp32 == 0, the default); a 0-dim CPU tensor would be used at fp32 instead (dt_fp32 != 0)
+    const float dtb = dt_fp32 ? dt : rbf(dt);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       o[k] = pack_bf16x2(bf16lo(xw[k]) + rbf(dtb * noise[2 * k]), bf16hi(xw[k]) + rbf(dtb * noise[2 * k + 1]));

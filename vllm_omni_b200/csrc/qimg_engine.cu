@@ -6,7 +6,10 @@
 // CUDA-graph capturable.
 #include "../../include/qimg_b200.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -25,6 +28,7 @@ struct qimg_engine {
   void* allreduce_user = nullptr;
   // peer-memory TP (qimg_engine_set_tp_p2p): every rank's workspace and barrier flags, mapped into this process
   bool p2p = false;
+  const int* blocks_predicate = nullptr;  // qimg_engine_set_blocks_predicate
   bool p2p_ready = false;  // peer pointers registered (qimg_engine_set_tp_p2p with non-NULL arrays)
   int tp_rank = 0;
   void* peer_ws[8] = {};
@@ -32,6 +36,29 @@ struct qimg_engine {
 };
 
 namespace {
+
+// NVTX ranges per launch family (SURVEY §5 tracing row): off by default (qimg_set_nvtx / env QIMG_NVTX=1); header-only NVTX3,
+// a no-op unless a profiler injects its library.
+int g_nvtx = -1;
+inline bool nvtx_on() {
+  if (g_nvtx < 0) {
+    const char* e = getenv("QIMG_NVTX");
+    g_nvtx = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_nvtx == 1;
+}
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(nvtx_on()) {
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
+  }
+};
+#define QIMG_RANGE_CAT2(a, b) a##b
+#define QIMG_RANGE_CAT(a, b) QIMG_RANGE_CAT2(a, b)
+#define QIMG_RANGE(name) NvtxRange QIMG_RANGE_CAT(_nvtx_range_, __LINE__)(name)
 
 inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
@@ -84,6 +111,14 @@ WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max, int
 }  // namespace
 
 extern "C" {
+
+void qimg_set_nvtx(int on) { g_nvtx = on != 0; }
+
+int qimg_engine_set_blocks_predicate(qimg_engine* e, const int* skip_flag) {
+  if (!e) return fail("qimg_engine_set_blocks_predicate: null engine");
+  e->blocks_predicate = skip_flag;
+  return 0;
+}
 
 int qimg_engine_create(const qimg_dims* dims, const qimg_global_weights* g, const qimg_block_weights* blocks,
                        qimg_engine** out) {
@@ -236,8 +271,10 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
   const long long mod_stride = (n_t == 1) ? 0 : mod_ld;         // shared timestep -> one modulation row
   const long long emb_stride = (n_t == 1) ? 0 : 2LL * D;
 
+  QIMG_RANGE("qimg.forward");
   // ---- prologue: temb, all modulations, img_in, txt_norm + txt_in -------------------------
   if (stages & QIMG_STAGE_PRE) {
+  QIMG_RANGE("qimg.pre (temb, modulations, img_in, txt_in)");
   QIMG_TRY(qimg_timestep_sinusoid(timestep, tsin, n_t, st));
   QIMG_TRY(qimg_linear_small_m(tsin, e->g.t_lin1_w, e->g.t_lin1_b, t1, n_t, D, 256, D, 0, st));
   QIMG_TRY(qimg_linear_small_m(t1, e->g.t_lin2_w, e->g.t_lin2_b, temb, n_t, D, D, D, 1, st));
@@ -271,7 +308,14 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
 
   // ---- 60 dual-stream blocks -----------------------------------------------------------------
   const float sm_scale = 1.0f / sqrtf(128.0f);
+  struct PredicateScope {  // the BLOCKS stage runs under the step cache's device predicate (if any)
+    explicit PredicateScope(const int* f) { set_launch_predicate(f); }
+    ~PredicateScope() { set_launch_predicate(nullptr); }
+  } predicate_scope((stages & QIMG_STAGE_BLOCKS) ? e->blocks_predicate : nullptr);
+  if (e->blocks_predicate && (stages & QIMG_STAGE_BLOCKS) && tp > 1)
+    return fail("qimg_engine_forward_stages: a blocks predicate is not supported under tensor parallelism");
   for (int l = 0; (stages & QIMG_STAGE_BLOCKS) && l < L; ++l) {
+    QIMG_RANGE("qimg.block");
     const qimg_block_weights& bw = e->blocks[l];
     // modulation layout per stream: [shift1, scale1, gate1, shift2, scale2, gate2] x D  (chunk(2) then chunk(3))
     const char* mi = mod_all + ((size_t)l * 12 * D) * 2;
@@ -284,6 +328,7 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
       QIMG_TRY(qimg_ln_modulate(x_txt, seg(mt, 0), seg(mt, 1), xm_txt, Mt, D, T, mod_stride, d.eps, st));
     }
     {
+      QIMG_RANGE("gemm.qkv+qknorm+rope");
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
       p[0].A = xm_img; p[0].W = bw.to_qkv_w; p[0].bias = bw.to_qkv_b; p[0].M = Mi; p[0].N = 3 * Dl; p[0].K = D;
@@ -295,7 +340,11 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
       p[1].pos_off = 0;
       QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_QKV, st));
     }
-    QIMG_TRY(qimg_fmha_joint(q, k, v, at_txt, at_img, B, Hl, S, T, sm_scale, st));
+    {
+      QIMG_RANGE("fmha.joint");
+      QIMG_TRY(qimg_fmha_joint(q, k, v, at_txt, at_img, B, Hl, S, T, sm_scale, st));
+    }
+    QIMG_RANGE("gemm.out_proj / ln2 / gemm.mlp_up / gemm.mlp_down (+ tp reductions)");
     if (tp == 1) {
       qimg_gemm_problem p[2];
       memset(p, 0, sizeof p);
@@ -383,6 +432,7 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
 
   // ---- epilogue: AdaLayerNormContinuous (scale first, then shift) + proj_out -------------------
   if (stages & QIMG_STAGE_POST) {
+  QIMG_RANGE("qimg.post (norm_out, proj_out)");
   if (!(tp > 1 && e->p2p))  // peer-memory TP: the last block's fused reduction already produced norm_out's rows in xm_img
     QIMG_TRY(qimg_ln_modulate(x_img, (const char*)emb_out + (size_t)D * 2, emb_out, xm_img, Mi, D, S_img, emb_stride, d.eps, st));
   {

@@ -46,6 +46,7 @@ struct FmhaParams {
   int B, H, S, T;
   float scale_log2;  // softmax_scale * log2(e)
   long long* trace;  // optional (qimg_set_fmha_trace): per-phase cycle counters of CTA 200
+  const int* skip;   // optional device predicate: non-zero -> exit at once (step-cache reuse)
   int* overflow;     // fast pipeline: set to 1 when a score exceeded the row's reference maximum by > 2^FMHA_OVF_LOG2
 };
 

@@ -38,6 +38,7 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (prm.skip && *prm.skip) return;  // uniform over the grid: nothing allocated or armed yet
   const int n_bh = prm.B * prm.H;
   const FmhaWork work = fmha_decode_cta(blockIdx.x, prm.S, n_bh);  // head-major, half pairs lagged (qimg_fmha.cuh)
   const int bh = work.bh, pair_idx = work.pair_idx;

@@ -60,6 +60,7 @@ struct GemmParams {
   GemmProblem p[2];
   int nprob;
   int total_tiles;
+  const int* skip;  // optional device predicate: non-zero -> the kernel exits at once (step-cache reuse, qimg_tea_decide)
 };
 
 constexpr int GEMM_BM = 128;
@@ -372,6 +373,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (prm.skip && *prm.skip) return;  // uniform over the grid: nothing allocated or armed yet
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);

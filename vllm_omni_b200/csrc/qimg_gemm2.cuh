@@ -95,6 +95,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  if (prm.skip && *prm.skip) return;  // uniform over the grid (both CTAs of every pair): nothing allocated or armed yet
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);

@@ -42,6 +42,12 @@ inline int fail(const char* what, const char* detail = nullptr) {
 
 int device_sm_count();  // cached; <= 0 on error
 
+// Device predicate applied to the launches of the CURRENT host thread (LN-modulate, tcgen05 GEMM, attention): while set,
+// every such kernel starts with `if (*flag) return;`.  The engine brackets its BLOCKS stage with it when a step cache
+// decided on the device (qimg_engine_set_blocks_predicate); nullptr = unconditional launches.
+void set_launch_predicate(const int* flag);
+const int* launch_predicate();
+
 // bf16 row-major matrix view [dim1 = rows][dim0 = cols] (optionally x dim2 batches), SWIZZLE_128B,
 // inner box = 64 elements (128 B).  Returns nullptr on failure (error recorded).
 const CUtensorMap* get_tmap_2d(const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows);

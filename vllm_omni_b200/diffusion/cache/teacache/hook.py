@@ -8,9 +8,12 @@ re-implementation of the blocks:
                             else               -> compute: BLOCKS, residual = x - x0  qimg_engine_forward_stages(2), qimg_bf16_sub
     POST  (norm_out, proj_out)                                                        qimg_engine_forward_stages(4)
 
-Like the reference (`.cpu().item()`, hook.py:204-205) the decision is taken on the host: one 8-byte read-back per forward.
-The relative distance goes through the same bf16 roundings as the reference's tensor expression (means in fp32 rounded to
-bf16, bf16 division).  Positive / negative CFG branches keep separate states (hook.py:115-122).
+The reference reads the distance back to the host every forward (`.cpu().item()`, hook.py:204-205).  Here the decision
+is taken ON THE DEVICE (`qimg_tea_decide`: one thread reproducing the host arithmetic bit for bit — means in fp32 rounded
+to bf16, bf16 division, the fp64 Horner polynomial and accumulator) and the engine's BLOCKS stage is launched predicated
+on the resulting flag, so the denoise loop issues no host<->device synchronisation; the (flag, distance) history is read
+once, when `decisions` is asked for.  Under tensor parallelism (collectives inside the blocks) the decision stays on the
+host, taken by TP rank 0 for the whole group.  Positive / negative CFG branches keep separate states (hook.py:115-122).
 """
 from __future__ import annotations
 
@@ -24,6 +27,8 @@ from vllm_omni_b200.diffusion.cache.teacache.state import TeaCacheState
 class TeaCacheHook:
     _HOOK_NAME = "teacache"
 
+    MAX_HISTORY = 4096  # forwards per run recorded in the device-side (flag, distance) history
+
     def __init__(self, config: TeaCacheConfig):
         self.config = config
         self.rescale_func = np.poly1d(config.coefficients)
@@ -31,7 +36,11 @@ class TeaCacheHook:
         self._forward_cnt = 0
         self._sums = None       # fp32 [2] device scratch of the reduction kernel
         self._ori = None        # image residual stream before the blocks
-        self.decisions: list[tuple[str, bool, float]] = []  # (branch, computed?, rel distance) of the current run
+        self._flag = None       # int32 [1]: 1 = reuse (device-side decision)
+        self._hist = None       # fp32 [2 * MAX_HISTORY]: (flag, rel distance) per forward
+        self._accum: dict[str, torch.Tensor] = {}  # branch -> fp64 [1] accumulated rescaled distance (device)
+        self._log: list[tuple[str, int]] = []      # (branch, force) per forward of the current run
+        self._host_decisions: list[tuple[str, bool, float]] = []
         self._tp_group = None   # set in run() when the transformer is tensor parallel
 
     # ---- state -------------------------------------------------------------------------------------------------
@@ -39,7 +48,16 @@ class TeaCacheHook:
         for st in self.states.values():
             st.reset()
         self._forward_cnt = 0
-        self.decisions = []
+        self._log = []
+        self._host_decisions = []
+
+    @property
+    def decisions(self) -> list[tuple[str, bool, float]]:
+        """(branch, computed?, rel distance) per forward of the current run.  Device mode: ONE read-back of the history."""
+        if self._tp_group is not None or self._hist is None:
+            return list(self._host_decisions)
+        h = self._hist[: 2 * len(self._log)].cpu().view(-1, 2)
+        return [(b, h[i, 0].item() == 0.0, float(h[i, 1])) for i, (b, _) in enumerate(self._log)]
 
     def _state(self, branch: str) -> TeaCacheState:
         if branch not in self.states:
@@ -52,7 +70,7 @@ class TeaCacheHook:
             return torch.empty_like(like)
         return t
 
-    # ---- decision (hook.py:170-217) ------------------------------------------------------------------------------
+    # ---- host decision (tensor-parallel runs; hook.py:170-217) ---------------------------------------------------
     def _should_compute(self, state: TeaCacheState, mod: torch.Tensor, qlib):
         if state.cnt == 0:
             state.accumulated_rel_l1_distance = 0.0
@@ -87,6 +105,49 @@ class TeaCacheHook:
         run_stage(qlib.STAGE_PRE)
         branch = "negative" if (module.do_true_cfg and self._forward_cnt % 2 == 1) else "positive"
         state = self._state(branch)
+        if self._tp_group is None:
+            self._run_device(module, run_stage, mod, x_img, qlib, branch, state)
+        else:
+            self._run_host(run_stage, mod, x_img, qlib, branch, state)
+        state.cnt += 1
+        self._forward_cnt += 1
+        run_stage(qlib.STAGE_POST)
+
+    def _run_device(self, module, run_stage, mod, x_img, qlib, branch, state):
+        dev = mod.device
+        if self._flag is None or self._flag.device != dev:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._hist = torch.zeros(2 * self.MAX_HISTORY, dtype=torch.float32, device=dev)
+            self._sums = torch.zeros(2, dtype=torch.float32, device=dev)
+            self._accum = {}
+        if branch not in self._accum:
+            self._accum[branch] = torch.zeros(1, dtype=torch.float64, device=dev)
+        # which steps are forced is step-count logic, known on the host without looking at data (hook.py:183-190)
+        force = 1 if state.cnt == 0 else (2 if not (state.has_mod and state.has_residual) else 0)
+        if force == 0:
+            qlib.rel_l1_sums(mod, state.previous_modulated_input, self._sums)
+        idx = len(self._log)
+        if idx >= self.MAX_HISTORY:
+            raise RuntimeError("TeaCache history overflow: call refresh() between generations")
+        qlib.tea_decide(self._sums, mod.numel(), self.config.coefficients, self.config.rel_l1_thresh, self._accum[branch],
+                        self._flag, self._hist, idx, force)
+        self._log.append((branch, force))
+        state.previous_modulated_input = self._buf(state.previous_modulated_input, mod)
+        state.previous_modulated_input.copy_(mod)   # before the blocks reuse the workspace buffer (hook.py:160)
+        state.has_mod = True
+        self._ori = self._buf(self._ori, x_img)
+        self._ori.copy_(x_img)
+        state.previous_residual = self._buf(state.previous_residual, x_img)
+        lib = qlib.load()
+        qlib.check(lib.qimg_engine_set_blocks_predicate(module._engine, self._flag.data_ptr()), "qimg_engine_set_blocks_predicate")
+        try:
+            run_stage(qlib.STAGE_BLOCKS)            # every kernel exits at once when the flag says "reuse"
+        finally:
+            qlib.check(lib.qimg_engine_set_blocks_predicate(module._engine, None), "qimg_engine_set_blocks_predicate")
+        qlib.tea_residual(x_img, self._ori, state.previous_residual, self._flag)  # reuse: x += r;  compute: r = x - x0
+        state.has_residual = True
+
+    def _run_host(self, run_stage, mod, x_img, qlib, branch, state):
         should_compute, rel = self._should_compute(state, mod, qlib)
         # keep this step's modulated input now: the blocks reuse its workspace buffer (hook.py:160 does it afterwards)
         state.previous_modulated_input = self._buf(state.previous_modulated_input, mod)
@@ -103,10 +164,7 @@ class TeaCacheHook:
             qlib.bf16_sub(state.previous_residual, x_img, self._ori)
             state.has_residual = True
             computed = True
-        state.cnt += 1
-        self._forward_cnt += 1
-        self.decisions.append((branch, computed, rel))
-        run_stage(qlib.STAGE_POST)
+        self._host_decisions.append((branch, computed, rel))
 
 
 def apply_teacache_hook(module, config: TeaCacheConfig) -> None:

@@ -14,6 +14,7 @@ Differences, all behind that interface:
 """
 from __future__ import annotations
 
+import dataclasses
 import logging
 import os
 import time
@@ -49,12 +50,21 @@ def shard_request(req: OmniDiffusionRequest, dp_rank: int, dp_size: int):
     def take(t):
         return None if t is None else t[idx]
 
+    def trim(e, m):
+        """Drop the padding columns no prompt of THIS shard uses (a shard that lacks the longest prompt would otherwise
+        carry a padded length T > max(txt_seq_lens), which the transformer rejects like the reference's RoPE broadcast)."""
+        if e is None or m is None:
+            return e, m
+        t_loc = max(int(m.sum(dim=1).max()), 1)
+        return e[:, :t_loc].contiguous(), m[:, :t_loc].contiguous()
+
+    pe_l, pm_l = trim(take(pe), take(req.prompt_attention_mask))
+    ne_l, nm_l = trim(take(req.negative_prompt_embeds), take(req.negative_attention_mask))
     local = dataclasses.replace(
-        req, prompt_embeds=take(pe), negative_prompt_embeds=take(req.negative_prompt_embeds),
-        prompt_attention_mask=take(req.prompt_attention_mask), negative_attention_mask=take(req.negative_attention_mask),
+        req, prompt_embeds=pe_l, negative_prompt_embeds=ne_l, prompt_attention_mask=pm_l, negative_attention_mask=nm_l,
         num_outputs_per_prompt=1, latents=None if req.latents is None else req.latents[lo:hi])
     if req.latents is None and req.seed is not None:
-        # deterministic per-unit noise independent of the DP layout: one generator per global unit index
+        # deterministic per-unit noise independent of the DP layout (also used at dp = 1): one generator per global unit
         g = [torch.Generator().manual_seed(req.seed + u) for u in range(lo, hi)]
         local.extra = dict(req.extra, unit_generators=g)
     return local, counts
@@ -116,22 +126,37 @@ class GPUWorker:
             self.cache_backend.refresh(self.pipeline, req.num_inference_steps)
         dp = ps.get_data_parallel_world_size()
         if dp == 1:
+            if req.latents is None and req.seed is not None and isinstance(req.prompt_embeds, torch.Tensor):
+                # the same per-unit noise a DP run draws, so dp=1 and dp>1 produce the same images for a seed
+                local, _ = shard_request(req, 0, 1)
+                req = dataclasses.replace(req, latents=self._unit_latents(local))
             return self.pipeline.forward(req)
         local, counts = shard_request(req, ps.get_data_parallel_rank(), dp)
-        lat = None
-        if local is not None:
-            gens = local.extra.get("unit_generators") if local.extra else None
-            if gens is not None and local.latents is None:
-                h, w = local.height or 1024, local.width or 1024
-                local.latents = torch.cat([self.pipeline.prepare_latents(1, self.pipeline.transformer.in_channels // 4, h, w,
-                                                                          torch.bfloat16, self.pipeline.device, g) for g in gens])
-            local.output_type = "latent"
-            lat = self.pipeline.forward(local).output
+        lat, err = None, None
+        try:
+            if local is not None:
+                if local.latents is None and local.extra and local.extra.get("unit_generators") is not None:
+                    local.latents = self._unit_latents(local)
+                local.output_type = "latent"
+                out = self.pipeline.forward(local)
+                lat, err = out.output, out.error
+        except Exception as e:  # a failing rank must not leave the others waiting in the gather
+            logger.error("Worker %d: denoise failed: %s", self.rank, e, exc_info=True)
+            err = str(e)
+        flag = torch.tensor([1 if err else 0], dtype=torch.int32, device=self.pipeline.device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=ps.get_dp_group())
+        if int(flag.item()):
+            return DiffusionOutput(error=err or "a data-parallel peer failed (see its log)")
         if lat is None:
             s_img = ((req.height or 1024) // 16) * ((req.width or 1024) // 16)
             lat = torch.zeros((0, s_img, self.pipeline.transformer.in_channels), dtype=torch.bfloat16, device=self.pipeline.device)
         full = ps.gather_to_rank0(lat, counts)
         return DiffusionOutput(output=full)
+
+    def _unit_latents(self, local: OmniDiffusionRequest) -> torch.Tensor:
+        h, w = local.height or 1024, local.width or 1024
+        return torch.cat([self.pipeline.prepare_latents(1, self.pipeline.transformer.in_channels // 4, h, w, torch.bfloat16,
+                                                        self.pipeline.device, g) for g in local.extra["unit_generators"]])
 
     def shutdown(self) -> None:
         ps.destroy_distributed_env()

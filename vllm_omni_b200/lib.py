@@ -27,7 +27,8 @@ EXPORTED_SYMBOLS = [
     "qimg_p2p_alloc", "qimg_p2p_free", "qimg_ipc_get_handle", "qimg_ipc_open_handle", "qimg_ipc_close_handle",
     "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error", "qimg_set_fmha_trace",
     "qimg_engine_forward_stages", "qimg_engine_ws_offset_mod", "qimg_rel_l1_sums", "qimg_bf16_sub", "qimg_bf16_add_inplace",
-    "qimg_fmha_joint_mode", "qimg_fmha_overflow",
+    "qimg_fmha_joint_mode", "qimg_fmha_overflow", "qimg_cfg_euler_step_dev", "qimg_set_euler_dt_fp32",
+    "qimg_set_nvtx", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
 ]
 
 
@@ -106,6 +107,10 @@ def load():
     lib.qimg_linear_small_m.argtypes = [vp, vp, vp, vp, i, ll, i, ll, i, vp]
     lib.qimg_timestep_sinusoid.argtypes = [vp, vp, i, vp]
     lib.qimg_cfg_euler_step.argtypes = [vp, vp, vp, ll, i, f, f, f, vp]
+    lib.qimg_cfg_euler_step_dev.argtypes = [vp, vp, vp, ll, i, f, vp, vp]
+    lib.qimg_set_euler_dt_fp32.argtypes = [i]
+    lib.qimg_set_nvtx.argtypes = [i]
+    lib.qimg_set_nvtx.restype = None
     lib.qimg_gemm.argtypes = [C.POINTER(GemmProblem), i, i, vp]
     lib.qimg_fmha_joint.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, f, vp]
     lib.qimg_fmha_joint_mode.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, f, i, vp]
@@ -126,6 +131,9 @@ def load():
     lib.qimg_rel_l1_sums.argtypes = [vp, vp, ll, vp, vp]
     lib.qimg_bf16_sub.argtypes = [vp, vp, vp, ll, vp]
     lib.qimg_bf16_add_inplace.argtypes = [vp, vp, ll, vp]
+    lib.qimg_tea_decide.argtypes = [vp, ll, C.POINTER(C.c_double), C.c_double, vp, vp, vp, i, i, vp]
+    lib.qimg_tea_residual.argtypes = [vp, vp, vp, ll, vp, vp]
+    lib.qimg_engine_set_blocks_predicate.argtypes = [vp, vp]
     lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.qimg_set_gemm_mode.argtypes = [i]
     lib.qimg_set_fmha_mode.argtypes = [i]
@@ -273,6 +281,21 @@ def cfg_euler_step(pos, neg, latents, cfg_scale: float, sigma: float, sigma_next
     return latents
 
 
+def cfg_euler_step_dev(pos, neg, latents, cfg_scale: float, sigma_pair: torch.Tensor):
+    """`cfg_euler_step` with (sigma_i, sigma_{i+1}) in a device fp32 tensor (CUDA-graph replayable)."""
+    _bf16c(pos), _bf16c(latents)
+    assert sigma_pair.dtype == torch.float32 and sigma_pair.is_cuda and sigma_pair.numel() >= 2
+    rows = latents.numel() // latents.shape[-1]
+    check(load().qimg_cfg_euler_step_dev(_p(pos), _p(neg), _p(latents), rows, latents.shape[-1], cfg_scale, _p(sigma_pair),
+                                         stream_ptr()), "qimg_cfg_euler_step_dev")
+    return latents
+
+
+def set_nvtx(on: bool):
+    """NVTX ranges around every launch family of the engine (Nsight Systems timelines); also env QIMG_NVTX=1."""
+    load().qimg_set_nvtx(int(on))
+
+
 def gemm(problems: list[GemmProblem], epilogue: int):
     arr = (GemmProblem * len(problems))(*problems)
     check(load().qimg_gemm(arr, len(problems), epilogue, stream_ptr()), "qimg_gemm")
@@ -349,6 +372,19 @@ def rel_l1_sums(a: torch.Tensor, b: torch.Tensor, sums2: torch.Tensor):
     _bf16c(a), _bf16c(b)
     assert a.numel() == b.numel() and sums2.dtype == torch.float32 and sums2.numel() >= 2
     check(load().qimg_rel_l1_sums(_p(a), _p(b), a.numel(), _p(sums2), stream_ptr()), "qimg_rel_l1_sums")
+
+
+def tea_decide(sums2, n: int, coefficients, thresh: float, accum: torch.Tensor, flag: torch.Tensor, hist, hist_idx: int, force: int):
+    """Device-side TeaCache decision (qimg_tea_decide): accum fp64 [1], flag int32 [1], hist fp32 [2 * steps] or None."""
+    assert accum.dtype == torch.float64 and flag.dtype == torch.int32
+    coef = (C.c_double * 5)(*[float(c) for c in coefficients])
+    check(load().qimg_tea_decide(_p(sums2), int(n), coef, float(thresh), _p(accum), _p(flag), _p(hist), int(hist_idx), int(force),
+                                 stream_ptr()), "qimg_tea_decide")
+
+
+def tea_residual(x: torch.Tensor, ori: torch.Tensor, resid: torch.Tensor, flag: torch.Tensor):
+    _bf16c(x), _bf16c(ori), _bf16c(resid)
+    check(load().qimg_tea_residual(_p(x), _p(ori), _p(resid), x.numel(), _p(flag), stream_ptr()), "qimg_tea_residual")
 
 
 def bf16_sub(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
