@@ -52,7 +52,7 @@ def test_library_loaded_and_device():
     assert os.path.exists(q.LIB_PATH)
 
 
-@pytest.fixture(params=[4, 6, 12, 14], ids=["exact", "fast", "exact-poly25", "fast-poly25"])
+@pytest.fixture(params=[4, 6, 7, 12, 14, 15], ids=["exact", "fast", "fast1tile", "exact-poly25", "fast-poly25", "fast1tile-poly25"])
 def fmha_mode(request):
     """Both shipped attention pipelines (exact = per-tile maximum first; fast = running reference maximum + overflow
     guard), each with and without the 25 % FMA-pipe polynomial share."""
@@ -301,14 +301,15 @@ def test_fmha_adversarial_score_jump_guard(spike_pos, nats):
     qo, ko, vo = (t.permute(0, 2, 1, 3).contiguous().to(dev) for t in (qq, kk, vv))
     _, oe = q.fmha_joint(qo, ko, vo, 0, 128 ** -0.5, mode=q.FMHA_EXACT)
     assert O.rel_fro(oe.cpu().view(1, S, 128), ref) < TOL_KERNEL
-    q.fmha_overflow(reset=True)
-    _, of = q.fmha_joint(qo, ko, vo, 0, 128 ** -0.5, mode=q.FMHA_FAST)
-    flagged = q.fmha_overflow(reset=True)
-    err = O.rel_fro(of.cpu().view(1, S, 128).nan_to_num(1e30), ref)
-    print(f"spike {spike_pos} +{nats} nats: fast flagged={flagged} err={err:.3e}")
-    assert flagged == (nats * 1.4427 > 100.0)          # 69.3 nats = 2^100
-    assert flagged or err < TOL_KERNEL
-    assert not q.fmha_overflow()                         # reset worked
+    for fast in (q.FMHA_FAST, 7):                        # both fast pipelines (two query tiles / one query tile per CTA)
+        q.fmha_overflow(reset=True)
+        _, of = q.fmha_joint(qo, ko, vo, 0, 128 ** -0.5, mode=fast)
+        flagged = q.fmha_overflow(reset=True)
+        err = O.rel_fro(of.cpu().view(1, S, 128).nan_to_num(1e30), ref)
+        print(f"spike {spike_pos} +{nats} nats: mode {fast} flagged={flagged} err={err:.3e}")
+        assert flagged == (nats * 1.4427 > 100.0)          # 69.3 nats = 2^100
+        assert flagged or err < TOL_KERNEL
+        assert not q.fmha_overflow()                         # reset worked
 
 
 def test_denoise_falls_back_to_exact_attention_when_flagged():

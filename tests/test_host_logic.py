@@ -405,3 +405,25 @@ def test_worker_proc_message_protocol(monkeypatch):
     p1.worker_busy_loop()
     assert p1.worker.shut
     assert gw.get_diffusion_worker_class() is gw.WorkerProc
+
+
+def test_prompt_encode_glue_matches_reference_golden(golden_dir):
+    """`QwenImagePipeline.encode_prompt` / `_get_qwen_prompt_embeds` (chat template, 34-token preamble drop, masked
+    extraction, right padding, per-image repeat, truncation) against the outputs of the UNMODIFIED reference functions
+    (pipeline_qwen_image.py:348-434) on the same deterministic tokenizer / encoder stand-ins — bit-equal."""
+    import os
+
+    from oracle import prompt_stubs
+    from vllm_omni_b200.diffusion.data import OmniDiffusionConfig, TransformerConfig
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image import QwenImagePipeline
+    fx = torch.load(os.path.join(golden_dir, "prompt_encode.pt"))
+    od = OmniDiffusionConfig(tf_model_config=TransformerConfig.from_dict({"num_layers": 1}))
+    pipe = QwenImagePipeline(od_config=od, text_encoder=prompt_stubs.StubTextEncoder(), tokenizer=prompt_stubs.StubTokenizer(),
+                             transformer_kwargs=dict(num_attention_heads=2, joint_attention_dim=48))
+    e, m = pipe.encode_prompt(fx["prompts"], num_images_per_prompt=2)
+    assert torch.equal(e, fx["embeds_x2"]) and torch.equal(m, fx["mask_x2"])
+    e, m = pipe.encode_prompt(fx["prompts"][1], num_images_per_prompt=1, max_sequence_length=40)
+    assert torch.equal(e, fx["embeds_trunc40"]) and torch.equal(m, fx["mask_trunc40"])
+    # pre-computed embeddings pass through untouched apart from the repeat (the stage-overlap path, SURVEY §8f N3)
+    e2, m2 = pipe.encode_prompt(None, num_images_per_prompt=2, prompt_embeds=fx["embeds_trunc40"], prompt_embeds_mask=fx["mask_trunc40"])
+    assert e2.shape[0] == 2 and torch.equal(e2[0], fx["embeds_trunc40"][0]) and torch.equal(m2[1], fx["mask_trunc40"][0])

@@ -9,6 +9,7 @@
 #include "qimg_fmha.cuh"
 #include "qimg_fmha4.cuh"
 #include "qimg_fmha6.cuh"
+#include "qimg_fmha7.cuh"
 #include "qimg_gemm.cuh"
 #include "qimg_gemm2.cuh"
 #include "qimg_host.cuh"
@@ -422,10 +423,14 @@ static int* fmha_overflow_flag() {
 template <uint32_t MASK>
 static int launch_fmha_inst(int pipeline, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
                             const FmhaParams& prm, cudaStream_t st) {
-  static bool done7[kMaxDevices] = {}, done9[kMaxDevices] = {};
+  static bool done7[kMaxDevices] = {}, done9[kMaxDevices] = {}, done10[kMaxDevices] = {};
   const int pairs = (prm.S + 255) / 256;
   const int grid = pairs * prm.B * prm.H;
-  if (pipeline == 6) {
+  if (pipeline == 7) {
+    if (ensure_smem_attr(fmha_joint_kernel_v10<MASK>, FMHA7_SMEM_BYTES, done10)) return 1;
+    const int grid10 = ((prm.S + 127) / 128) * prm.B * prm.H;  // one 128-row query tile per CTA
+    fmha_joint_kernel_v10<MASK><<<grid10, FMHA7_THREADS, FMHA7_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
+  } else if (pipeline == 6) {
     if (ensure_smem_attr(fmha_joint_kernel_v9<MASK>, FMHA4_SMEM_BYTES, done9)) return 1;
     fmha_joint_kernel_v9<MASK><<<grid, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   } else {
@@ -665,13 +670,13 @@ static int fmha_mode() {
   if (g_fmha_mode < 0) {
     const char* e = getenv("QIMG_FMHA_MODE");
     g_fmha_mode = e ? atoi(e) : 6;
-    if ((g_fmha_mode & 7) != 4 && (g_fmha_mode & 7) != 6) g_fmha_mode = 6;
+    if ((g_fmha_mode & 7) != 4 && (g_fmha_mode & 7) != 6 && (g_fmha_mode & 7) != 7) g_fmha_mode = 6;
   }
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode < 0 || mode > 15 || ((mode & 7) != 4 && (mode & 7) != 6))
-    return fail("qimg_set_fmha_mode: mode must be 4 (exact) or 6 (fast), optionally | 8 (25 % polynomial exponentials)");
+  if (mode < 0 || mode > 15 || ((mode & 7) != 4 && (mode & 7) != 6 && (mode & 7) != 7))
+    return fail("qimg_set_fmha_mode: mode must be 4 (exact), 6 or 7 (fast), optionally | 8 (25 % polynomial exponentials)");
   g_fmha_mode = mode;
   return 0;
 }
@@ -698,7 +703,7 @@ int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
   if (mode < 0) mode = fmha_mode();
   const int pipeline = mode & 7;
-  if (mode > 15 || (pipeline != 4 && pipeline != 6)) return fail("qimg_fmha_joint: mode must be 4 (exact) or 6 (fast) [| 8]");
+  if (mode > 15 || (pipeline != 4 && pipeline != 6 && pipeline != 7)) return fail("qimg_fmha_joint: mode must be 4 (exact), 6 or 7 (fast) [| 8]");
   tmap_cache_trim();
   const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
   const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, 128);

@@ -117,10 +117,19 @@ class ComponentSource:
 
 
 class QwenImagePipeline(nn.Module):
-    def __init__(self, *, od_config: OmniDiffusionConfig, prefix: str = "", text_encoder=None, vae=None,
+    # prompt template of the reference pipeline (pipeline_qwen_image.py:283-285): the first 34 tokens of the encoded
+    # sequence are the system preamble and are dropped from the embeddings
+    prompt_template_encode = ("<|im_start|>system\nDescribe the image by detailing the color, shape, size, texture, quantity, text, "
+                              "spatial relationships of the objects and background:<|im_end|>\n<|im_start|>user\n{}<|im_end|>\n"
+                              "<|im_start|>assistant\n")
+    prompt_template_encode_start_idx = 34
+    tokenizer_max_length = 1024
+
+    def __init__(self, *, od_config: OmniDiffusionConfig, prefix: str = "", text_encoder=None, vae=None, tokenizer=None,
                  transformer_kwargs: dict | None = None):
         super().__init__()
         self.od_config = od_config
+        self.tokenizer = tokenizer
         self.weights_sources = [ComponentSource(model_or_path=od_config.model, subfolder="transformer", revision=None,
                                                 prefix="transformer.", fall_back_to_pt=True)]
         self.scheduler = FlowMatchEulerDiscreteScheduler()
@@ -155,6 +164,45 @@ class QwenImagePipeline(nn.Module):
                 if n.startswith("transformer."):
                     yield n[len("transformer."):], t
         return {"transformer." + n for n in self.transformer.load_weights(strip(weights))}
+
+    # ---- prompt encoding glue: reference :348-434 (the encoder / tokenizer are the transformers objects the reference
+    # itself loads, `Qwen2_5_VLForConditionalGeneration` / `Qwen2Tokenizer` :264-272 — injected, not re-implemented) ----
+    @staticmethod
+    def _extract_masked_hidden(hidden_states: torch.Tensor, mask: torch.Tensor):
+        keep = mask.bool()
+        return torch.split(hidden_states[keep], keep.sum(dim=1).tolist(), dim=0)
+
+    def _get_qwen_prompt_embeds(self, prompt, dtype: torch.dtype | None = None):
+        """Chat-template the prompts, run the text encoder, take the last hidden state, drop each sample's padding and the
+        34-token preamble, right-pad to the longest remainder -> (embeds [B, T, joint], mask [B, T] of ones / zeros)."""
+        if self.text_encoder is None or self.tokenizer is None:
+            raise ValueError("a text encoder and a tokenizer are required to encode prompts (inject them, or pass prompt_embeds)")
+        dtype = dtype or self.text_encoder.dtype
+        prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+        drop = self.prompt_template_encode_start_idx
+        tok = self.tokenizer([self.prompt_template_encode.format(p) for p in prompts], max_length=self.tokenizer_max_length + drop,
+                             padding=True, truncation=True, return_tensors="pt").to(self.device)
+        hidden = self.text_encoder(input_ids=tok.input_ids, attention_mask=tok.attention_mask,
+                                   output_hidden_states=True).hidden_states[-1]
+        rows = [h[drop:] for h in self._extract_masked_hidden(hidden, tok.attention_mask)]
+        T = max(r.size(0) for r in rows)
+        embeds = torch.stack([torch.cat([r, r.new_zeros(T - r.size(0), r.size(1))]) for r in rows])
+        mask = torch.stack([torch.cat([torch.ones(r.size(0), dtype=torch.long, device=r.device),
+                                       torch.zeros(T - r.size(0), dtype=torch.long, device=r.device)]) for r in rows])
+        return embeds.to(dtype=dtype), mask
+
+    def encode_prompt(self, prompt, num_images_per_prompt: int = 1, prompt_embeds: torch.Tensor | None = None,
+                      prompt_embeds_mask: torch.Tensor | None = None, max_sequence_length: int = 1024):
+        """reference :398-434: encode (unless embeddings are given), truncate, repeat per output image (prompt-major)."""
+        prompts = [prompt] if isinstance(prompt, str) else prompt
+        b = len(prompts) if prompt_embeds is None else prompt_embeds.shape[0]
+        if prompt_embeds is None:
+            prompt_embeds, prompt_embeds_mask = self._get_qwen_prompt_embeds(prompts)
+        prompt_embeds, prompt_embeds_mask = prompt_embeds[:, :max_sequence_length], prompt_embeds_mask[:, :max_sequence_length]
+        t = prompt_embeds.shape[1]
+        prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, t, -1)
+        prompt_embeds_mask = prompt_embeds_mask.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, t)
+        return prompt_embeds, prompt_embeds_mask
 
     # ---- reference :435-488 ---------------------------------------------------------------------
     @staticmethod
@@ -382,14 +430,12 @@ class QwenImagePipeline(nn.Module):
                                        else negative_prompt_embeds_mask)
         if height % (self.vae_scale_factor * 2) or width % (self.vae_scale_factor * 2):
             raise ValueError(f"height and width must be divisible by {self.vae_scale_factor * 2}")
-        if prompt_embeds is None:
-            if self.text_encoder is None:
-                raise ValueError("prompt_embeds are required: the Qwen2.5-VL prompt encoder is outside the native "
-                                 "DiT engine's scope (inject `text_encoder` or pass embeddings)")
-            prompt_embeds, prompt_embeds_mask = self.text_encoder(req.prompt if req.prompt is not None else prompt)
+        if prompt_embeds is None:  # in-process prompt encoding, as the reference does (:357-396); else the embeddings come
+            # from the request (an upstream encoder stage feeds them through a connector)
+            prompt_embeds, prompt_embeds_mask = self._get_qwen_prompt_embeds(req.prompt if req.prompt is not None else prompt)
             neg = req.negative_prompt if req.negative_prompt is not None else negative_prompt
             if neg is not None and true_cfg_scale > 1:
-                negative_prompt_embeds, negative_prompt_embeds_mask = self.text_encoder(neg)
+                negative_prompt_embeds, negative_prompt_embeds_mask = self._get_qwen_prompt_embeds(neg)
         dev = self.device
 
         def rep(e, m):
