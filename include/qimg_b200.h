@@ -45,6 +45,9 @@ void qimg_set_nvtx(int on);
  * (cta_group::2, cluster of 2).  Default 1; env QIMG_GEMM_MODE overrides. */
 int qimg_set_gemm_mode(int mode);
 int qimg_get_gemm_mode(void);
+/* Raster band height in 256-row tiles (default 8; env QIMG_GEMM_GROUP_M): tiles of a band visit every weight column while
+ * the band's activations stay in L2; each band streams the weight matrix from HBM once. */
+int qimg_set_gemm_group_m(int tiles);
 
 /* Attention pipeline, mode = pipeline | (poly << 3):
  *   pipeline 4 = EXACT: every KV tile's row maximum is reduced (and exchanged between the two threads of a row) before
@@ -54,9 +57,6 @@ int qimg_get_gemm_mode(void);
  *                tensor pipe in two halves.  Exact as long as no score exceeds the reference by more than 2^100 (a jump
  *                of > 69 nats inside one 128-key tile); such a launch sets a device-side flag — see qimg_fmha_overflow —
  *                and the caller must recompute with pipeline 4 (the native denoise loop does, once per 50 steps).
- *            7 = FAST, one 128-row query tile per CTA with double-buffered scores and a separate P region (four softmax
- *                threads per row, scores in registers): Q*K^T of tile j+2 and P*V of tile j run in the shadow of the
- *                exponentials of tile j+1; same softmax scheme and guard as 6 (csrc/qimg_fmha7.cuh).
  *   poly 1 = 25 % of the softmax exponentials on a degree-3 FMA-pipe polynomial instead of MUFU.EX2.
  * Env QIMG_FMHA_MODE overrides the default.  (Round 1 shipped seven pipelines; five lost and were deleted.) */
 int qimg_set_fmha_mode(int mode);

@@ -34,6 +34,8 @@ CASES = {
     # image-edit layout (pipeline_qwen_image_edit.py:602): noisy latents (8x6) followed by one condition image (4x6) on
     # the sequence axis; two RoPE grids, text positions after the larger one
     "tiny_edit_two_grids": dict(L=2, H=2, joint=256, B=2, grid=(8, 6), extra_grids=[(4, 6)], T=24, seed=5),
+    # edit-plus layout (pipeline_qwen_image_edit_plus.py:436-464,729-737): TWO condition images of different sizes
+    "tiny_edit_three_grids": dict(L=2, H=2, joint=256, B=1, grid=(8, 6), extra_grids=[(4, 6), (3, 5)], T=24, seed=8),
     # the headline shape of BASELINE configs[1] (1024 px: 64x64 latent grid, T=128, D=3072, H=24, S=4224: 33 KV tiles,
     # 17 query-tile pairs, 8-band GEMM raster), depth cut to 2 so the fp32 reference fits the build container
     "fullwidth_1024px_L2": dict(L=2, H=24, joint=3584, B=1, grid=(64, 64), T=128, seed=6),

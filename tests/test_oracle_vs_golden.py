@@ -9,7 +9,7 @@ import torch
 from oracle import qwen_image_oracle as O
 from vllm_omni_b200 import synthetic
 
-CASES = ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1", "tiny_edit_two_grids"]
+CASES = ["tiny_L2_H2", "narrow_L1_H4_ragged", "fullwidth_L1", "tiny_edit_two_grids", "tiny_edit_three_grids"]
 
 
 def case_grids(c):

@@ -12,7 +12,7 @@ from vllm_omni_b200 import lib as q  # noqa: E402
 
 dev, bf, H, T = "cuda", torch.bfloat16, 24, 128
 shapes = [tuple(int(v) for v in s.split(",")) for s in os.environ.get("FS_SHAPES", "4,4224;1,4224;4,1152;1,16512").split(";")]
-modes = [int(m) for m in os.environ.get("FS_MODES", "4,6,14,7,15").split(",")]
+modes = [int(m) for m in os.environ.get("FS_MODES", "4,6,12,14").split(",")]
 g = torch.Generator(device=dev).manual_seed(0)
 
 

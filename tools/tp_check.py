@@ -7,6 +7,11 @@ and times both (CUDA events, max over ranks).
                 kernel reduces, applies bias + gate + residual + the next AdaLN and all-gathers the rows (qimg_tp_p2p.cu)
   TP_COMM=nccl  bf16 partial sums + NCCL all-reduce + epilogue kernel (comparison baseline)
   TP_CASES="comm,L,res,B;..." runs several cases in one launch (overrides TP_COMM / TP_LAYERS / TP_RES / TP_BATCH).
+  TP_GOLDEN=<fixture>  instead: the TP engine on a reference-generated fixture (tests/golden/<fixture>.pt), judged by
+                criterion (iii): err(TP, fp32 reference) <= err(reference-bf16, fp32 reference) + 1e-2.  Two bf16 evaluation
+                orders (TP vs one GPU, or native vs reference) differ by the bf16 noise floor of the depth — 7e-3 at L=8,
+                1.7e-2 at L=60 — however exact the partial sums are, so accuracy is measured against fp32, not against
+                another bf16 run.
 """
 import os
 import sys
@@ -31,6 +36,31 @@ def build(L, dev, **kw):
         torch.set_default_dtype(torch.float32)
     m.load_weights(synthetic.synthetic_weights(L, seed=0, norm_jitter=0.1, device=dev, device_generate=True))
     return m
+
+
+def golden_check(name, rank, world, dev, comm):
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", name + ".pt"))
+    c = fx["case"]
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(dev):
+            m = QwenImageTransformer2DModel(num_layers=c["L"], num_attention_heads=c["H"], joint_attention_dim=c["joint"],
+                                            tp_size=world, tp_rank=ps.get_tensor_model_parallel_rank(), tp_group=ps.get_tp_group(),
+                                            tp_comm=comm)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    m.load_weights(synthetic.synthetic_weights(c["L"], seed=c["seed"], norm_jitter=0.1, num_heads=c["H"], joint_dim=c["joint"]))
+    h, w_ = c["grid"]
+    out = m(fx["hidden_states"].to(dev), fx["encoder_hidden_states"].to(dev), None, fx["timestep"].to(dev),
+            [[(1, h, w_)]] * c["B"], [c["T"]] * c["B"], return_dict=False)[0].cpu()
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())  # noqa: E731
+    e32, eref = rel(out, fx["ref_fp32"]), rel(out, fx["ref_bf16"])
+    ok = (not torch.isnan(out).any()) and e32 <= fx["ref_bf16_vs_fp32"] + 1e-2
+    if rank == 0:
+        print(f"tp_check golden {name} tp={world} comm={comm}: TP vs fp32 {e32:.3e}; reference-bf16 vs fp32 "
+              f"{fx['ref_bf16_vs_fp32']:.3e}; TP vs reference-bf16 {eref:.3e} -> criterion (iii) {'ok' if ok else 'FAILED'}", flush=True)
+    return bool(ok)
 
 
 def timed(fn, n, dev):
@@ -58,6 +88,11 @@ def main():
                                                                os.environ.get("TP_RES", "512"), os.environ.get("TP_BATCH", "1"))
     tol = float(os.environ.get("TP_TOL", "1e-2"))
     ok = True
+    if os.environ.get("TP_GOLDEN"):
+        ok = golden_check(os.environ["TP_GOLDEN"], rank, world, dev, os.environ.get("TP_COMM", "p2p"))
+        dist.barrier()
+        ps.destroy_distributed_env()
+        sys.exit(0 if ok else 1)
     for case in cases.split(";"):
         comm, L, res, B = case.split(",")
         L, res, B = int(L), int(res), int(B)

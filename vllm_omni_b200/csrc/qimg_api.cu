@@ -9,7 +9,6 @@
 #include "qimg_fmha.cuh"
 #include "qimg_fmha4.cuh"
 #include "qimg_fmha6.cuh"
-#include "qimg_fmha7.cuh"
 #include "qimg_gemm.cuh"
 #include "qimg_gemm2.cuh"
 #include "qimg_host.cuh"
@@ -226,6 +225,19 @@ static int gemm_mode() {
   return g_gemm_mode;
 }
 
+// raster band height of the CTA-pair kernel in 256-row tiles (the 1-CTA kernel uses twice as many 128-row tiles): the
+// tiles of a band sweep every weight column while the band's activations stay L2-resident; each band re-streams the weight
+// matrix from HBM once, so taller bands cut weight re-reads (8 bands -> 4 at M = 16384 with 16)
+static int g_gemm_group_m = -1;
+static int gemm_group_m() {
+  if (g_gemm_group_m < 0) {
+    const char* e = getenv("QIMG_GEMM_GROUP_M");
+    g_gemm_group_m = e ? atoi(e) : GEMM2_GROUP_M;
+    if (g_gemm_group_m < 1) g_gemm_group_m = GEMM2_GROUP_M;
+  }
+  return g_gemm_group_m;
+}
+
 static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStream_t st) {
   if (nprob < 1 || nprob > 2) return fail("qimg_gemm: nprob must be 1 or 2");
   tmap_cache_trim();
@@ -291,6 +303,7 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
   }
   prm.total_tiles = tiles;
   prm.skip = launch_predicate();
+  prm.group_m = pair ? gemm_group_m() : 2 * gemm_group_m();
   double flops = 0;
   for (int i = 0; i < nprob; ++i) flops += 2.0 * pr[i].M * (double)pr[i].N * pr[i].K;
   ProfScope prof(0, flops, st);
@@ -423,14 +436,10 @@ static int* fmha_overflow_flag() {
 template <uint32_t MASK>
 static int launch_fmha_inst(int pipeline, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
                             const FmhaParams& prm, cudaStream_t st) {
-  static bool done7[kMaxDevices] = {}, done9[kMaxDevices] = {}, done10[kMaxDevices] = {};
+  static bool done7[kMaxDevices] = {}, done9[kMaxDevices] = {};
   const int pairs = (prm.S + 255) / 256;
   const int grid = pairs * prm.B * prm.H;
-  if (pipeline == 7) {
-    if (ensure_smem_attr(fmha_joint_kernel_v10<MASK>, FMHA7_SMEM_BYTES, done10)) return 1;
-    const int grid10 = ((prm.S + 127) / 128) * prm.B * prm.H;  // one 128-row query tile per CTA
-    fmha_joint_kernel_v10<MASK><<<grid10, FMHA7_THREADS, FMHA7_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
-  } else if (pipeline == 6) {
+  if (pipeline == 6) {
     if (ensure_smem_attr(fmha_joint_kernel_v9<MASK>, FMHA4_SMEM_BYTES, done9)) return 1;
     fmha_joint_kernel_v9<MASK><<<grid, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
   } else {
@@ -456,6 +465,11 @@ int qimg_set_gemm_mode(int mode) {
   return 0;
 }
 int qimg_get_gemm_mode(void) { return gemm_mode(); }
+int qimg_set_gemm_group_m(int tiles) {
+  if (tiles < 1 || tiles > 1024) return fail("qimg_set_gemm_group_m: band height must be in [1, 1024] tiles");
+  g_gemm_group_m = tiles;
+  return 0;
+}
 
 int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* flops_total) {
   if (kind < 0 || kind > 1) return fail("qimg_prof_collect: kind");
@@ -670,13 +684,13 @@ static int fmha_mode() {
   if (g_fmha_mode < 0) {
     const char* e = getenv("QIMG_FMHA_MODE");
     g_fmha_mode = e ? atoi(e) : 6;
-    if ((g_fmha_mode & 7) != 4 && (g_fmha_mode & 7) != 6 && (g_fmha_mode & 7) != 7) g_fmha_mode = 6;
+    if ((g_fmha_mode & 7) != 4 && (g_fmha_mode & 7) != 6) g_fmha_mode = 6;
   }
   return g_fmha_mode;
 }
 int qimg_set_fmha_mode(int mode) {
-  if (mode < 0 || mode > 15 || ((mode & 7) != 4 && (mode & 7) != 6 && (mode & 7) != 7))
-    return fail("qimg_set_fmha_mode: mode must be 4 (exact), 6 or 7 (fast), optionally | 8 (25 % polynomial exponentials)");
+  if (mode < 0 || mode > 15 || ((mode & 7) != 4 && (mode & 7) != 6))
+    return fail("qimg_set_fmha_mode: mode must be 4 (exact) or 6 (fast), optionally | 8 (25 % polynomial exponentials)");
   g_fmha_mode = mode;
   return 0;
 }
@@ -703,7 +717,7 @@ int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
   if (mode < 0) mode = fmha_mode();
   const int pipeline = mode & 7;
-  if (mode > 15 || (pipeline != 4 && pipeline != 6 && pipeline != 7)) return fail("qimg_fmha_joint: mode must be 4 (exact), 6 or 7 (fast) [| 8]");
+  if (mode > 15 || (pipeline != 4 && pipeline != 6)) return fail("qimg_fmha_joint: mode must be 4 (exact) or 6 (fast) [| 8]");
   tmap_cache_trim();
   const CUtensorMap* tq = get_tmap_3d(q, 128, (uint64_t)S, (uint64_t)B * H, 128);
   const CUtensorMap* tk = get_tmap_3d(k, 128, (uint64_t)S, (uint64_t)B * H, 128);

@@ -60,6 +60,7 @@ struct GemmParams {
   GemmProblem p[2];
   int nprob;
   int total_tiles;
+  int group_m;      // raster band height in tiles (launcher: qimg_set_gemm_group_m)
   const int* skip;  // optional device predicate: non-zero -> the kernel exits at once (step-cache reuse, qimg_tea_decide)
 };
 
@@ -403,7 +404,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-      TileCoord tc = decode_tile(prm, tile);
+      TileCoord tc = decode_tile(prm, tile, prm.group_m);
       const GemmProblem& P = prm.p[tc.pi];
       const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
       const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
@@ -431,7 +432,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-      TileCoord tc = decode_tile(prm, tile);
+      TileCoord tc = decode_tile(prm, tile, prm.group_m);
       const GemmProblem& P = prm.p[tc.pi];
       const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -475,7 +476,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-      TileCoord tc = decode_tile(prm, tile);
+      TileCoord tc = decode_tile(prm, tile, prm.group_m);
       const GemmProblem& P = prm.p[tc.pi];
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();

@@ -18,7 +18,7 @@
 namespace qimg {
 
 constexpr int GEMM2_STAGES = 6;
-constexpr int GEMM2_GROUP_M = 8;  // 8 x 256 rows per raster band (same 2048 rows as the 1-CTA kernel)
+constexpr int GEMM2_GROUP_M = 16;  // default raster band: 16 x 256 rows = 4 bands at M = 16384 (8 -> 16: +1.5..2 % and half the weight re-reads, profiles/r02_gemm_group_m.log; 32 loses: the activation band falls out of L2) (qimg_set_gemm_group_m overrides; 1-CTA kernel: 2x as many 128-row tiles)
 constexpr int GEMM2_A_BYTES = 128 * GEMM_BK * 2;
 constexpr int GEMM2_B_BYTES = 128 * GEMM_BK * 2;
 constexpr int GEMM2_STAGE_BYTES = GEMM2_A_BYTES + GEMM2_B_BYTES;
@@ -125,7 +125,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < prm.total_tiles; tile += num_clusters) {
-      TileCoord tc = decode_tile(prm, tile, GEMM2_GROUP_M);
+      TileCoord tc = decode_tile(prm, tile, prm.group_m);
       const GemmProblem& P = prm.p[tc.pi];
       const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
       const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
@@ -157,7 +157,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < prm.total_tiles; tile += num_clusters) {
-        TileCoord tc = decode_tile(prm, tile, GEMM2_GROUP_M);
+        TileCoord tc = decode_tile(prm, tile, prm.group_m);
         const GemmProblem& P = prm.p[tc.pi];
         const int kblocks = (P.K + GEMM_BK - 1) / GEMM_BK;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -200,7 +200,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < prm.total_tiles; tile += num_clusters) {
-      TileCoord tc = decode_tile(prm, tile, GEMM2_GROUP_M);
+      TileCoord tc = decode_tile(prm, tile, prm.group_m);
       const GemmProblem& P = prm.p[tc.pi];
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();

@@ -43,5 +43,38 @@ class QwenImageEditPipeline(QwenImagePipeline):
         return il, shapes
 
 
+class QwenImageEditPlusPipeline(QwenImageEditPipeline):
+    """Several condition images (reference pipeline_qwen_image_edit_plus.py:436-464,729-737): each image's packed latents
+    follow the noisy latents on the sequence axis in the order given, `img_shapes` lists the output grid and then one grid
+    per image, RoPE gives the k-th image the frame index k.  The request carries
+        req.extra["image_latents"]       list of [B or 1, S_k, 64] tensors (or one tensor already concatenated on dim 1)
+        req.extra["image_latent_grids"]  [(h_k, w_k), ...] with h_k * w_k == S_k
+    A single image behaves exactly like QwenImageEditPipeline."""
+
+    def _condition_latents(self, req: OmniDiffusionRequest, batch: int, img_shapes):
+        ex = req.extra or {}
+        il, grids = ex.get("image_latents"), ex.get("image_latent_grids")
+        if il is None:
+            return None, img_shapes
+        if grids is None:
+            return super()._condition_latents(req, batch, img_shapes)
+        parts = list(il) if isinstance(il, (list, tuple)) else list(torch.split(il, [int(h) * int(w) for h, w in grids], dim=1))
+        if len(parts) != len(grids) or any(p.shape[1] != int(h) * int(w) for p, (h, w) in zip(parts, grids)):
+            raise ValueError("image_latent_grids must list one (h, w) per condition image with h * w == its token count")
+        rep = []
+        for p in parts:
+            if p.shape[0] != batch:
+                if batch % p.shape[0]:
+                    raise ValueError(f"Cannot duplicate `image` of batch size {p.shape[0]} to {batch} text prompts.")
+                p = torch.cat([p] * (batch // p.shape[0]), dim=0)
+            rep.append(p)
+        shapes = [[img_shapes[0][0]] + [(1, int(h), int(w)) for h, w in grids]] * batch
+        return torch.cat(rep, dim=1), shapes
+
+
 def get_qwen_image_edit_post_process_func(od_config):
+    return get_qwen_image_post_process_func(od_config)
+
+
+def get_qwen_image_edit_plus_post_process_func(od_config):
     return get_qwen_image_post_process_func(od_config)

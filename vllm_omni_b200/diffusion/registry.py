@@ -11,9 +11,11 @@ _DIFFUSION_MODELS = {
     # arch: (mod_folder, mod_relname, cls_name)
     "QwenImagePipeline": ("qwen_image", "pipeline_qwen_image", "QwenImagePipeline"),
     "QwenImageEditPipeline": ("qwen_image", "pipeline_qwen_image_edit", "QwenImageEditPipeline"),
+    "QwenImageEditPlusPipeline": ("qwen_image", "pipeline_qwen_image_edit", "QwenImageEditPlusPipeline"),
 }
 _DIFFUSION_POST_PROCESS_FUNCS = {"QwenImagePipeline": "get_qwen_image_post_process_func",
-                                 "QwenImageEditPipeline": "get_qwen_image_edit_post_process_func"}
+                                 "QwenImageEditPipeline": "get_qwen_image_edit_post_process_func",
+                                 "QwenImageEditPlusPipeline": "get_qwen_image_edit_plus_post_process_func"}
 
 
 class _Registry:

@@ -70,6 +70,55 @@ def shard_request(req: OmniDiffusionRequest, dp_rank: int, dp_size: int):
     return local, counts
 
 
+def batch_key(req: OmniDiffusionRequest):
+    """Requests that can share one denoise batch: same geometry, schedule, CFG setting and text length (the transformer's
+    RoPE needs one text length per batch, and attention carries no mask — padding a shorter prompt would change its
+    result, so only equal lengths are merged), pre-computed embeddings, no condition image, no caller-provided latents."""
+    pe = req.prompt_embeds
+    if not isinstance(pe, torch.Tensor) or req.extra or req.latents is not None or req.generator is not None:
+        return None
+    ne = req.negative_prompt_embeds
+    return (req.height, req.width, req.num_inference_steps, req.true_cfg_scale, tuple(req.sigmas) if req.sigmas is not None else None,
+            req.output_type, pe.shape[1], None if ne is None else ne.shape[1], req.num_outputs_per_prompt)
+
+
+def merge_requests(reqs: list[OmniDiffusionRequest]):
+    """Cross-request batching (the reference leaves it as a TODO and runs reqs[0] only, gpu_worker.py:129-130): requests
+    with the same `batch_key` are concatenated along the prompt axis.  Returns [(merged request, [(index, n_units)])]."""
+    groups: dict = {}
+    order = []
+    for i, r in enumerate(reqs):
+        k = batch_key(r)
+        k = ("solo", i) if k is None else k
+        if k not in groups:
+            groups[k] = []
+            order.append(k)
+        groups[k].append(i)
+    out = []
+    for k in order:
+        idx = groups[k]
+        per = max(int(reqs[idx[0]].num_outputs_per_prompt or 1), 1)
+        if len(idx) == 1:
+            r = reqs[idx[0]]
+            n = (r.prompt_embeds.shape[0] if isinstance(r.prompt_embeds, torch.Tensor) else 1) * per
+            out.append((r, [(idx[0], n)]))
+            continue
+
+        def cat(name):
+            ts = [getattr(reqs[i], name) for i in idx]
+            return None if ts[0] is None else torch.cat(ts, dim=0)
+
+        # per-unit noise: every unit keeps the seed it would have had on its own (seed + local unit index)
+        seeds = None
+        if all(reqs[i].seed is not None for i in idx):
+            seeds = [reqs[i].seed + u for i in idx for u in range(reqs[i].prompt_embeds.shape[0] * per)]
+        merged = dataclasses.replace(reqs[idx[0]], prompt_embeds=cat("prompt_embeds"), negative_prompt_embeds=cat("negative_prompt_embeds"),
+                                     prompt_attention_mask=cat("prompt_attention_mask"), negative_attention_mask=cat("negative_attention_mask"),
+                                     seed=None, extra={"unit_seeds": seeds} if seeds else {})
+        out.append((merged, [(i, reqs[i].prompt_embeds.shape[0] * per) for i in idx]))
+    return out
+
+
 class GPUWorker:
     def __init__(self, local_rank: int, rank: int, od_config: OmniDiffusionConfig):
         self.local_rank, self.rank, self.od_config = local_rank, rank, od_config
@@ -118,12 +167,36 @@ class GPUWorker:
 
     @torch.inference_mode()
     def execute_model(self, reqs: list[OmniDiffusionRequest], od_config: OmniDiffusionConfig) -> DiffusionOutput:
+        """One request (what the reference scheduler sends, scheduler.py:51-72) or a LIST of requests: compatible ones are
+        merged into one denoise batch (`merge_requests`); the output then is the concatenation of the per-request results
+        in request order (`DiffusionOutput.output` [sum units, S_img, 64]; `trajectory_timesteps` carries the unit counts)."""
         assert self.pipeline is not None
         if not reqs:
             raise ValueError("Cannot execute model with empty request list")
-        req = reqs[0]  # one request at a time, as the reference scheduler sends them (scheduler.py:51-72)
+        if len(reqs) == 1:
+            return self._execute_one(reqs[0])
+        results: list = [None] * len(reqs)
+        for merged, parts in merge_requests(list(reqs)):
+            out = self._execute_one(merged)
+            if out.error is not None:
+                return out
+            if out.output is None:  # non-zero DP ranks
+                continue
+            off = 0
+            for i, n in parts:
+                results[i] = out.output[off:off + n]
+                off += n
+        if any(r is None for r in results):
+            return DiffusionOutput(output=None)
+        return DiffusionOutput(output=torch.cat(results, dim=0), trajectory_timesteps=[int(r.shape[0]) for r in results])
+
+    def _execute_one(self, req: OmniDiffusionRequest) -> DiffusionOutput:
         if self.cache_backend is not None and self.cache_backend.is_enabled():  # reference :132-134
             self.cache_backend.refresh(self.pipeline, req.num_inference_steps)
+        if req.extra and req.extra.get("unit_seeds") and req.latents is None:
+            # merged requests: one generator per unit, seeded as the unit's own request would have seeded it
+            gens = [torch.Generator().manual_seed(s) for s in req.extra["unit_seeds"]]
+            req = dataclasses.replace(req, extra={}, latents=self._unit_latents(dataclasses.replace(req, extra={"unit_generators": gens})))
         dp = ps.get_data_parallel_world_size()
         if dp == 1:
             if req.latents is None and req.seed is not None and isinstance(req.prompt_embeds, torch.Tensor):

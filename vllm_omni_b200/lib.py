@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error", "qimg_set_fmha_trace",
     "qimg_engine_forward_stages", "qimg_engine_ws_offset_mod", "qimg_rel_l1_sums", "qimg_bf16_sub", "qimg_bf16_add_inplace",
     "qimg_fmha_joint_mode", "qimg_fmha_overflow", "qimg_cfg_euler_step_dev", "qimg_set_euler_dt_fp32",
-    "qimg_set_nvtx", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
+    "qimg_set_nvtx", "qimg_set_gemm_group_m", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
 ]
 
 
@@ -136,6 +136,7 @@ def load():
     lib.qimg_engine_set_blocks_predicate.argtypes = [vp, vp]
     lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.qimg_set_gemm_mode.argtypes = [i]
+    lib.qimg_set_gemm_group_m.argtypes = [i]
     lib.qimg_set_fmha_mode.argtypes = [i]
     lib.qimg_set_fmha_trace.argtypes = [vp]
     lib.qimg_prof_enable.argtypes = [i]
