@@ -8,7 +8,9 @@
 //     TMEM 512 columns = O (128) | S0 (128) | S1 (128) | P0 (64) | P1 (64)
 // so the chain is broken twice: the scores live in REGISTERS (4 threads per row x 32 columns), the S buffer is handed
 // back right after the TMEM load and QK(j+2) is issued while softmax(j) is still exponentiating; P(j) goes to its own
-// buffer, so nothing waits for P*V either.  Steady state: softmax never waits (XU bound, 128x128 exponentials =
+// buffer, so nothing waits for P*V either.  (v10a loaded the whole score tile before the first exponential: tcgen05.ld
+// moves 64 B/clk per SM, 64 KB = 1024 cycles, serialised in front of 1024 cycles of XU work -> 2300 cycles per tile;
+// v10b reads the scores in 16-column chunks under the exponentials.)  Steady state: softmax never waits (XU bound, 128x128 exponentials =
 // 1024 cycles per KV tile at 16/clk/SM), the tensor pipe runs PV(j), QK(j+2) back to back (2 x 512 cycles) in its shadow.
 // K/V are fetched once per 128 (not 256) query rows: 2x the L2->SM traffic of v9, i.e. ~30 % of the measured L2 peak
 // (v9: 4.7 TB/s = 15 %, profiles/r01_ncu_fmha_v9.csv) — bandwidth that was idle.
@@ -188,31 +190,36 @@ fmha_joint_kernel_v10(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tS0 + b * 128, r);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);  // the scores are in registers: QK(j+2) may overwrite this buffer
+      const uint32_t tS = tS0 + b * 128;
       const int kv_valid = prm.S - j * 128 - cq * 32;  // valid columns of my quarter (< 32 only on a ragged last tile)
       float* my_x = xch + ((j & 1) * 4 + cq) * 128 + row;
       const float* grp_x = xch + (j & 1) * 4 * 128 + row;
       auto softmax_tile = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-        if (MASKED) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i >= kv_valid) r[i] = 0xff800000u;  // -inf
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = max3_f32(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-          mx1 = max3_f32(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-        }
-        const float tile_max = fmaxf(mx0, mx1);
+        // tcgen05.ld moves 64 B/clk per SM: the 64 KB score tile takes ~1024 cycles to read, as long as its exponentials
+        // take on the XU pipe, so the two must overlap — 16 columns at a time, the next load in flight (the first version
+        // of this kernel loaded the whole tile first and ran at 2300 cycles per tile)
+        uint32_t ra[16], rb[16];
+        tmem_ld_32x32b_x16(tS, ra);
+        float tile_max;
         if (j == 0) {
-          // ---- first tile: no reference yet -> the row maximum of this tile (exchange between the four threads) ----
+          // ---- first tile: no reference yet -> the row maximum of this tile first (exchange between the four threads) ----
+          tmem_ld_32x32b_x16(tS + 16, rb);
+          tmem_ld_wait();
+          if (MASKED) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i >= kv_valid) ra[i] = 0xff800000u;
+              if (16 + i >= kv_valid) rb[i] = 0xff800000u;
+            }
+          }
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            mx0 = max3_f32(mx0, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+            mx1 = max3_f32(mx1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+          }
+          tile_max = fmaxf(mx0, mx1);
           *my_x = tile_max;
           named_bar_sync(grp_bar, 128);
           m_ref = fmaxf(fmaxf(grp_x[0], grp_x[128]), fmaxf(grp_x[256], grp_x[384]));
@@ -227,40 +234,67 @@ fmha_joint_kernel_v10(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             tc_fence_after();
             const float f = need ? ex2_approx((m_ref - m_new) * c) : 1.0f;
             l *= f;
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tO, o);
-            tmem_ld_wait();
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(tO + cc * 16, o);
+              tmem_ld_wait();  // (also completes the score chunk load issued above)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st_32x32b_x32(tO, o);
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st_32x32b_x16(tO + cc * 16, o);
+            }
             tmem_st_wait();
             if (need) m_ref = m_new;
           }
         }
-        // ---- exp2((s - m_ref) c) -> bf16 P; the partial row sum stays in fp32 ----
+        // ---- exp2((s - m_ref) c) -> bf16 P, two chunks of 16 columns; the partial row sum stays in fp32 ----
         const uint64_t c2 = splat_f32x2(c), nmc2 = splat_f32x2(-m_ref * c);
         uint64_t la = 0, lb = 0;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
         uint32_t pk[16];
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          const uint64_t x = fma_f32x2(pack_f32x2(r[2 * kk], r[2 * kk + 1]), c2, nmc2);
-          uint64_t p;
-          if ((POLY_MASK >> (kk & 7)) & 1u) {
-            p = exp2_poly_f32x2(x);
-          } else {
-            uint32_t xl, xh;
-            unpack_f32x2(x, xl, xh);
-            p = pack_f32x2(__float_as_uint(ex2_approx(__uint_as_float(xl))), __float_as_uint(ex2_approx(__uint_as_float(xh))));
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t* cur = ch ? rb : ra;
+          if (j > 0) {
+            tmem_ld_wait();
+            if (ch == 0) tmem_ld_32x32b_x16(tS + 16, rb);
+            if (MASKED) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ch * 16 + i >= kv_valid) cur[i] = 0xff800000u;
+            }
           }
-          if (kk & 1) lb = add_f32x2(lb, p); else la = add_f32x2(la, p);
-          uint32_t pl, ph;
-          unpack_f32x2(p, pl, ph);
-          pk[kk] = pack_bf16x2(__uint_as_float(pl), __uint_as_float(ph));
+          if (ch == 1) {  // all my score columns are in registers: QK(j+2) may overwrite this S buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[b]);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            if (j > 0) {
+              if (kk & 1) mx1 = max3_f32(mx1, __uint_as_float(cur[2 * kk]), __uint_as_float(cur[2 * kk + 1]));
+              else mx0 = max3_f32(mx0, __uint_as_float(cur[2 * kk]), __uint_as_float(cur[2 * kk + 1]));
+            }
+            const uint64_t x = fma_f32x2(pack_f32x2(cur[2 * kk], cur[2 * kk + 1]), c2, nmc2);
+            uint64_t p;
+            if ((POLY_MASK >> kk) & 1u) {
+              p = exp2_poly_f32x2(x);
+            } else {
+              uint32_t xl, xh;
+              unpack_f32x2(x, xl, xh);
+              p = pack_f32x2(__float_as_uint(ex2_approx(__uint_as_float(xl))), __float_as_uint(ex2_approx(__uint_as_float(xh))));
+            }
+            if (kk & 1) lb = add_f32x2(lb, p); else la = add_f32x2(la, p);
+            uint32_t pl, ph;
+            unpack_f32x2(p, pl, ph);
+            pk[ch * 8 + kk] = pack_bf16x2(__uint_as_float(pl), __uint_as_float(ph));
+          }
         }
         uint32_t a0, a1, b0, b1;
         unpack_f32x2(la, a0, a1);
         unpack_f32x2(lb, b0, b1);
         l += (__uint_as_float(a0) + __uint_as_float(a1)) + (__uint_as_float(b0) + __uint_as_float(b1));
+        if (j > 0) tile_max = fmaxf(mx0, mx1);
         my_tile_max = (j == 0) ? m_ref : tile_max;
         // guard (see qimg_fmha.cuh): exact while no argument exceeded 2^FMHA_OVF_LOG2, otherwise flag the launch
         if (j > 0 && (tile_max - m_ref) * c > FMHA_OVF_LOG2) *prm.overflow = 1;

@@ -303,7 +303,14 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
   }
   prm.total_tiles = tiles;
   prm.skip = launch_predicate();
-  prm.group_m = pair ? gemm_group_m() : 2 * gemm_group_m();
+  // band height: as tall as the setting allows while the band's A rows (group_m x 256 rows x K) stay L2-resident next to
+  // the streaming weights (<= 56 MB; K = 12288 -> 8 tiles, K = 3072 -> 16): with 16 tiles the MLP-down GEMM re-read its
+  // 100 MB activation band from HBM for every weight column group (2.1 GB per launch, profiles/r02_ncu_summary.md)
+  int maxK = 0;
+  for (int i = 0; i < nprob; ++i) maxK = pr[i].K > maxK ? pr[i].K : maxK;
+  int gm = gemm_group_m();
+  while (gm > 1 && (long long)gm * 256 * maxK * 2 > 56ll * 1024 * 1024) gm /= 2;
+  prm.group_m = pair ? gm : 2 * gm;
   double flops = 0;
   for (int i = 0; i < nprob; ++i) flops += 2.0 * pr[i].M * (double)pr[i].N * pr[i].K;
   ProfScope prof(0, flops, st);
