@@ -61,6 +61,10 @@ int qimg_set_gemm_group_m(int tiles);
  * Env QIMG_FMHA_MODE overrides the default.  (Round 1 shipped seven pipelines; five lost and were deleted.) */
 int qimg_set_fmha_mode(int mode);
 int qimg_get_fmha_mode(void);
+/* Query tiling of the attention grid: 0 = one CTA per PAIR of 128-row query tiles (K/V fetched once per 256 rows),
+ * 1 = one CTA per tile, -1 (default) = per tile while tiles x B x H still fits one wave of SMs (small grids, e.g. the 3
+ * local heads of TP=8 at B=1: 99 half-size CTAs instead of 51 full-size ones), pairs otherwise. */
+int qimg_set_fmha_single_tile(int mode);
 
 /* ---- bandwidth-bound fused ops ------------------------------------------------------ */
 /* y[r,:] = LN(x[r,:]; eps, no affine) * (1 + scale[b,:]) + shift[b,:],  b = r / rows_per_batch.

@@ -52,14 +52,18 @@ def test_library_loaded_and_device():
     assert os.path.exists(q.LIB_PATH)
 
 
-@pytest.fixture(params=[4, 6, 12, 14], ids=["exact", "fast", "exact-poly25", "fast-poly25"])
+@pytest.fixture(params=[(4, 0), (6, 0), (12, 0), (14, 0), (4, 1), (6, 1)],
+                ids=["exact", "fast", "exact-poly25", "fast-poly25", "exact-1tile", "fast-1tile"])
 def fmha_mode(request):
     """Both shipped attention pipelines (exact = per-tile maximum first; fast = running reference maximum + overflow
-    guard), each with and without the 25 % FMA-pipe polynomial share."""
+    guard), with and without the 25 % FMA-pipe polynomial share, and both query tilings (a CTA per pair of query tiles /
+    per single tile — forced here, chosen by grid size in production)."""
     prev = q.get_fmha_mode()
-    q.set_fmha_mode(request.param)
-    yield request.param
+    q.set_fmha_mode(request.param[0])
+    q.set_fmha_single_tile(request.param[1])
+    yield request.param[0]
     q.set_fmha_mode(prev)
+    q.set_fmha_single_tile(-1)
 
 
 def test_umma_probe_all_operand_paths():

@@ -303,14 +303,7 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
   }
   prm.total_tiles = tiles;
   prm.skip = launch_predicate();
-  // band height: as tall as the setting allows while the band's A rows (group_m x 256 rows x K) stay L2-resident next to
-  // the streaming weights (<= 56 MB; K = 12288 -> 8 tiles, K = 3072 -> 16): with 16 tiles the MLP-down GEMM re-read its
-  // 100 MB activation band from HBM for every weight column group (2.1 GB per launch, profiles/r02_ncu_summary.md)
-  int maxK = 0;
-  for (int i = 0; i < nprob; ++i) maxK = pr[i].K > maxK ? pr[i].K : maxK;
-  int gm = gemm_group_m();
-  while (gm > 1 && (long long)gm * 256 * maxK * 2 > 56ll * 1024 * 1024) gm /= 2;
-  prm.group_m = pair ? gm : 2 * gm;
+  prm.group_m = pair ? gemm_group_m() : 2 * gemm_group_m();
   double flops = 0;
   for (int i = 0; i < nprob; ++i) flops += 2.0 * pr[i].M * (double)pr[i].N * pr[i].K;
   ProfScope prof(0, flops, st);
@@ -445,7 +438,7 @@ static int launch_fmha_inst(int pipeline, const CUtensorMap* tq, const CUtensorM
                             const FmhaParams& prm, cudaStream_t st) {
   static bool done7[kMaxDevices] = {}, done9[kMaxDevices] = {};
   const int pairs = (prm.S + 255) / 256;
-  const int grid = pairs * prm.B * prm.H;
+  const int grid = prm.single_tile ? ((prm.S + 127) / 128) * prm.B * prm.H : pairs * prm.B * prm.H;
   if (pipeline == 6) {
     if (ensure_smem_attr(fmha_joint_kernel_v9<MASK>, FMHA4_SMEM_BYTES, done9)) return 1;
     fmha_joint_kernel_v9<MASK><<<grid, FMHA4_THREADS, FMHA4_SMEM_BYTES, st>>>(*tq, *tk, *tv, prm);
@@ -686,6 +679,7 @@ int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_s
 
 // mode = pipeline | (poly << 3): pipeline 6 = fast (delayed reference maximum, guarded by the overflow flag; DEFAULT),
 // pipeline 4 = exact (every tile's maximum reduced first); poly 1 = 25 % of the exponentials on the FMA-pipe polynomial
+static int g_fmha_single_tile = -1;  // -1: auto (one query tile per CTA while that fits one wave)
 static int g_fmha_mode = -1;
 static int fmha_mode() {
   if (g_fmha_mode < 0) {
@@ -702,6 +696,11 @@ int qimg_set_fmha_mode(int mode) {
   return 0;
 }
 int qimg_get_fmha_mode(void) { return fmha_mode(); }
+int qimg_set_fmha_single_tile(int mode) {
+  if (mode < -1 || mode > 1) return fail("qimg_set_fmha_single_tile: -1 (auto), 0 (query-tile pairs) or 1 (one query tile per CTA)");
+  g_fmha_single_tile = mode;
+  return 0;
+}
 
 int qimg_set_fmha_trace(void* dev_buf_32_i64) {
   if (dev_buf_32_i64 && !kFmhaTrace) return fail("qimg_set_fmha_trace: library built without -DQIMG_FMHA_TRACE");
@@ -737,6 +736,10 @@ int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
   prm.trace = g_fmha_trace;
   prm.skip = launch_predicate();
+  {  // one query tile per CTA while that still fits a single wave (halves the critical path of small grids)
+    const int sms = device_sm_count();
+    prm.single_tile = g_fmha_single_tile >= 0 ? g_fmha_single_tile : ((sms > 0 && ((S + 127) / 128) * B * H <= sms) ? 1 : 0);
+  }
   prm.overflow = fmha_overflow_flag();
   if (!prm.overflow) return fail("qimg_fmha_joint: could not allocate the overflow flag");
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);

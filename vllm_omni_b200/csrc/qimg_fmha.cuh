@@ -46,6 +46,8 @@ struct FmhaParams {
   int B, H, S, T;
   float scale_log2;  // softmax_scale * log2(e)
   long long* trace;  // optional (qimg_set_fmha_trace): per-phase cycle counters of CTA 200
+  int single_tile;   // 1: one 128-row query tile per CTA (grid = tiles x B x H) — chosen by the launcher when that still
+                     // fits one wave, e.g. 3 local heads under TP=8: 99 half-size CTAs instead of 51 full-size ones
   const int* skip;   // optional device predicate: non-zero -> exit at once (step-cache reuse)
   int* overflow;     // fast pipeline: set to 1 when a score exceeded the row's reference maximum by > 2^FMHA_OVF_LOG2
 };

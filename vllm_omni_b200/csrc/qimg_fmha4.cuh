@@ -40,10 +40,19 @@ fmha_joint_kernel_v7(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int lane = threadIdx.x & 31;
   if (prm.skip && *prm.skip) return;  // uniform over the grid: nothing allocated or armed yet
   const int n_bh = prm.B * prm.H;
-  const FmhaWork work = fmha_decode_cta(blockIdx.x, prm.S, n_bh);  // head-major, half pairs lagged (qimg_fmha.cuh)
-  const int bh = work.bh, pair_idx = work.pair_idx;
-  const int q_row0 = pair_idx * 256;
-  const bool two = q_row0 + 128 < prm.S;  // is the second query tile (partly) in range?
+  int bh, q_row0;
+  bool two;
+  if (prm.single_tile) {  // one query tile per CTA (the tile-1 softmax warps idle): small grids only
+    const int q_tiles = (prm.S + 127) / 128;
+    bh = blockIdx.x / q_tiles;
+    q_row0 = (blockIdx.x - bh * q_tiles) * 128;
+    two = false;
+  } else {
+    const FmhaWork work = fmha_decode_cta(blockIdx.x, prm.S, n_bh);  // head-major, half pairs lagged (qimg_fmha.cuh)
+    bh = work.bh;
+    q_row0 = work.pair_idx * 256;
+    two = q_row0 + 128 < prm.S;  // is the second query tile (partly) in range?
+  }
   const int n_kv = (prm.S + 127) / 128;
 
   if (warp == 0 && lane == 0) {

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error", "qimg_set_fmha_trace",
     "qimg_engine_forward_stages", "qimg_engine_ws_offset_mod", "qimg_rel_l1_sums", "qimg_bf16_sub", "qimg_bf16_add_inplace",
     "qimg_fmha_joint_mode", "qimg_fmha_overflow", "qimg_cfg_euler_step_dev", "qimg_set_euler_dt_fp32",
-    "qimg_set_nvtx", "qimg_set_gemm_group_m", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
+    "qimg_set_nvtx", "qimg_set_gemm_group_m", "qimg_set_fmha_single_tile", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
 ]
 
 
@@ -138,6 +138,7 @@ def load():
     lib.qimg_set_gemm_mode.argtypes = [i]
     lib.qimg_set_gemm_group_m.argtypes = [i]
     lib.qimg_set_fmha_mode.argtypes = [i]
+    lib.qimg_set_fmha_single_tile.argtypes = [i]
     lib.qimg_set_fmha_trace.argtypes = [vp]
     lib.qimg_prof_enable.argtypes = [i]
     lib.qimg_prof_enable.restype = None
@@ -197,6 +198,11 @@ def get_gemm_mode() -> int:
 
 def set_fmha_mode(mode: int):
     check(load().qimg_set_fmha_mode(int(mode)), "qimg_set_fmha_mode")
+
+
+def set_fmha_single_tile(mode: int):
+    """-1 auto, 0 query-tile pairs per CTA, 1 one query tile per CTA (qimg_set_fmha_single_tile)."""
+    check(load().qimg_set_fmha_single_tile(int(mode)), "qimg_set_fmha_single_tile")
 
 
 def get_fmha_mode() -> int:
