@@ -13,8 +13,10 @@ configs[1]).  N GPUs = data parallel over images (weak scaling, no collective on
            attention kernel and the whole step are reported beside it
   gpu_eager_baseline (N = 1)  SURVEY §8d "GPU reference timing": the reference's eager op sequence (cuBLAS + ATen + the
            SDPA / flash-attn attention backend) on the same weights and inputs, >= 3 warm-up + >= 5 timed forwards
-  tp, cfg_parallel (N > 1)    BASELINE configs[2]: tensor parallel over heads / FFN at B = 1 and B = 4 (fused GEMM +
-           peer-memory reduce-scatter, csrc/qimg_tp_p2p.cu) and CFG parallel, measured after the DP region
+  sp, tp, cfg_parallel (N > 1)    BASELINE configs[2]: one forward split over N GPUs at B = 1 and B = 4 — fused sequence
+           parallelism (Ulysses with the all-to-alls as peer stores of the GEMM / attention epilogues; bit-identical to
+           one GPU), tensor parallelism over heads / FFN (fused GEMM + peer-memory reduce-scatter, csrc/qimg_tp_p2p.cu) —
+           and CFG parallel, measured after the DP region
   cpu_baseline / --impl reference   the reference's CPU torch path (oracle port, see oracle/) on this host's cores
   --sweep  BASELINE configs[4]: batch x resolution grid (profiles/r02_sweep.json)
 
@@ -471,6 +473,48 @@ def multi_gpu_legs(args, dp_pipe, world, rank, local_rank, dev, barrier) -> dict
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    # ---- single-GPU reference for both legs: every rank runs its full replica on the same inputs ----
+    t_half = torch.tensor([0.5], dtype=torch.bfloat16, device=dev)
+    ref = {}
+    for b in (1, 4):
+        lat, txt = (t.to(dev) for t in synthetic.synthetic_inputs(b, res, res, T))
+        denoise(dp_pipe, lat, txt, ns=2)
+        ms_1, lat_1 = cuda_timed(lambda: denoise(dp_pipe, lat, txt), 1, barrier)
+        f_1 = dp_pipe.transformer(lat, txt, None, t_half, [[grid]] * b, [T] * b, return_dict=False, uniform_timestep=True)[0]
+        ref[b] = (lat, txt, max_ms(ms_1), lat_1, f_1.clone())
+
+    def leg(pipe, b, bytes_per_forward):
+        lat, txt, ms_1, lat_1, f_1 = ref[b]
+        denoise(pipe, lat, txt, ns=2)  # warm-up: workspaces, IPC exchange, descriptors
+        ms_p, lat_p = cuda_timed(lambda: denoise(pipe, lat, txt), 1, barrier)
+        ms_p = max_ms(ms_p)
+        f_p = pipe.transformer(lat, txt, None, t_half, [[grid]] * b, [T] * b, return_dict=False, uniform_timestep=True)[0]
+        return {"value": b / (ms_p / 1e3), "unit": UNIT, "ms_per_forward": ms_p / NS, "ms_per_forward_n1": ms_1 / NS,
+                "speedup_vs_n1": ms_1 / ms_p, "rel_fro_vs_single_gpu": rel_fro(f_p, f_1),
+                "bit_identical_to_single_gpu": bool(torch.equal(f_p, f_1)) and bool(torch.equal(lat_p, lat_1)),
+                "rel_fro_vs_single_gpu_50_steps": rel_fro(lat_p, lat_1), "nvlink_bytes_per_forward": bytes_per_forward}
+
+    # ---- fused sequence parallelism (Ulysses), all N ranks in one SP group; the DP replica's own weights ----
+    try:
+        ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=1, ulysses_degree=world)
+        dp_pipe.transformer.enable_sequence_parallel(world, ps.get_sequence_parallel_rank(), ps.get_sp_group())
+        sp = {"sp_size": world,
+              "kernel": "gemm_umma2_kernel<EPI_QKV> stores each head's q/k/v rows into the head owner's buffers, "
+                        "fmha_joint_kernel stores each output row into the row owner's buffer (peer stores over NVLink); "
+                        "all other kernels run on this rank's rows with the full weights"}
+        for b in (1, 4):
+            rows = b * (S_img + T)
+            sp[f"b{b}"] = leg(dp_pipe, b, L * (world - 1) / world * (rows / world) * (3 * D + D) * 2)
+        sp["healthy"] = bool(dp_pipe.transformer.p2p_healthy())
+        out["sp"] = sp
+    except Exception as exc:
+        out["sp"] = {"error": repr(exc)[:400]}
+    try:
+        dp_pipe.transformer.enable_sequence_parallel(1, 0, None)
+    except Exception as exc:
+        out.setdefault("sp", {})["teardown_error"] = repr(exc)[:200]
+    barrier()
+
     # ---- tensor parallel over heads / FFN, all N ranks in one TP group ----
     try:
         ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=world)
@@ -487,21 +531,8 @@ def multi_gpu_legs(args, dp_pipe, world, rank, local_rank, dev, barrier) -> dict
               "kernel": "gemm_umma2_kernel<EPI_PARTIAL_F32> (fp32 partial tiles pushed to the row owners over NVLink) + "
                         "tp_reduce_ln_push_kernel (reduce + bias/gate/residual + next AdaLN + all-gather)"}
         for b in (1, 4):
-            lat, txt = (t.to(dev) for t in synthetic.synthetic_inputs(b, res, res, T))
-            denoise(tp_pipe, lat, txt)  # warm-up: workspaces, IPC exchange, descriptors
-            ms_tp, lat_tp = cuda_timed(lambda: denoise(tp_pipe, lat, txt), 1, barrier)
-            ms_tp = max_ms(ms_tp)
-            denoise(dp_pipe, lat, txt, ns=2)
-            ms_1, lat_1 = cuda_timed(lambda: denoise(dp_pipe, lat, txt), 1, barrier)  # every rank runs its full replica
-            ms_1 = max_ms(ms_1)
-            t = torch.tensor([0.5], dtype=torch.bfloat16, device=dev)
-            f_tp = tp_pipe.transformer(lat, txt, None, t, [[grid]] * b, [T] * b, return_dict=False, uniform_timestep=True)[0]
-            f_1 = dp_pipe.transformer(lat, txt, None, t, [[grid]] * b, [T] * b, return_dict=False, uniform_timestep=True)[0]
             rows = b * (S_img + T)
-            tp[f"b{b}"] = {"value": b / (ms_tp / 1e3), "unit": UNIT, "ms_per_forward": ms_tp / NS, "ms_per_forward_n1": ms_1 / NS,
-                           "speedup_vs_n1": ms_1 / ms_tp, "rel_fro_vs_single_gpu": rel_fro(f_tp, f_1),
-                           "rel_fro_vs_single_gpu_50_steps": rel_fro(lat_tp, lat_1),
-                           "nvlink_bytes_per_forward": 2 * L * (world - 1) / world * rows * D * (4 + 2)}
+            tp[f"b{b}"] = leg(tp_pipe, b, 2 * L * (world - 1) / world * rows * D * (4 + 2))
         tp["healthy"] = bool(tp_pipe.transformer.p2p_healthy()) if tp_pipe.transformer.tp_comm == "p2p" else True
         out["tp"] = tp
         del tp_pipe

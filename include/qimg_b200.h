@@ -73,6 +73,10 @@ int qimg_set_fmha_single_tile(int mode);
  * consecutive batches of shift/scale (0 => one modulation row shared by the whole batch). */
 int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
                      long long mod_stride, float eps, qimg_stream_t stream);
+/* Same on a slice of the stream: x / y point at the slice, row_base is the global index of its first row (selects the
+ * batch's modulation row).  Sequence-parallel engine mode. */
+int qimg_ln_modulate_rows(const void* x, const void* shift, const void* scale, void* y, int rows, int row_base, int D,
+                          int rows_per_batch, long long mod_stride, float eps, qimg_stream_t stream);
 
 /* x[r,:] += gate[b,:] * y[r,:]  — gated residual, qwen_image_transformer.py:586-587,592,597. */
 int qimg_gate_residual(void* x, const void* y, const void* gate, int rows, int D, int rows_per_batch,
@@ -151,6 +155,16 @@ typedef struct qimg_gemm_problem {
    * buffer at index tp_rank).  The reduction itself is qimg_tp_reduce_ln_push. */
   void* tp_recv[8];
   int tp_size, tp_rank, tp_recv_rows, tp_recv_row_off;
+  /* Sequence parallelism: A holds a rank's OWN rows of the stream; row_base is the global index of its first row (batch,
+   * position and gate lookups are done on global rows; `out` / A are addressed with local rows).  With sp_size > 1 the
+   * QIMG_EPI_QKV epilogue stores head h into the q/k/v buffers of the rank that owns the head — sp_q/k/v[h / (H / sp_size)],
+   * local head h % (H / sp_size), each [B, H / sp_size, S_joint, 128] — i.e. the all-to-all in front of Ulysses attention
+   * (reference attention/parallel/ulysses.py:110-112) as peer stores of the GEMM epilogue; q / k / v are then unused. */
+  int row_base;
+  int sp_size;
+  void* sp_q[8];
+  void* sp_k[8];
+  void* sp_v[8];
 } qimg_gemm_problem;
 
 int qimg_gemm(const qimg_gemm_problem* problems, int nprob, int epilogue, qimg_stream_t stream);
@@ -166,6 +180,18 @@ int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, 
  * AttentionImpl plug-in passes 4 (exact): it has no end-of-denoise point at which to consult the overflow flag. */
 int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
                          int T, float softmax_scale, int mode, qimg_stream_t stream);
+/* Sequence-parallel (Ulysses) form: this rank holds H_local heads of q / k / v over ALL S rows (written there by every
+ * rank's QKV epilogue, qimg_gemm_problem.sp_q/k/v) and the output rows are stored straight into the buffers of the ranks
+ * that OWN them: out_img[o] / out_txt[o] = owner o's [own rows, H_local * sp_size * 128] buffers (device pointers valid in
+ * this process); rows of each stream are split contiguously and balanced over the sp_size owners.  The two all-to-alls of
+ * reference attention/parallel/ulysses.py:27-135 become peer stores of the producing kernels. */
+typedef struct qimg_fmha_sp {
+  int sp_size, sp_rank;
+  void* out_img[8];
+  void* out_txt[8];
+} qimg_fmha_sp;
+int qimg_fmha_joint_sp(const void* q, const void* k, const void* v, int B, int H_local, int S, int T, float softmax_scale,
+                       const qimg_fmha_sp* sp, qimg_stream_t stream);
 /* Overflow flag of the fast pipeline on the current device: *out = 1 if any launch since the last reset saw a score more
  * than 2^100 above its row's reference maximum (results of that launch are then not trustworthy).  Synchronising 4-byte
  * read; reset != 0 clears the flag.  Reference semantics being guarded: exact softmax, attention/backends/sdpa.py:56-64. */
@@ -234,6 +260,15 @@ int qimg_ipc_get_handle(const void* dev_ptr, void* handle64);
 int qimg_ipc_open_handle(const void* handle64, void** out);
 int qimg_ipc_close_handle(void* ptr);
 int qimg_engine_set_tp_p2p(qimg_engine* e, int tp_size, int tp_rank, void* const* peer_workspaces, void* const* peer_flags);
+/* Sequence parallelism (the reference's own multi-GPU mode for this model: Ulysses, attention/parallel/ulysses.py:27-135,
+ * `ulysses_degree`), fused: every rank keeps the FULL weights (like a data-parallel replica), runs the LayerNorms and all
+ * four linears of a block on ITS rows only, and attention on ITS heads over all rows.  The two all-to-alls are not separate
+ * collectives: the QKV GEMM epilogue stores each head's q / k / v rows into the head owner's buffers and the attention
+ * epilogue stores each output row into the row owner's buffer (peer stores over NVLink), with one cross-GPU flag barrier
+ * after each.  Per block and rank (P - 1) / P * own rows * (3 D + D) * 2 bytes leave the GPU — about a tenth of the
+ * tensor-parallel mode — and every dot product runs over its full K on one GPU, so the result is BIT-IDENTICAL to the
+ * single-GPU engine.  Same registration protocol as qimg_engine_set_tp_p2p (NULL arrays = declare the mode). */
+int qimg_engine_set_sp_p2p(qimg_engine* e, int sp_size, int sp_rank, void* const* peer_workspaces, void* const* peer_flags);
 int qimg_engine_p2p_error(qimg_engine* e, int* out);
 
 int qimg_engine_create(const qimg_dims* dims, const qimg_global_weights* g, const qimg_block_weights* blocks,

@@ -746,6 +746,17 @@ def test_tp2_matches_single_gpu(comm):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sp2_bit_identical_to_single_gpu():
+    """Fused sequence parallelism (Ulysses: the two all-to-alls as peer stores of the QKV-GEMM / attention epilogues):
+    every dot product runs over its full K on one GPU, so the output must equal the single-GPU engine's BIT FOR BIT —
+    at a ragged resolution too (rows and heads split unevenly over tiles) and on the full-depth reference fixture."""
+    out = _torchrun("tp_check.py", 2, env={"TP_CASES": "sp,2,512,1;sp,3,272,2"})
+    assert out.count("bit-identical: True") == 2, out[-2000:]
+    out = _torchrun("tp_check.py", 2, env={"TP_GOLDEN": "narrow_L60_H8", "TP_COMM": "sp"})
+    assert "criterion (iii) ok" in out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_tp2_full_depth_criterion_iii():
     """Tensor parallel at FULL DEPTH (60 blocks, reference-generated fixture narrow_L60_H8): err(TP, fp32 reference) <=
     err(reference-bf16, fp32 reference) + 1e-2 — the fp32 partial sums of the fused push GEMM add no error of their own."""

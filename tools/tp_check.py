@@ -6,6 +6,9 @@ and times both (CUDA events, max over ranks).
   TP_COMM=p2p   (default) GEMM epilogue pushes fp32 partial tiles to the row owners over NVLink peer memory; one fused
                 kernel reduces, applies bias + gate + residual + the next AdaLN and all-gathers the rows (qimg_tp_p2p.cu)
   TP_COMM=nccl  bf16 partial sums + NCCL all-reduce + epilogue kernel (comparison baseline)
+  TP_COMM=sp    fused SEQUENCE parallelism (Ulysses): full weights per rank, own rows through the linears, own heads through
+                attention, the two all-to-alls as peer stores of the QKV-GEMM / attention epilogues; must be BIT-IDENTICAL
+                to the single-GPU engine
   TP_CASES="comm,L,res,B;..." runs several cases in one launch (overrides TP_COMM / TP_LAYERS / TP_RES / TP_BATCH).
   TP_GOLDEN=<fixture>  instead: the TP engine on a reference-generated fixture (tests/golden/<fixture>.pt), judged by
                 criterion (iii): err(TP, fp32 reference) <= err(reference-bf16, fp32 reference) + 1e-2.  Two bf16 evaluation
@@ -38,15 +41,13 @@ def build(L, dev, **kw):
     return m
 
 
-def golden_check(name, rank, world, dev, comm):
+def golden_check(name, rank, world, dev, comm, par):
     fx = torch.load(os.path.join(ROOT, "tests", "golden", name + ".pt"))
     c = fx["case"]
     torch.set_default_dtype(torch.bfloat16)
     try:
         with torch.device(dev):
-            m = QwenImageTransformer2DModel(num_layers=c["L"], num_attention_heads=c["H"], joint_attention_dim=c["joint"],
-                                            tp_size=world, tp_rank=ps.get_tensor_model_parallel_rank(), tp_group=ps.get_tp_group(),
-                                            tp_comm=comm)
+            m = QwenImageTransformer2DModel(num_layers=c["L"], num_attention_heads=c["H"], joint_attention_dim=c["joint"], **par)
     finally:
         torch.set_default_dtype(torch.float32)
     m.load_weights(synthetic.synthetic_weights(c["L"], seed=c["seed"], norm_jitter=0.1, num_heads=c["H"], joint_dim=c["joint"]))
@@ -83,26 +84,34 @@ def main():
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     torch.cuda.set_device(dev)
     ps.init_distributed_environment(world_size=world, rank=rank, backend="nccl")
-    ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=world, backend="nccl")
+
+    def par_kwargs(comm):
+        """(re)build the process groups for the mode of this case and return the model's parallel kwargs"""
+        if comm == "sp":
+            ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=1, ulysses_degree=world, backend="nccl")
+            return dict(sp_size=world, sp_rank=ps.get_sequence_parallel_rank(), sp_group=ps.get_sp_group())
+        ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=world, backend="nccl")
+        return dict(tp_size=world, tp_rank=ps.get_tensor_model_parallel_rank(), tp_group=ps.get_tp_group(), tp_comm=comm)
     cases = os.environ.get("TP_CASES") or "{},{},{},{}".format(os.environ.get("TP_COMM", "p2p"), os.environ.get("TP_LAYERS", "4"),
                                                                os.environ.get("TP_RES", "512"), os.environ.get("TP_BATCH", "1"))
     tol = float(os.environ.get("TP_TOL", "1e-2"))
     ok = True
     if os.environ.get("TP_GOLDEN"):
-        ok = golden_check(os.environ["TP_GOLDEN"], rank, world, dev, os.environ.get("TP_COMM", "p2p"))
+        comm = os.environ.get("TP_COMM", "p2p")
+        ok = golden_check(os.environ["TP_GOLDEN"], rank, world, dev, comm, par_kwargs(comm))
         dist.barrier()
         ps.destroy_distributed_env()
         sys.exit(0 if ok else 1)
     for case in cases.split(";"):
         comm, L, res, B = case.split(",")
         L, res, B = int(L), int(res), int(B)
-        m = build(L, dev, tp_size=world, tp_rank=ps.get_tensor_model_parallel_rank(), tp_group=ps.get_tp_group(), tp_comm=comm)
+        m = build(L, dev, **par_kwargs(comm))
         lat, txt = synthetic.synthetic_inputs(B, res, res, 128)
         t = torch.tensor([0.5], dtype=torch.bfloat16, device=dev)
         grid = [[(1, res // 16, res // 16)]] * B
         args = (lat.to(dev), txt.to(dev), None, t, grid, [128] * B)
         out_tp, ms_tp = timed(lambda: m(*args, return_dict=False, uniform_timestep=True)[0], 3, dev)
-        if comm == "p2p" and not m.p2p_healthy():
+        if comm in ("p2p", "sp") and not m.p2p_healthy():
             print(f"rank {rank}: peer-memory barrier timed out", flush=True)
             ok = False
         if rank == 0:
@@ -119,11 +128,15 @@ def main():
             ms_1 = e0.elapsed_time(e1) / 3
             err = float((out_tp.float() - out_1.float()).norm() / out_1.float().norm())
             rows, D, P = B * ((res // 16) ** 2 + 128), 3072, world
-            nvl = 2 * L * (P - 1) / P * rows * D * ((4 + 2) if comm == "p2p" else 2 * 2)  # bytes sent per rank per forward
-            print(f"tp_check tp={world} comm={comm} L={L} {res}px B={B}: rel_fro(TP, single GPU) = {err:.3e}; forward {ms_tp:.2f} ms "
+            # bytes sent per rank per forward: TP p2p = fp32 partial push + bf16 row all-gather, twice per block; NCCL ring
+            # all-reduce of bf16 partials; SP = q/k/v of my rows to the other head owners + attention rows back
+            nvl = (L * (P - 1) / P * (rows / P) * (3 * D + D) * 2 if comm == "sp"
+                   else 2 * L * (P - 1) / P * rows * D * ((4 + 2) if comm == "p2p" else 2 * 2))
+            bit = bool(torch.equal(out_tp, out_1))
+            print(f"tp_check tp={world} comm={comm} L={L} {res}px B={B}: rel_fro(TP, single GPU) = {err:.3e} (bit-identical: {bit}); forward {ms_tp:.2f} ms "
                   f"(TP{world}) vs {ms_1:.2f} ms (1 GPU) -> speed-up {ms_1 / ms_tp:.2f}x; NVLink bytes sent per rank per forward "
                   f"{nvl / 1e6:.0f} MB (algorithmic)", flush=True)
-            ok = ok and err <= tol and not torch.isnan(out_tp).any()
+            ok = ok and err <= tol and not torch.isnan(out_tp).any() and (comm != "sp" or bit)
             del m1
         dist.barrier()
         del m

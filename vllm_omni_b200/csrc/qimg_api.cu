@@ -269,6 +269,17 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
     d.nq_w = (const bf16*)s.norm_q_w; d.nk_w = (const bf16*)s.norm_k_w;
     d.cos = (const bf16*)s.rope_cos; d.sin = (const bf16*)s.rope_sin;
     d.S_joint = s.S_joint; d.pos_off = s.pos_off; d.H = s.H; d.eps = s.eps;
+    if (s.row_base < 0) return fail("qimg_gemm: negative row_base");
+    d.row_base = s.row_base;
+    d.sp_size = s.sp_size > 1 ? s.sp_size : 1;
+    if (d.sp_size > 1) {
+      if (epi != QIMG_EPI_QKV) return fail("qimg_gemm: sp_size > 1 is only meaningful with the QKV epilogue");
+      if (d.sp_size > 8 || s.H % d.sp_size) return fail("qimg_gemm: sp_size must divide H and be <= 8");
+      for (int r = 0; r < d.sp_size; ++r) {
+        if (!s.sp_q[r] || !s.sp_k[r] || !s.sp_v[r]) return fail("qimg_gemm: null sp_q / sp_k / sp_v pointer");
+        d.sp_q[r] = (bf16*)s.sp_q[r]; d.sp_k[r] = (bf16*)s.sp_k[r]; d.sp_v[r] = (bf16*)s.sp_v[r];
+      }
+    }
     if (epi == QIMG_EPI_PARTIAL_F32) {
       if (s.tp_size < 1 || s.tp_size > 8 || s.tp_rank < 0 || s.tp_rank >= s.tp_size)
         return fail("qimg_gemm: partial-sum epilogue needs 1 <= tp_size <= 8 and 0 <= tp_rank < tp_size");
@@ -283,7 +294,7 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
     }
     if (epi == QIMG_EPI_QKV) {
       if (s.N != 3 * s.H * 128) return fail("qimg_gemm: QKV epilogue needs N == 3*H*128");
-      if (!s.q || !s.k || !s.v || !s.norm_q_w || !s.norm_k_w || !s.rope_cos || !s.rope_sin)
+      if ((d.sp_size == 1 && (!s.q || !s.k || !s.v)) || !s.norm_q_w || !s.norm_k_w || !s.rope_cos || !s.rope_sin)
         return fail("qimg_gemm: QKV epilogue pointers missing");
     } else if (epi != QIMG_EPI_PARTIAL_F32 && (!s.out || s.ldo % 8)) {
       return fail("qimg_gemm: out missing or ldo not a multiple of 8");
@@ -506,25 +517,31 @@ int qimg_device_check(int* sm_count) {
   return 0;
 }
 
-int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
-                     long long mod_stride, float eps, qimg_stream_t stream) {
+int qimg_ln_modulate_rows(const void* x, const void* shift, const void* scale, void* y, int rows, int row_base, int D,
+                          int rows_per_batch, long long mod_stride, float eps, qimg_stream_t stream) {
   if (rows <= 0) return 0;
   if (D % 8 || D > EW_MAX_CHUNKS * 256) return fail("qimg_ln_modulate: D must be a multiple of 8 and <= 4096");
-  if (rows_per_batch <= 0) return fail("qimg_ln_modulate: rows_per_batch");
+  if (rows_per_batch <= 0 || row_base < 0) return fail("qimg_ln_modulate: rows_per_batch / row_base");
   const dim3 grid((rows + 3) / 4);
   cudaStream_t st = (cudaStream_t)stream;
   const bf16 *xp = (const bf16*)x, *shp = (const bf16*)shift, *scp = (const bf16*)scale;
+  const int* skip = launch_predicate();
   if (D == 3072) {  // Qwen-Image width: compile-time row length
-    ln_modulate_fast_kernel<12><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps, launch_predicate());
+    ln_modulate_fast_kernel<12><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip);
   } else if (D == 1024) {
-    ln_modulate_fast_kernel<4><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps, launch_predicate());
+    ln_modulate_fast_kernel<4><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip);
   } else if (D == 256) {
-    ln_modulate_fast_kernel<1><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, rows_per_batch, mod_stride, eps, launch_predicate());
+    ln_modulate_fast_kernel<1><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip);
   } else {
-    ln_modulate_kernel<<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, D, rows_per_batch, mod_stride, eps, launch_predicate());
+    ln_modulate_kernel<<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, D, rows_per_batch, mod_stride, eps, skip);
   }
   QIMG_LAUNCH_CHECK("ln_modulate_kernel");
   return 0;
+}
+
+int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
+                     long long mod_stride, float eps, qimg_stream_t stream) {
+  return qimg_ln_modulate_rows(x, shift, scale, y, rows, 0, D, rows_per_batch, mod_stride, eps, stream);
 }
 
 int qimg_rms_norm(const void* x, const void* w, void* y, int rows, int D, float eps, qimg_stream_t stream) {
@@ -718,8 +735,8 @@ int qimg_fmha_overflow(int* out, int reset) {
   return 0;
 }
 
-int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
-                         int T, float softmax_scale, int mode, qimg_stream_t stream) {
+static int fmha_launch(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S, int T,
+                       float softmax_scale, int mode, const qimg_fmha_sp* sp, qimg_stream_t stream) {
   if (B <= 0 || H <= 0 || S <= 0 || T < 0 || T > S) return fail("qimg_fmha_joint: bad shape");
   if (mode < 0) mode = fmha_mode();
   const int pipeline = mode & 7;
@@ -730,11 +747,25 @@ int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_
   const CUtensorMap* tv = get_tmap_3d(v, 128, (uint64_t)S, (uint64_t)B * H, 128);
   if (!tq || !tk || !tv) return 1;
   FmhaParams prm;
+  memset(&prm, 0, sizeof prm);
   prm.out_txt = (bf16*)out_txt;
   prm.out_img = (bf16*)out_img;
   prm.B = B; prm.H = H; prm.S = S; prm.T = T;
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;
   prm.trace = g_fmha_trace;
+  prm.sp_size = 1;
+  if (sp && sp->sp_size > 1) {
+    if (sp->sp_size > 8 || sp->sp_rank < 0 || sp->sp_rank >= sp->sp_size) return fail("qimg_fmha_joint_sp: bad sp_size / sp_rank");
+    prm.sp_size = sp->sp_size; prm.sp_rank = sp->sp_rank;
+    prm.sp_rows_img = B * (S - T); prm.sp_rows_txt = B * T;
+    for (int r = 0; r < sp->sp_size; ++r) {
+      if (!sp->out_img[r] || (T > 0 && !sp->out_txt[r])) return fail("qimg_fmha_joint_sp: null owner buffer");
+      prm.sp_out_img[r] = (bf16*)sp->out_img[r];
+      prm.sp_out_txt[r] = (bf16*)sp->out_txt[r];
+    }
+  } else if (!out_img || (T > 0 && !out_txt)) {
+    return fail("qimg_fmha_joint: null output");
+  }
   prm.skip = launch_predicate();
   {  // one query tile per CTA while that still fits a single wave (halves the critical path of small grids)
     const int sms = device_sm_count();
@@ -745,6 +776,17 @@ int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_
   ProfScope prof(1, 4.0 * B * H * (double)S * S * 128, (cudaStream_t)stream);
   if (mode & 8) return launch_fmha_inst<0x11u>(pipeline, tq, tk, tv, prm, (cudaStream_t)stream);
   return launch_fmha_inst<0x00u>(pipeline, tq, tk, tv, prm, (cudaStream_t)stream);
+}
+
+int qimg_fmha_joint_mode(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,
+                         int T, float softmax_scale, int mode, qimg_stream_t stream) {
+  return fmha_launch(q, k, v, out_txt, out_img, B, H, S, T, softmax_scale, mode, nullptr, stream);
+}
+
+int qimg_fmha_joint_sp(const void* q, const void* k, const void* v, int B, int H_local, int S, int T, float softmax_scale,
+                       const qimg_fmha_sp* sp, qimg_stream_t stream) {
+  if (!sp) return fail("qimg_fmha_joint_sp: null descriptor");
+  return fmha_launch(q, k, v, nullptr, nullptr, B, H_local, S, T, softmax_scale, -1, sp, stream);
 }
 
 int qimg_fmha_joint(const void* q, const void* k, const void* v, void* out_txt, void* out_img, int B, int H, int S,

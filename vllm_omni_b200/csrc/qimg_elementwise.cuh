@@ -16,8 +16,8 @@ constexpr int EW_MAX_CHUNKS = 16;  // 16 x 256 = 4096 elements per row max (D=30
 // shift/scale are [*, D] slices of the modulation buffer, row -> batch = row / rows_per_batch.
 __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
                                                           const bf16* __restrict__ scale, bf16* __restrict__ y, int rows,
-                                                          int D, int rows_per_batch, long long mod_stride, float eps,
-                                                          const int* __restrict__ skip) {
+                                                          int row_base, int D, int rows_per_batch, long long mod_stride,
+                                                          float eps, const int* __restrict__ skip) {
   if (skip && *skip) return;  // step cache: this forward reuses the cached residual (qimg_tea_decide)
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
   const float nmr = -mean * rstd;
-  const int b = row / rows_per_batch;
+  const int b = (row_base + row) / rows_per_batch;
   const bf16* sh = shift + (size_t)b * mod_stride;
   const bf16* sc = scale + (size_t)b * mod_stride;
   bf16* yr = y + (size_t)row * D;
@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
 template <int NCH>
 __global__ void __launch_bounds__(128) ln_modulate_fast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
                                                                const bf16* __restrict__ scale, bf16* __restrict__ y,
-                                                               int rows, int rows_per_batch, long long mod_stride,
-                                                               float eps, const int* __restrict__ skip) {
+                                                               int rows, int row_base, int rows_per_batch,
+                                                               long long mod_stride, float eps,
+                                                               const int* __restrict__ skip) {
   if (skip && *skip) return;
   constexpr int D = NCH * 256;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(128) ln_modulate_fast_kernel(const bf16* __res
   }
   const float rstd = rsqrtf(warp_sum(ew_hsum2(ew_add2(q0, q1))) * (1.0f / (float)D) + eps);
   const uint64_t rstd2 = ew_splat2(rstd), zero2 = 0;
-  const int b = row / rows_per_batch;
+  const int b = (row_base + row) / rows_per_batch;
   const bf16* sh = shift + (size_t)b * mod_stride + lane * 8;
   const bf16* sc = scale + (size_t)b * mod_stride + lane * 8;
   bf16* yr = y + (size_t)row * D + lane * 8;

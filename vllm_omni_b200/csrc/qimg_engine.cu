@@ -28,6 +28,9 @@ struct qimg_engine {
   void* allreduce_user = nullptr;
   // peer-memory TP (qimg_engine_set_tp_p2p): every rank's workspace and barrier flags, mapped into this process
   bool p2p = false;
+  // sequence parallelism (qimg_engine_set_sp_p2p): full weights, own rows through the linears, local heads through attention
+  int sp_size = 1;
+  int sp_rank = 0;
   const int* blocks_predicate = nullptr;  // qimg_engine_set_blocks_predicate
   bool p2p_ready = false;  // peer pointers registered (qimg_engine_set_tp_p2p with non-NULL arrays)
   int tp_rank = 0;
@@ -64,12 +67,14 @@ inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; 
 
 struct WsLayout {
   size_t x_img, x_txt, xm_img, xm_txt, q, k, v, at_img, at_txt, h_img, h_txt, txt_normed, tsin, t1, temb, mod_all, emb_out,
-      part, zero_bias, recv, total;
+      part, zero_bias, recv, out_own, out_all, total;
   int own_img, own_txt;  // peer-memory TP: largest owner slice of the image / text rows
 };
 
 // tp > 1: head-sharded q/k/v/attention-output and FF-sharded MLP hidden buffers are 1/tp of the full size
-WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max, int tp = 1, bool p2p = false) {
+// sp > 1 (sequence parallel): same head split for q/k/v; attention output and MLP hidden hold OWN rows at full width
+WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max, int tp = 1, bool p2p = false, int sp = 1) {
+  if (sp > 1) tp = sp;
   const size_t D = (size_t)d.num_heads * d.head_dim, FF = 4 * D, S = (size_t)S_img + T;
   const size_t Mi = (size_t)B * S_img, Mt = (size_t)B * T;
   const size_t Hl = (size_t)d.num_heads / tp, Dl = D / tp, FFl = FF / tp;
@@ -87,23 +92,26 @@ WsLayout ws_layout(const qimg_dims& d, int B, int S_img, int T, int n_t_max, int
   w.q = take((size_t)B * Hl * S * 128);
   w.k = take((size_t)B * Hl * S * 128);
   w.v = take((size_t)B * Hl * S * 128);
-  w.at_img = take(Mi * Dl);
-  w.at_txt = take(Mt * Dl);
-  w.h_img = take(Mi * FFl);
-  w.h_txt = take(Mt * FFl);
+  const size_t oi = (Mi + tp - 1) / tp, ot = (Mt + tp - 1) / tp;  // largest owner slice (sequence parallel)
+  w.at_img = take(sp > 1 ? oi * D : Mi * Dl);
+  w.at_txt = take(sp > 1 ? ot * D : Mt * Dl);
+  w.h_img = take(sp > 1 ? oi * FF : Mi * FFl);
+  w.h_txt = take(sp > 1 ? ot * FF : Mt * FFl);
   w.txt_normed = take(Mt * d.joint_dim);
   w.tsin = take((size_t)n_t_max * 256);
   w.t1 = take((size_t)n_t_max * D);
   w.temb = take((size_t)n_t_max * D);
   w.mod_all = take((size_t)n_t_max * d.num_layers * 12 * D);
   w.emb_out = take((size_t)n_t_max * 2 * D);
-  const bool nccl_tp = tp > 1 && !p2p;
+  const bool nccl_tp = tp > 1 && !p2p && sp <= 1;
   w.part = take(nccl_tp ? (Mi + Mt) * D : 0);  // NCCL mode: [img rows | txt rows] x D bf16 partial sums of the row-parallel linears
   w.zero_bias = take(nccl_tp ? D : 0);
   // peer-memory mode: fp32 partial sums of MY rows from every source rank, [tp][own_img + own_txt][D]
   w.own_img = tp > 1 ? (int)((Mi + tp - 1) / tp) : 0;
   w.own_txt = tp > 1 ? (int)((Mt + tp - 1) / tp) : 0;
-  w.recv = take((tp > 1 && p2p) ? (size_t)tp * (w.own_img + w.own_txt) * D * 2 : 0);
+  w.recv = take((tp > 1 && p2p && sp <= 1) ? (size_t)tp * (w.own_img + w.own_txt) * D * 2 : 0);
+  w.out_own = take(sp > 1 ? oi * d.out_dim : 0);   // sequence parallel: proj_out of my rows ...
+  w.out_all = take(sp > 1 ? Mi * d.out_dim : 0);   // ... and every rank's rows, pushed by their owners
   w.total = off;
   return w;
 }
@@ -169,17 +177,39 @@ int qimg_engine_set_tp_p2p(qimg_engine* e, int tp_size, int tp_rank, void* const
   return 0;
 }
 
+int qimg_engine_set_sp_p2p(qimg_engine* e, int sp_size, int sp_rank, void* const* peer_workspaces, void* const* peer_flags) {
+  if (!e) return fail("qimg_engine_set_sp_p2p: null engine");
+  if (sp_size != 2 && sp_size != 4 && sp_size != 8) return fail("qimg_engine_set_sp_p2p: sp_size must be 2, 4 or 8");
+  if (e->dims.num_heads % sp_size) return fail("qimg_engine_set_sp_p2p: sp_size must divide num_heads");
+  if (sp_rank < 0 || sp_rank >= sp_size) return fail("qimg_engine_set_sp_p2p: bad rank");
+  if (e->tp_size > 1) return fail("qimg_engine_set_sp_p2p: the engine is already tensor parallel");
+  if ((peer_workspaces == nullptr) != (peer_flags == nullptr)) return fail("qimg_engine_set_sp_p2p: pass both pointer arrays or neither");
+  e->p2p_ready = false;
+  if (peer_workspaces) {
+    for (int p = 0; p < sp_size; ++p) {
+      if (!peer_workspaces[p] || !peer_flags[p]) return fail("qimg_engine_set_sp_p2p: null peer pointer");
+      e->peer_ws[p] = peer_workspaces[p];
+      e->peer_flags[p] = peer_flags[p];
+    }
+    e->p2p_ready = true;
+  }
+  e->sp_size = sp_size;
+  e->sp_rank = sp_rank;
+  e->tp_rank = sp_rank;  // barrier / error plumbing shared with the TP mode
+  return 0;
+}
+
 int qimg_engine_p2p_error(qimg_engine* e, int* out) {
-  if (!e || !e->p2p || !e->p2p_ready || !out) return fail("qimg_engine_p2p_error: engine is not in peer-memory TP mode");
+  if (!e || !(e->p2p || e->sp_size > 1) || !e->p2p_ready || !out) return fail("qimg_engine_p2p_error: engine is not in a peer-memory mode");
   QIMG_CUDA_CHECK(cudaMemcpy(out, (char*)e->peer_flags[e->tp_rank] + 64, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 
 size_t qimg_engine_workspace_bytes(const qimg_engine* e, int B, int S_img, int T) {
-  return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p).total;
+  return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p, e->sp_size).total;
 }
-size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p).x_img; }
-size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p).x_txt; }
+size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p, e->sp_size).x_img; }
+size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p, e->sp_size).x_txt; }
 
 #define QIMG_TRY(expr)      \
   do {                      \
@@ -194,7 +224,7 @@ int qimg_engine_forward(qimg_engine* e, const void* hidden, const void* enc, con
                                     out, workspace, workspace_bytes, st);
 }
 
-size_t qimg_engine_ws_offset_mod(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p).xm_img; }
+size_t qimg_engine_ws_offset_mod(const qimg_engine* e, int B, int S_img, int T) { return ws_layout(e->dims, B, S_img, T, B, e->tp_size, e->p2p, e->sp_size).xm_img; }
 
 int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, const void* enc, const void* timestep, int n_t,
                                const void* img_cos, const void* img_sin, const void* txt_cos, const void* txt_sin, int B,
@@ -205,7 +235,7 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
   if (n_t != 1 && n_t != B) return fail("qimg_engine_forward: n_t must be 1 or B");
   const qimg_dims& d = e->dims;
   const int tp = e->tp_size;
-  const WsLayout w = ws_layout(d, B, S_img, T, B, tp, e->p2p);
+  const WsLayout w = ws_layout(d, B, S_img, T, B, tp, e->p2p, e->sp_size);
   if (workspace_bytes < w.total) return fail("qimg_engine_forward: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail("qimg_engine_forward: workspace must be 1024-byte aligned");
   char* ws = static_cast<char*>(workspace);
@@ -214,6 +244,12 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
   void *part = ws + w.part, *zero_bias = ws + w.zero_bias;
   char* part_txt = (char*)part + (size_t)B * S_img * D * 2;
   if (tp > 1 && !e->p2p) QIMG_CUDA_CHECK(cudaMemsetAsync(zero_bias, 0, (size_t)D * 2, (cudaStream_t)st));
+  const int sp = e->sp_size;
+  if (sp > 1) {
+    if (!e->p2p_ready) return fail("qimg_engine_forward: sequence parallelism declared but no peer workspaces registered");
+    if (workspace != e->peer_ws[e->sp_rank]) return fail("qimg_engine_forward: sequence parallelism needs the registered workspace");
+    if (stages != QIMG_STAGE_ALL) return fail("qimg_engine_forward_stages: staged forwards are not available under sequence parallelism");
+  }
   if (e->p2p) {
     if (!e->p2p_ready) return fail("qimg_engine_forward: peer-memory TP declared but no peer workspaces registered");
     if (workspace != e->peer_ws[e->tp_rank]) return fail("qimg_engine_forward: peer-memory TP needs the registered workspace");
@@ -305,6 +341,114 @@ int qimg_engine_forward_stages(qimg_engine* e, int stages, const void* hidden, c
     QIMG_TRY(qimg_ln_modulate(x_img, mi0, mi0 + (size_t)D * 2, xm_img, Mi, D, S_img, mod_stride, d.eps, st));
   }
   }  // QIMG_STAGE_PRE
+
+  // ---- sequence parallel (Ulysses, fused): own rows through every linear with the FULL weights, local heads through
+  //      attention; the two all-to-alls are peer stores of the QKV-GEMM and attention epilogues -----------------------------
+  if (sp > 1) {
+    const int r = e->sp_rank;
+    auto own = [&](int rows, int* r0, int* n) {
+      const int base = rows / sp, extra = rows % sp;
+      *r0 = r * base + (r < extra ? r : extra);
+      *n = base + (r < extra ? 1 : 0);
+    };
+    int i0, ni, t0, nt;
+    own(Mi, &i0, &ni);
+    own(Mt, &t0, &nt);
+    const int Hs = H / sp;
+    auto rows_at = [&](void* base, int row0, int width) { return (void*)((char*)base + (size_t)row0 * width * 2); };
+    void *xi = rows_at(x_img, i0, D), *xt = rows_at(x_txt, t0, D), *xmi = rows_at(xm_img, i0, D), *xmt = rows_at(xm_txt, t0, D);
+    const float sm_scale_sp = 1.0f / sqrtf(128.0f);
+    for (int l = 0; l < L; ++l) {
+      QIMG_RANGE("qimg.block (sequence parallel)");
+      const qimg_block_weights& bw = e->blocks[l];
+      const char* mi = mod_all + ((size_t)l * 12 * D) * 2;
+      const char* mt = mi + (size_t)6 * D * 2;
+      auto seg = [&](const char* base, int i) { return (const void*)(base + (size_t)i * D * 2); };
+      QIMG_TRY(qimg_ln_modulate_rows(xi, seg(mi, 0), seg(mi, 1), xmi, ni, i0, D, S_img, mod_stride, d.eps, st));
+      QIMG_TRY(qimg_ln_modulate_rows(xt, seg(mt, 0), seg(mt, 1), xmt, nt, t0, D, T, mod_stride, d.eps, st));
+      {  // QKV of MY rows for ALL heads; each head's rows land in its owner's joint q / k / v (all-to-all #1)
+        qimg_gemm_problem p[2];
+        memset(p, 0, sizeof p);
+        p[0].A = xmi; p[0].W = bw.to_qkv_w; p[0].bias = bw.to_qkv_b; p[0].M = ni; p[0].N = 3 * D; p[0].K = D;
+        p[0].rows_per_batch = S_img; p[0].row_base = i0; p[0].norm_q_w = bw.norm_q; p[0].norm_k_w = bw.norm_k;
+        p[0].rope_cos = img_cos; p[0].rope_sin = img_sin; p[0].S_joint = S; p[0].pos_off = T; p[0].H = H; p[0].eps = d.eps;
+        p[0].sp_size = sp;
+        for (int o = 0; o < sp; ++o) {
+          p[0].sp_q[o] = (char*)e->peer_ws[o] + w.q; p[0].sp_k[o] = (char*)e->peer_ws[o] + w.k; p[0].sp_v[o] = (char*)e->peer_ws[o] + w.v;
+        }
+        p[1] = p[0];
+        p[1].A = xmt; p[1].W = bw.add_kv_w; p[1].bias = bw.add_kv_b; p[1].M = nt; p[1].rows_per_batch = T; p[1].row_base = t0;
+        p[1].norm_q_w = bw.norm_added_q; p[1].norm_k_w = bw.norm_added_k; p[1].rope_cos = txt_cos; p[1].rope_sin = txt_sin;
+        p[1].pos_off = 0;
+        if (nt > 0) QIMG_TRY(qimg_gemm(p, 2, QIMG_EPI_QKV, st));
+        else QIMG_TRY(qimg_gemm(p, 1, QIMG_EPI_QKV, st));
+      }
+      QIMG_TRY(tp_p2p_barrier(e->peer_flags, sp, r, (cudaStream_t)st));  // every rank's q / k / v rows have landed
+      {  // attention over my heads, all rows; output rows go to their owners' at buffers (all-to-all #2)
+        qimg_fmha_sp fs;
+        memset(&fs, 0, sizeof fs);
+        fs.sp_size = sp; fs.sp_rank = r;
+        for (int o = 0; o < sp; ++o) {
+          fs.out_img[o] = (char*)e->peer_ws[o] + w.at_img;
+          fs.out_txt[o] = (char*)e->peer_ws[o] + w.at_txt;
+        }
+        QIMG_TRY(qimg_fmha_joint_sp(q, k, v, B, Hs, S, T, sm_scale_sp, &fs, st));
+      }
+      QIMG_TRY(tp_p2p_barrier(e->peer_flags, sp, r, (cudaStream_t)st));  // every head's contribution to my rows has landed
+      auto own_problem = [&](qimg_gemm_problem& p, const void* A, const void* W, const void* bias, int M, int N, int K, int rpb,
+                             int row_base) {
+        p.A = A; p.W = W; p.bias = bias; p.M = M; p.N = N; p.K = K; p.rows_per_batch = rpb; p.row_base = row_base;
+      };
+      {
+        qimg_gemm_problem p[2];
+        memset(p, 0, sizeof p);
+        own_problem(p[0], at_img, bw.to_out_w, bw.to_out_b, ni, D, D, S_img, i0);
+        p[0].out = xi; p[0].ldo = D; p[0].gate = seg(mi, 2); p[0].gate_stride = mod_stride;
+        own_problem(p[1], at_txt, bw.to_add_out_w, bw.to_add_out_b, nt, D, D, T, t0);
+        p[1].out = xt; p[1].ldo = D; p[1].gate = seg(mt, 2); p[1].gate_stride = mod_stride;
+        QIMG_TRY(qimg_gemm(p, nt > 0 ? 2 : 1, QIMG_EPI_BIAS_GATE_RES, st));
+      }
+      QIMG_TRY(qimg_ln_modulate_rows(xi, seg(mi, 3), seg(mi, 4), xmi, ni, i0, D, S_img, mod_stride, d.eps, st));
+      QIMG_TRY(qimg_ln_modulate_rows(xt, seg(mt, 3), seg(mt, 4), xmt, nt, t0, D, T, mod_stride, d.eps, st));
+      {
+        qimg_gemm_problem p[2];
+        memset(p, 0, sizeof p);
+        own_problem(p[0], xmi, bw.img_mlp_w1, bw.img_mlp_b1, ni, FF, D, S_img, i0);
+        p[0].out = h_img; p[0].ldo = FF;
+        own_problem(p[1], xmt, bw.txt_mlp_w1, bw.txt_mlp_b1, nt, FF, D, T, t0);
+        p[1].out = h_txt; p[1].ldo = FF;
+        QIMG_TRY(qimg_gemm(p, nt > 0 ? 2 : 1, QIMG_EPI_BIAS_GELU, st));
+      }
+      {
+        qimg_gemm_problem p[2];
+        memset(p, 0, sizeof p);
+        own_problem(p[0], h_img, bw.img_mlp_w2, bw.img_mlp_b2, ni, D, FF, S_img, i0);
+        p[0].out = xi; p[0].ldo = D; p[0].gate = seg(mi, 5); p[0].gate_stride = mod_stride;
+        own_problem(p[1], h_txt, bw.txt_mlp_w2, bw.txt_mlp_b2, nt, D, FF, T, t0);
+        p[1].out = xt; p[1].ldo = D; p[1].gate = seg(mt, 5); p[1].gate_stride = mod_stride;
+        QIMG_TRY(qimg_gemm(p, nt > 0 ? 2 : 1, QIMG_EPI_BIAS_GATE_RES, st));
+      }
+    }
+    // epilogue on my rows; the [rows, out_dim] result (0.5 MB per image) is all-gathered into every rank's workspace
+    QIMG_TRY(qimg_ln_modulate_rows(xi, (const char*)emb_out + (size_t)D * 2, emb_out, xmi, ni, i0, D, S_img, emb_stride, d.eps, st));
+    {
+      qimg_gemm_problem p;
+      memset(&p, 0, sizeof p);
+      p.A = xmi; p.W = e->g.proj_out_w; p.bias = e->g.proj_out_b; p.M = ni; p.N = d.out_dim; p.K = D;
+      p.rows_per_batch = S_img; p.row_base = i0; p.out = ws + w.out_own; p.ldo = d.out_dim;
+      QIMG_TRY(qimg_gemm(&p, 1, QIMG_EPI_BIAS, st));
+    }
+    {
+      void* dst[8];
+      for (int o = 0; o < sp; ++o) dst[o] = (char*)e->peer_ws[o] + w.out_all + (size_t)i0 * d.out_dim * 2;
+      QIMG_TRY(tp_p2p_push_rows(ws + w.out_own, dst, (long long)ni * d.out_dim, sp, (cudaStream_t)st));
+    }
+    QIMG_TRY(tp_p2p_barrier(e->peer_flags, sp, r, (cudaStream_t)st));
+    QIMG_CUDA_CHECK(cudaMemcpyAsync(out, ws + w.out_all, (size_t)Mi * d.out_dim * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)st));
+    // the next forward's first pushes (q / k / v of block 0) must not overtake a peer still copying out_all: it reads only
+    // its OWN workspace there, and nobody writes out_all before the next forward's final push, which lies behind 2 L barriers
+    return 0;
+  }
 
   // ---- 60 dual-stream blocks -----------------------------------------------------------------
   const float sm_scale = 1.0f / sqrtf(128.0f);

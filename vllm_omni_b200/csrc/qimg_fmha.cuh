@@ -46,6 +46,12 @@ struct FmhaParams {
   int B, H, S, T;
   float scale_log2;  // softmax_scale * log2(e)
   long long* trace;  // optional (qimg_set_fmha_trace): per-phase cycle counters of CTA 200
+  // sequence parallelism (Ulysses): this rank computed H LOCAL heads over ALL rows; output rows go to the rank that owns
+  // them — the all-to-all behind the attention (reference attention/parallel/ulysses.py:135) as peer stores of the epilogue.
+  // sp_out_img/txt[o]: owner o's [own rows, H * sp_size * 128] buffers; rows are split balanced over sp_size owners.
+  int sp_size, sp_rank, sp_rows_img, sp_rows_txt;
+  bf16* sp_out_img[8];
+  bf16* sp_out_txt[8];
   int single_tile;   // 1: one 128-row query tile per CTA (grid = tiles x B x H) — chosen by the launcher when that still
                      // fits one wave, e.g. 3 local heads under TP=8: 99 half-size CTAs instead of 51 full-size ones
   const int* skip;   // optional device predicate: non-zero -> exit at once (step-cache reuse)
@@ -115,6 +121,31 @@ __device__ __forceinline__ uint64_t exp2_poly_f32x2(uint64_t x) {
   unpack_f32x2(p, pl, ph);
   unpack_f32x2(t, tl, th);
   return pack_f32x2(pl + (tl << 23), ph + (th << 23));
+}
+
+// Destination of the 16-byte chunk c16 of output row (batch b, joint position pos, local head h).
+__device__ __forceinline__ bf16* fmha_out_ptr(const FmhaParams& prm, int b, int h, int pos, int c16) {
+  const int S_img = prm.S - prm.T;
+  const bool txt = pos < prm.T;
+  if (prm.sp_size <= 1) {
+    const int D = prm.H * 128;
+    bf16* row = txt ? prm.out_txt + ((size_t)b * prm.T + pos) * D : prm.out_img + ((size_t)b * S_img + (pos - prm.T)) * D;
+    return row + h * 128 + c16 * 8;
+  }
+  const int m = txt ? b * prm.T + pos : b * S_img + (pos - prm.T);  // global row of its stream
+  const int M = txt ? prm.sp_rows_txt : prm.sp_rows_img;
+  const int base = M / prm.sp_size, extra = M % prm.sp_size, cut = extra * (base + 1);
+  int o, li;
+  if (m < cut) {
+    o = m / (base + 1);
+    li = m - o * (base + 1);
+  } else {
+    o = extra + (m - cut) / base;
+    li = (m - cut) - (o - extra) * base;
+  }
+  const int Dtot = prm.H * prm.sp_size * 128;
+  bf16* buf = txt ? prm.sp_out_txt[o] : prm.sp_out_img[o];
+  return buf + (size_t)li * Dtot + (prm.sp_rank * prm.H + h) * 128 + c16 * 8;
 }
 
 // CTA -> (batch*head, query-tile pair).  S = 4224 gives 16 full pairs + 1 "half" pair (second tile beyond S) per head.

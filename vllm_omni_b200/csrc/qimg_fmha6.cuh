@@ -397,8 +397,6 @@ fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     named_bar_sync(pair_bar, 64);  // both halves of my 32 rows are staged
     const int b = bh / prm.H, h = bh - b * prm.H;
-    const int D = prm.H * 128;
-    const int S_img = prm.S - prm.T;
 #pragma unroll 1
     for (int it = 0; it < 8; ++it) {  // this warp stores 16 of the pair's 32 rows
       const int rr = q * 32 + hh * 16 + it * 2 + (lane >> 4);
@@ -406,9 +404,7 @@ fmha_joint_kernel_v9(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int pos = q_row0 + t * 128 + rr;
       if (pos < prm.S) {
         const uint4 v = lds_v4(stg + rr * 256 + ((c16 ^ (rr & 7)) << 4));
-        bf16* dst = (pos < prm.T) ? prm.out_txt + ((size_t)b * prm.T + pos) * D
-                                  : prm.out_img + ((size_t)b * S_img + (pos - prm.T)) * D;
-        stg_v4(dst + h * 128 + c16 * 8, v);
+        stg_v4(fmha_out_ptr(prm, b, h, pos, c16), v);  // local buffer, or the row owner's over NVLink (sequence parallel)
       }
     }
     }  // active tile

@@ -52,6 +52,15 @@ struct GemmProblem {
   // keeps the rows of source rank s at tp_recv[o] + ((s * tp_recv_rows + tp_recv_row_off + local_row) * N) floats.
   float* tp_recv[8];
   int tp_size, tp_rank, tp_recv_rows, tp_recv_row_off;
+  // Sequence parallelism (rows of A are a rank's OWN slice of the stream): row_base = global index of local row 0 (batch /
+  // position / gate lookups use global rows).  EPI_QKV with sp_size > 1: head h goes to the rank that owns it,
+  // sp_q/k/v[h / H_local] with the local head index h % H_local (H_local = H / sp_size) — the all-to-all in front of
+  // Ulysses attention (reference attention/parallel/ulysses.py:110-112), fused into the GEMM epilogue as peer stores.
+  int row_base;
+  int sp_size;
+  bf16* sp_q[8];
+  bf16* sp_k[8];
+  bf16* sp_v[8];
   // tile bookkeeping (filled by the host launcher)
   int m_tiles, n_tiles, tile_begin;
 };
@@ -168,9 +177,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& P, int m_blk, i
 
   // batch / in-batch index of the first row of this warp's 32-row slab: one division per tile, rows
   // then advance incrementally (no per-row integer division in the store loops)
-  const int slab_m0 = m_blk * GEMM_BM + q * 32;
-  const int slab_b0 = slab_m0 / P.rows_per_batch;
-  const int slab_i0 = slab_m0 - slab_b0 * P.rows_per_batch;
+  const int slab_m0 = m_blk * GEMM_BM + q * 32;  // local row (addresses); + row_base = global row (batch, position)
+  const int slab_b0 = (P.row_base + slab_m0) / P.rows_per_batch;
+  const int slab_i0 = (P.row_base + slab_m0) - slab_b0 * P.rows_per_batch;
   float rstd = 0.f;
   const bf16* cos_row = nullptr;
   const bf16* sin_row = nullptr;
@@ -341,8 +350,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmProblem& P, int m_blk, i
             i -= P.rows_per_batch;
             ++b;
           }
-          const size_t off = (((size_t)b * P.H + head) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
-          stg_v4(base + off, yv[it]);
+          if (P.sp_size > 1) {  // sequence parallel: the head's owner holds heads [o * Hl, (o + 1) * Hl) as local heads
+            const int Hl = P.H / P.sp_size, o = head / Hl;
+            bf16* pb = (which == 0) ? P.sp_q[o] : (which == 1 ? P.sp_k[o] : P.sp_v[o]);
+            const size_t off = (((size_t)b * Hl + (head - o * Hl)) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
+            stg_v4(pb + off, yv[it]);
+          } else {
+            const size_t off = (((size_t)b * P.H + head) * P.S_joint + (P.pos_off + i)) * 128 + half * 64 + c16 * 8;
+            stg_v4(base + off, yv[it]);
+          }
         }
       }
     }

@@ -24,5 +24,7 @@ struct TpReduceArgs {
 
 int tp_p2p_barrier(void* const* flags, int P, int rank, cudaStream_t st);
 int tp_p2p_reduce_ln_push(const TpReduceArgs& a, cudaStream_t st);
+// copy n bf16 elements (n % 8 == 0) from a local buffer to P destinations (own and peers'): a small all-gather
+int tp_p2p_push_rows(const void* src, void* const* dst, long long n, int P, cudaStream_t st);
 
 }  // namespace qimg

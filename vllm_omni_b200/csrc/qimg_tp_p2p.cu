@@ -217,6 +217,27 @@ int tp_p2p_reduce_ln_push(const TpReduceArgs& a, cudaStream_t st) {
   return fail("tp_reduce_ln_push: tp_size must be 2, 4 or 8");
 }
 
+__global__ void __launch_bounds__(256) tp_push_rows_kernel(const bf16* __restrict__ src, PeerPtrs dst, long long n_vec, int P) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const uint4 v = ldg_nc_v4(src + i * 8);
+    for (int p = 0; p < P; ++p) stg_v4(reinterpret_cast<bf16*>(dst.p[p]) + i * 8, v);
+  }
+}
+
+int tp_p2p_push_rows(const void* src, void* const* dst, long long n, int P, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n % 8) return fail("tp_p2p_push_rows: element count must be a multiple of 8");
+  PeerPtrs d;
+  memset(&d, 0, sizeof d);
+  for (int p = 0; p < P; ++p) d.p[p] = dst[p];
+  long long blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  tp_push_rows_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)src, d, n / 8, P);
+  QIMG_LAUNCH_CHECK("tp_push_rows_kernel");
+  return 0;
+}
+
 int tp_p2p_barrier(void* const* flags, int P, int rank, cudaStream_t st) {
   PeerPtrs f;
   memset(&f, 0, sizeof f);

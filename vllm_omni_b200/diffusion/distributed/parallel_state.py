@@ -6,6 +6,9 @@ reference's "tp-sp-pp-cfg-dp" string (:659): TP ranks are adjacent, DP is the ou
   * DP (data parallel over images): independent units, NO collective on the data path; only the final
     gather of the [B/P, S_img, 64] latents to rank 0.  Not wired in the reference (groups only, :661-668).
   * TP group: kept for the tensor-parallel engine mode (all-reduce of row-parallel partial sums).
+  * SP group (`ulysses_degree`, the reference's own multi-GPU mode for this model, attention/parallel/ulysses.py): ranks that
+    split the ROWS of one forward between them (fused sequence parallelism: full weights per rank, the two all-to-alls of
+    Ulysses are peer stores of the QKV-GEMM / attention epilogues; no collective call on the data path).
   * CFG group (size 1 or 2): with true-CFG on, the conditional and unconditional forwards of a step are independent;
     rank 0 of the group runs the positive branch, rank 1 the negative one, and one all-gather of the [B,S_img,64]
     noise predictions per step lets both apply the same fused combine + Euler step (SURVEY §8e "CFG parallel").
@@ -26,6 +29,8 @@ class _State:
     dp_size: int = 1
     tp_size: int = 1
     cfg_size: int = 1
+    sp_size: int = 1
+    sp_group: "dist.ProcessGroup | None" = None
     dp_group: "dist.ProcessGroup | None" = None
     tp_group: "dist.ProcessGroup | None" = None
     cfg_group: "dist.ProcessGroup | None" = None
@@ -53,36 +58,40 @@ def init_distributed_environment(world_size: int = -1, rank: int = -1, backend: 
 
 
 def initialize_model_parallel(data_parallel_size: int = 1, tensor_parallel_size: int = 1, backend: str | None = None,
-                              cfg_parallel_size: int = 1, **unused_reference_kwargs):
-    """reference parallel_state.py:563-713 (DP, CFG and TP groups are created; PP/SP groups are dead scaffolding for
-    this model — SURVEY §2b).  rank = (dp * cfg_size + cfg) * tp_size + tp, the reference's "tp-sp-pp-cfg-dp" order."""
+                              cfg_parallel_size: int = 1, ulysses_degree: int = 1, **unused_reference_kwargs):
+    """reference parallel_state.py:563-713 (DP, CFG, SP(ulysses) and TP groups are created; PP / ring groups are dead
+    scaffolding for this model — SURVEY §2b).  rank = ((dp * cfg_size + cfg) * sp_size + sp) * tp_size + tp, the reference's
+    "tp-sp-pp-cfg-dp" order."""
     ws = dist.get_world_size() if dist.is_initialized() else 1
     if cfg_parallel_size not in (1, 2):
         raise ValueError("cfg_parallel_size must be 1 or 2 (positive / negative branch)")
-    if data_parallel_size * cfg_parallel_size * tensor_parallel_size != ws:
-        raise ValueError(f"dp({data_parallel_size}) * cfg({cfg_parallel_size}) * tp({tensor_parallel_size}) != world_size({ws})")
-    _STATE.dp_size, _STATE.tp_size, _STATE.cfg_size = data_parallel_size, tensor_parallel_size, cfg_parallel_size
+    sp = int(ulysses_degree or 1)
+    if data_parallel_size * cfg_parallel_size * sp * tensor_parallel_size != ws:
+        raise ValueError(f"dp({data_parallel_size}) * cfg({cfg_parallel_size}) * sp({sp}) * tp({tensor_parallel_size}) != world_size({ws})")
+    _STATE.dp_size, _STATE.tp_size, _STATE.cfg_size, _STATE.sp_size = data_parallel_size, tensor_parallel_size, cfg_parallel_size, sp
+    _STATE.tp_group = _STATE.cfg_group = _STATE.dp_group = _STATE.sp_group = None
     rank = dist.get_rank() if dist.is_initialized() else 0
+    _STATE.rank = rank
     if ws == 1:
         return
     tp, cfg = tensor_parallel_size, cfg_parallel_size
-    for o in range(data_parallel_size * cfg):  # TP groups: adjacent ranks
-        ranks = list(range(o * tp, (o + 1) * tp))
-        g = dist.new_group(ranks, backend=backend)
-        if rank in ranks:
-            _STATE.tp_group = g
-    for d in range(data_parallel_size):  # CFG groups: stride tp inside one DP replica
-        for t in range(tp):
-            ranks = [(d * cfg + c) * tp + t for c in range(cfg)]
+
+    def rk(d, c, s_, t):
+        return ((d * cfg + c) * sp + s_) * tp + t
+
+    def make(groups):
+        mine = None
+        for ranks in groups:
             g = dist.new_group(ranks, backend=backend)
             if rank in ranks:
-                _STATE.cfg_group = g
-    for c in range(cfg):  # DP groups: stride cfg * tp
-        for t in range(tp):
-            ranks = [(d * cfg + c) * tp + t for d in range(data_parallel_size)]
-            g = dist.new_group(ranks, backend=backend)
-            if rank in ranks:
-                _STATE.dp_group = g
+                mine = g
+        return mine
+
+    dp_r, cfg_r, sp_r, tp_r = range(data_parallel_size), range(cfg), range(sp), range(tp)
+    _STATE.tp_group = make([[rk(d, c, s_, t) for t in tp_r] for d in dp_r for c in cfg_r for s_ in sp_r])
+    _STATE.sp_group = make([[rk(d, c, s_, t) for s_ in sp_r] for d in dp_r for c in cfg_r for t in tp_r])
+    _STATE.cfg_group = make([[rk(d, c, s_, t) for c in cfg_r] for d in dp_r for s_ in sp_r for t in tp_r])
+    _STATE.dp_group = make([[rk(d, c, s_, t) for d in dp_r] for c in cfg_r for s_ in sp_r for t in tp_r])
 
 
 def get_world_size() -> int:
@@ -94,7 +103,19 @@ def get_data_parallel_world_size() -> int:
 
 
 def get_data_parallel_rank() -> int:
-    return _STATE.rank // (_STATE.tp_size * _STATE.cfg_size)
+    return _STATE.rank // (_STATE.tp_size * _STATE.sp_size * _STATE.cfg_size)
+
+
+def get_sequence_parallel_world_size() -> int:
+    return _STATE.sp_size
+
+
+def get_sequence_parallel_rank() -> int:
+    return (_STATE.rank // _STATE.tp_size) % _STATE.sp_size
+
+
+def get_sp_group():
+    return _STATE.sp_group
 
 
 def get_cfg_parallel_world_size() -> int:
@@ -102,7 +123,7 @@ def get_cfg_parallel_world_size() -> int:
 
 
 def get_cfg_parallel_rank() -> int:
-    return (_STATE.rank // _STATE.tp_size) % _STATE.cfg_size
+    return (_STATE.rank // (_STATE.tp_size * _STATE.sp_size)) % _STATE.cfg_size
 
 
 def get_cfg_group():
@@ -117,13 +138,15 @@ def cfg_all_gather(local: torch.Tensor) -> list[torch.Tensor]:
 
 
 def any_rank_in_model_group(flag: bool, device=None) -> bool:
-    """Logical OR of `flag` over the ranks that compute ONE trajectory together (the TP group and the CFG group; DP
+    """Logical OR of `flag` over the ranks that compute ONE trajectory together (the TP, SP and CFG groups; DP
     replicas are independent and are not consulted).  Used for decisions every such rank must take identically."""
-    if _STATE.tp_size == 1 and _STATE.cfg_size == 1:
+    if _STATE.tp_size == 1 and _STATE.cfg_size == 1 and _STATE.sp_size == 1:
         return bool(flag)
     t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device if dist.get_backend() == "nccl" else "cpu")
     if _STATE.tp_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_STATE.tp_group)
+    if _STATE.sp_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_STATE.sp_group)
     if _STATE.cfg_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_STATE.cfg_group)
     return bool(int(t.item()))

@@ -240,6 +240,9 @@ class QwenImageTransformer2DModel(nn.Module):
         tp_rank: int | None = None,
         tp_group=None,
         tp_comm: str | None = None,
+        sp_size: int | None = None,
+        sp_rank: int | None = None,
+        sp_group=None,
     ):
         super().__init__()
         if od_config is not None and getattr(od_config, "tf_model_config", None) is not None:
@@ -266,6 +269,18 @@ class QwenImageTransformer2DModel(nn.Module):
             raise ValueError(f"tp_comm must be 'nccl' or 'p2p', got {self.tp_comm!r}")
         if num_attention_heads % self.tp_size:
             raise ValueError(f"tensor_parallel_size {self.tp_size} must divide num_attention_heads {num_attention_heads}")
+        # sequence parallelism (the reference's Ulysses mode, `ulysses_degree`), fused: full weights on every rank, own rows
+        # through the linears, own heads through attention; the all-to-alls are peer stores of the GEMM / attention epilogues
+        if sp_size is None:
+            sp_size = getattr(self.parallel_config, "ulysses_degree", 1) if self.parallel_config is not None else 1
+        if sp_size > 1 and sp_rank is None:
+            from vllm_omni_b200.diffusion.distributed import parallel_state as _ps
+            sp_rank, sp_group = _ps.get_sequence_parallel_rank(), _ps.get_sp_group()
+        self.sp_size, self.sp_rank, self.sp_group = int(sp_size), int(sp_rank or 0), sp_group
+        if self.sp_size > 1 and self.tp_size > 1:
+            raise ValueError("tensor parallelism and sequence parallelism cannot be combined in the native engine")
+        if num_attention_heads % self.sp_size:
+            raise ValueError(f"ulysses_degree {self.sp_size} must divide num_attention_heads {num_attention_heads}")
         self.in_channels = in_channels
         self.out_channels = out_channels or in_channels
         self.inner_dim = num_attention_heads * attention_head_dim
@@ -413,6 +428,9 @@ class QwenImageTransformer2DModel(nn.Module):
             # declare the mode (workspace layout depends on it); the peer pointers follow in _p2p_workspace
             qlib.check(qlib.load().qimg_engine_set_tp_p2p(self._engine, self.tp_size, self.tp_rank, None, None),
                        "qimg_engine_set_tp_p2p")
+        if self.sp_size > 1:
+            qlib.check(qlib.load().qimg_engine_set_sp_p2p(self._engine, self.sp_size, self.sp_rank, None, None),
+                       "qimg_engine_set_sp_p2p")
         if self.tp_size > 1 and self.tp_comm == "nccl":
             import torch.distributed as dist
 
@@ -436,17 +454,36 @@ class QwenImageTransformer2DModel(nn.Module):
         except Exception:
             pass
 
+    @property
+    def _peer(self):
+        """(size, rank, group) of the ranks that share peer-memory workspaces: the SP group or the TP group."""
+        return (self.sp_size, self.sp_rank, self.sp_group) if self.sp_size > 1 else (self.tp_size, self.tp_rank, self.tp_group)
+
+    def enable_sequence_parallel(self, sp_size: int, sp_rank: int, sp_group) -> None:
+        """Switch an (unsharded, tp_size == 1) model to fused sequence parallelism over `sp_group`, or back (sp_size = 1).
+        Weights stay as they are — every rank holds the full model, exactly like a data-parallel replica."""
+        if self.tp_size > 1:
+            raise ValueError("a tensor-parallel model cannot switch to sequence parallelism")
+        if self.num_attention_heads % max(int(sp_size), 1):
+            raise ValueError(f"ulysses_degree {sp_size} must divide num_attention_heads {self.num_attention_heads}")
+        self._p2p_release()
+        if self._engine is not None:
+            qlib.load().qimg_engine_destroy(self._engine)
+        self.sp_size, self.sp_rank, self.sp_group = int(sp_size), int(sp_rank), sp_group
+        self._engine = None  # rebuilt (and the mode declared) on the next forward
+
     def _p2p_release(self):
         """Unmap the peers' buffers and free the local ones (the next forward re-registers; collective like the set-up)."""
         groups = list(self._p2p_ws.values()) + ([(self._p2p_flags[0], self._p2p_flags[1], 0)] if self._p2p_flags else [])
+        _, prank, pgroup = self._peer
         for local, peers, _ in groups:
             for r, ptr in enumerate(peers):
-                if r != self.tp_rank:
+                if r != prank:
                     qlib.ipc_close_handle(ptr)
         if groups:
             torch.cuda.synchronize()
             import torch.distributed as dist
-            dist.barrier(group=self.tp_group)  # nobody frees while a peer still has the buffer mapped
+            dist.barrier(group=pgroup)  # nobody frees while a peer still has the buffer mapped
             for local, _, _ in groups:
                 qlib.p2p_free(local)
         self._p2p_ws.clear()
@@ -457,9 +494,10 @@ class QwenImageTransformer2DModel(nn.Module):
         """All ranks of the TP group swap the CUDA-IPC handle of `ptr`; returns the pointer per rank (own = local)."""
         import torch.distributed as dist
 
-        handles = [None] * self.tp_size
-        dist.all_gather_object(handles, qlib.ipc_get_handle(ptr), group=self.tp_group)
-        return [ptr if r == self.tp_rank else qlib.ipc_open_handle(h) for r, h in enumerate(handles)]
+        psize, prank, pgroup = self._peer
+        handles = [None] * psize
+        dist.all_gather_object(handles, qlib.ipc_get_handle(ptr), group=pgroup)
+        return [ptr if r == prank else qlib.ipc_open_handle(h) for r, h in enumerate(handles)]
 
     def _p2p_workspace(self, B: int, S_img: int, T: int):
         """Peer-memory TP: the workspace (and once, the barrier flags) is cudaMalloc'ed by the library, exported over
@@ -474,10 +512,11 @@ class QwenImageTransformer2DModel(nn.Module):
             self._p2p_ws[key] = (ws, self._p2p_exchange(ws), nbytes)
         ws, peers, nbytes = self._p2p_ws[key]
         if self._p2p_key != key:
-            P = self.tp_size
+            P, prank, _ = self._peer
             arr_ws = (C.c_void_p * P)(*peers)
             arr_fl = (C.c_void_p * P)(*self._p2p_flags[1])
-            qlib.check(qlib.load().qimg_engine_set_tp_p2p(self._engine, P, self.tp_rank, arr_ws, arr_fl), "qimg_engine_set_tp_p2p")
+            setter = qlib.load().qimg_engine_set_sp_p2p if self.sp_size > 1 else qlib.load().qimg_engine_set_tp_p2p
+            qlib.check(setter(self._engine, P, prank, arr_ws, arr_fl), "qimg_engine_set_{sp,tp}_p2p")
             self._p2p_key = key
         return ws, nbytes
 
@@ -541,7 +580,8 @@ class QwenImageTransformer2DModel(nn.Module):
         (ic, isn, tc, tsn), s_expected = self._rope(img_shapes, T, dev)
         if s_expected != S_img:
             raise ValueError(f"img_shapes implies {s_expected} image tokens, hidden_states has {S_img}")
-        if self.tp_size > 1 and self.tp_comm == "p2p":
+        peer_mode = (self.tp_size > 1 and self.tp_comm == "p2p") or self.sp_size > 1
+        if peer_mode:
             ws_ptr, nbytes = self._p2p_workspace(B, S_img, T)
         else:
             buf, off, nbytes = self._workspace(B, S_img, T, dev)
@@ -559,8 +599,8 @@ class QwenImageTransformer2DModel(nn.Module):
             run_stage(qlib.STAGE_ALL)
         else:
             # step cache: the hook decides between the blocks and the cached residual (cache/teacache/hook.py)
-            if self.tp_size > 1 and self.tp_comm == "p2p":
-                raise NotImplementedError("TeaCache with the peer-memory TP workspace is not wired (use tp_comm='nccl')")
+            if peer_mode:
+                raise NotImplementedError("TeaCache with a peer-memory workspace (TP p2p / sequence parallel) is not wired")
             D = self.inner_dim
             lib = qlib.load()
 

@@ -141,7 +141,7 @@ class GPUWorker:
                 ps.init_distributed_environment(world_size=world_size, rank=self.rank)
             pc = self.od_config.parallel_config
             ps.initialize_model_parallel(data_parallel_size=pc.data_parallel_size, tensor_parallel_size=pc.tensor_parallel_size,
-                                         cfg_parallel_size=pc.cfg_parallel_size)
+                                         cfg_parallel_size=pc.cfg_parallel_size, ulysses_degree=pc.ulysses_degree)
             t0 = time.perf_counter()
             prev = torch.get_default_dtype()
             torch.set_default_dtype(self.od_config.dtype)

@@ -28,7 +28,8 @@ EXPORTED_SYMBOLS = [
     "qimg_engine_set_tp_p2p", "qimg_engine_p2p_error", "qimg_set_fmha_trace",
     "qimg_engine_forward_stages", "qimg_engine_ws_offset_mod", "qimg_rel_l1_sums", "qimg_bf16_sub", "qimg_bf16_add_inplace",
     "qimg_fmha_joint_mode", "qimg_fmha_overflow", "qimg_cfg_euler_step_dev", "qimg_set_euler_dt_fp32",
-    "qimg_set_nvtx", "qimg_set_gemm_group_m", "qimg_set_fmha_single_tile", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
+    "qimg_set_nvtx", "qimg_set_gemm_group_m", "qimg_set_fmha_single_tile", "qimg_ln_modulate_rows", "qimg_fmha_joint_sp",
+    "qimg_engine_set_sp_p2p", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
 ]
 
 
@@ -42,6 +43,7 @@ class GemmProblem(C.Structure):
         ("S_joint", C.c_int), ("pos_off", C.c_int), ("H", C.c_int), ("eps", C.c_float),
         ("tp_recv", C.c_void_p * 8), ("tp_size", C.c_int), ("tp_rank", C.c_int), ("tp_recv_rows", C.c_int),
         ("tp_recv_row_off", C.c_int),
+        ("row_base", C.c_int), ("sp_size", C.c_int), ("sp_q", C.c_void_p * 8), ("sp_k", C.c_void_p * 8), ("sp_v", C.c_void_p * 8),
     ]
 
 
@@ -93,6 +95,7 @@ def load():
     lib.qimg_launch_count.restype = ll
     lib.qimg_reset_launch_count.restype = None
     lib.qimg_ln_modulate.argtypes = [vp, vp, vp, vp, i, i, i, ll, f, vp]
+    lib.qimg_ln_modulate_rows.argtypes = [vp, vp, vp, vp, i, i, i, i, ll, f, vp]
     lib.qimg_gate_residual.argtypes = [vp, vp, vp, i, i, i, ll, vp]
     lib.qimg_rms_norm.argtypes = [vp, vp, vp, i, i, f, vp]
     lib.qimg_gate_residual_bias.argtypes = [vp, vp, vp, vp, i, i, i, ll, vp]
@@ -103,6 +106,7 @@ def load():
     lib.qimg_ipc_open_handle.argtypes = [C.c_char_p, C.POINTER(vp)]
     lib.qimg_ipc_close_handle.argtypes = [vp]
     lib.qimg_engine_set_tp_p2p.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(vp)]
+    lib.qimg_engine_set_sp_p2p.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(vp)]
     lib.qimg_engine_p2p_error.argtypes = [vp, C.POINTER(i)]
     lib.qimg_linear_small_m.argtypes = [vp, vp, vp, vp, i, ll, i, ll, i, vp]
     lib.qimg_timestep_sinusoid.argtypes = [vp, vp, i, vp]
