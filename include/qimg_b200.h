@@ -42,7 +42,8 @@ int qimg_prof_collect(int kind, double* ms_total, long long* launches, double* f
 void qimg_set_nvtx(int on);
 
 /* GEMM tile mode: 0 = one CTA per 128x256 tile (tcgen05 cta_group::1), 1 = CTA pair per 256x256 tile
- * (cta_group::2, cluster of 2).  Default 1; env QIMG_GEMM_MODE overrides. */
+ * (cta_group::2, cluster of 2), 2 (default) = the pair unless 128-row tiles save whole rounds of the grid (small M: one
+ * image split over several GPUs).  Results are bit-identical across modes.  Env QIMG_GEMM_MODE overrides. */
 int qimg_set_gemm_mode(int mode);
 int qimg_get_gemm_mode(void);
 /* Raster band height in 256-row tiles (default 8; env QIMG_GEMM_GROUP_M): tiles of a band visit every weight column while
@@ -62,8 +63,9 @@ int qimg_set_gemm_group_m(int tiles);
 int qimg_set_fmha_mode(int mode);
 int qimg_get_fmha_mode(void);
 /* Query tiling of the attention grid: 0 = one CTA per PAIR of 128-row query tiles (K/V fetched once per 256 rows),
- * 1 = one CTA per tile, -1 (default) = per tile while tiles x B x H still fits one wave of SMs (small grids, e.g. the 3
- * local heads of TP=8 at B=1: 99 half-size CTAs instead of 51 full-size ones), pairs otherwise. */
+ * 1 = one CTA per tile, -1 (default) = per tile when that needs fewer rounds of the grid x relative CTA time (small grids:
+ * 204 pair CTAs on 148 SMs take 2 rounds, 396 tile CTAs 3 half-rounds), pairs otherwise.  Each row's result does not
+ * depend on the tiling. */
 int qimg_set_fmha_single_tile(int mode);
 
 /* ---- bandwidth-bound fused ops ------------------------------------------------------ */

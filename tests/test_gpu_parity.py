@@ -183,6 +183,26 @@ def test_gemm_bias_and_gelu(M, N, K, gemm_mode):
         assert O.rel_fro(y, F.gelu(F.linear(x, W, b), approximate="tanh")) < 5e-3  # reference bf16 op order
 
 
+def test_gemm_tile_modes_bit_identical():
+    """CTA-pair (256-row) and single-CTA (128-row) tiles run the same K loop per output element: bit-identical outputs.
+    The launcher relies on it when it picks the tile shape by grid size (mode 2), and so does the bit-identity of the
+    sequence-parallel engine (own-row GEMMs with small M may use the other tile shape than the single-GPU GEMM)."""
+    g = gen(60)
+    prev = q.get_gemm_mode()
+    try:
+        for (M, N, K) in ((1088, 3072, 3072), (300, 768, 1024), (2176, 12288, 3072)):
+            x = torch.randn(M, K, generator=g).bfloat16().to(dev)
+            W = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16().to(dev)
+            b = torch.randn(N, generator=g).bfloat16().to(dev)
+            outs = []
+            for mode in (0, 1, 2):
+                q.set_gemm_mode(mode)
+                outs.append(q.linear(x, W, b, q.EPI_BIAS_GELU).clone())
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), (M, N, K)
+    finally:
+        q.set_gemm_mode(prev)
+
+
 def test_gemm_grouped_gate_residual(gemm_mode):
     g = gen(7)
     Mi, Mt, D, K = 2 * 200, 2 * 24, 256, 1024

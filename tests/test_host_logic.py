@@ -310,7 +310,9 @@ def test_c_abi_argument_checks_without_gpu():
         lib.qimg_engine_destroy(h)
     bad = qlib.Dims(2, 24, 64, 64, 64, 3584, 1e-6)
     assert lib.qimg_engine_create(C.byref(bad), C.byref(g), blocks, C.byref(h)) != 0 and b"head_dim" in lib.qimg_last_error()
-    assert lib.qimg_set_fmha_mode(7) != 0 and lib.qimg_set_fmha_mode(0) != 0 and lib.qimg_set_gemm_mode(2) != 0
+    assert lib.qimg_set_fmha_mode(7) != 0 and lib.qimg_set_fmha_mode(0) != 0 and lib.qimg_set_gemm_mode(3) != 0
+    assert lib.qimg_set_gemm_mode(2) == 0 and lib.qimg_get_gemm_mode() == 2 and lib.qimg_set_fmha_single_tile(2) != 0
+    assert lib.qimg_engine_set_sp_p2p(None, 2, 0, None, None) != 0
     assert lib.qimg_rel_l1_sums(None, None, 12, None, None) != 0 and b"multiple of 8" in lib.qimg_last_error()
 
 

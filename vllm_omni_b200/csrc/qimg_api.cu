@@ -216,11 +216,14 @@ static int launch_gemm2_inst(const CUtensorMap* tA[2], const CUtensorMap* tB[2],
 }
 
 // 0 = one CTA per tile (128x256, cta_group::1); 1 = CTA pair per tile (256x256, cta_group::2)
+static int g_gemm_auto_tile = 1;  // qimg_set_gemm_mode(2): pair tiles unless 128-row tiles save whole rounds (default)
 static int g_gemm_mode = -1;
 static int gemm_mode() {
   if (g_gemm_mode < 0) {
     const char* e = getenv("QIMG_GEMM_MODE");
-    g_gemm_mode = e ? atoi(e) : 1;  // CTA pair: +6 % over cta_group::1 on every block GEMM (profiles/r01_kernel_bench.md)
+    const int m = e ? atoi(e) : 2;  // CTA pair: +6 % over cta_group::1 on every block GEMM (profiles/r01_kernel_bench.md)
+    g_gemm_mode = m == 0 ? 0 : 1;
+    g_gemm_auto_tile = (m == 2) ? 1 : 0;
   }
   return g_gemm_mode;
 }
@@ -244,7 +247,24 @@ static int launch_gemm(const qimg_gemm_problem* pr, int nprob, int epi, cudaStre
   int maxN = 0;
   for (int i = 0; i < nprob; ++i) maxN = pr[i].N > maxN ? pr[i].N : maxN;
   const int BN = (maxN <= 64 && epi == QIMG_EPI_BIAS) ? 64 : 256;
-  const bool pair = (BN == 256) && gemm_mode() == 1;
+  // tile shape: the CTA pair (256 x 256, cta_group::2) is 6 % faster per FLOP, but small M (one image under sequence /
+  // tensor parallelism: M = 1088 is 4.25 pair tiles) loses whole rounds to tile quantisation; 128-row tiles on single CTAs
+  // then need fewer rounds.  Estimated cost = rounds x relative tile time; both kernels run the same K loop per output
+  // element, so the choice does not change a single bit of the result (test_gemm_tile_modes_bit_identical).
+  bool pair = (BN == 256) && gemm_mode() == 1;
+  if (pair && g_gemm_auto_tile) {
+    const int sms = device_sm_count();
+    long long t2 = 0, t1 = 0;
+    for (int i = 0; i < nprob; ++i) {
+      const long long nt = (pr[i].N + 255) / 256;
+      t2 += (long long)((pr[i].M + 255) / 256) * nt;
+      t1 += (long long)((pr[i].M + 127) / 128) * nt;
+    }
+    if (sms >= 2) {
+      const long long r2 = (t2 + sms / 2 - 1) / (sms / 2), r1 = (t1 + sms - 1) / sms;
+      if ((double)r1 * 1.06 < (double)r2) pair = false;
+    }
+  }
   const int tile_m = pair ? 256 : GEMM_BM;
   GemmParams prm;
   memset(&prm, 0, sizeof prm);
@@ -471,11 +491,12 @@ void qimg_reset_launch_count(void) { g_launch_count.store(0); }
 void qimg_prof_enable(int on) { g_prof_on.store(on != 0); }
 
 int qimg_set_gemm_mode(int mode) {
-  if (mode != 0 && mode != 1) return fail("qimg_set_gemm_mode: mode must be 0 (cta_group::1) or 1 (cta_group::2 pair)");
-  g_gemm_mode = mode;
+  if (mode < 0 || mode > 2) return fail("qimg_set_gemm_mode: mode must be 0 (cta_group::1), 1 (cta_group::2 pair) or 2 (pair unless single saves rounds)");
+  g_gemm_mode = mode == 0 ? 0 : 1;
+  g_gemm_auto_tile = mode == 2;
   return 0;
 }
-int qimg_get_gemm_mode(void) { return gemm_mode(); }
+int qimg_get_gemm_mode(void) { return gemm_mode() == 0 ? 0 : (g_gemm_auto_tile ? 2 : 1); }
 int qimg_set_gemm_group_m(int tiles) {
   if (tiles < 1 || tiles > 1024) return fail("qimg_set_gemm_group_m: band height must be in [1, 1024] tiles");
   g_gemm_group_m = tiles;
@@ -769,7 +790,15 @@ static int fmha_launch(const void* q, const void* k, const void* v, void* out_tx
   prm.skip = launch_predicate();
   {  // one query tile per CTA while that still fits a single wave (halves the critical path of small grids)
     const int sms = device_sm_count();
-    prm.single_tile = g_fmha_single_tile >= 0 ? g_fmha_single_tile : ((sms > 0 && ((S + 127) / 128) * B * H <= sms) ? 1 : 0);
+    // rounds x relative CTA time: a one-tile CTA does half the work of a pair CTA at ~10 % lower efficiency (K/V fetched
+    // per 128 instead of 256 rows), so it wins when the pair grid wastes a large part of its last wave: 204 CTAs on 148
+    // SMs (12 local heads at B = 1) -> 2 rounds vs 3 x 0.55; each row's result is independent of the tiling
+    int single = 0;
+    if (sms > 0) {
+      const long long tiles = (long long)((S + 127) / 128) * B * H, prs = (long long)((S + 255) / 256) * B * H;
+      single = 0.55 * (double)((tiles + sms - 1) / sms) < (double)((prs + sms - 1) / sms) ? 1 : 0;
+    }
+    prm.single_tile = g_fmha_single_tile >= 0 ? g_fmha_single_tile : single;
   }
   prm.overflow = fmha_overflow_flag();
   if (!prm.overflow) return fail("qimg_fmha_joint: could not allocate the overflow flag");
