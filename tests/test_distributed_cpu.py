@@ -85,3 +85,45 @@ def test_rank_layout_dp_cfg_tp():
         assert (ps.get_data_parallel_rank(), ps.get_cfg_parallel_rank(), ps.get_tensor_model_parallel_rank()) == (1, 0, 1)
     finally:
         st.rank, st.tp_size, st.cfg_size, st.dp_size = saved
+
+
+def _sp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    ps.init_distributed_environment(world_size=world, rank=rank, backend="gloo")
+    ps.initialize_model_parallel(data_parallel_size=1, tensor_parallel_size=1, ulysses_degree=2, backend="gloo")
+    assert ps.get_sequence_parallel_world_size() == 2 and ps.get_sequence_parallel_rank() == rank
+    assert ps.get_data_parallel_rank() == 0 and ps.get_cfg_parallel_rank() == 0
+    t = torch.full((3,), float(rank + 1))
+    torch.distributed.all_reduce(t, group=ps.get_sp_group())
+    flag = ps.any_rank_in_model_group(rank == 1)   # the attention-guard decision is shared by the SP group
+    q.put(("sp", rank, t.tolist(), flag))
+    ps.destroy_distributed_env()
+
+
+def test_sequence_parallel_group_gloo():
+    """SP (ulysses_degree) group layout and the group-wide OR used by the attention guard."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sp_worker, args=(r, 2, 29634, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert res == [("sp", 0, [3.0] * 3, True), ("sp", 1, [3.0] * 3, True)]
+
+
+def test_rank_layout_with_sp():
+    """rank = ((dp * cfg + c) * sp + s) * tp + t."""
+    st = ps._STATE
+    saved = (st.rank, st.tp_size, st.cfg_size, st.dp_size, st.sp_size)
+    try:
+        st.tp_size, st.cfg_size, st.dp_size, st.sp_size = 1, 2, 2, 2
+        seen = set()
+        for r in range(8):
+            st.rank = r
+            seen.add((ps.get_data_parallel_rank(), ps.get_cfg_parallel_rank(), ps.get_sequence_parallel_rank()))
+        assert seen == {(d, c, s_) for d in range(2) for c in range(2) for s_ in range(2)}
+        st.rank = 6
+        assert (ps.get_data_parallel_rank(), ps.get_cfg_parallel_rank(), ps.get_sequence_parallel_rank()) == (1, 1, 0)
+    finally:
+        st.rank, st.tp_size, st.cfg_size, st.dp_size, st.sp_size = saved
