@@ -338,13 +338,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e_max = float(t[0]), float(t[1])
 
-    extras = {}
-    if not args.no_extras and args.cache == "none":
-        if world == 1:
-            extras["gpu_eager_baseline"] = eager_gpu_baseline(pipe, lat_d, txt_d, grid, T, L, S_img, B)
-        else:
-            extras.update(multi_gpu_legs(args, pipe, world, rank, local_rank, dev, barrier))
-
+    line = None
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         n_img = B * world * args.steps
@@ -393,15 +387,46 @@ def main():
                            "h2d_bytes_per_step": (lat_all.numel() + txt_all.numel() * (2 if args.cfg else 1)) * 2,
                            "d2h_bytes_per_step": out_h.numel() * 2,
                            "through": "GPUWorker.execute_model: one request of %d images, sharded over %d DP rank(s), gathered on rank 0" % (B * world, world)}
-        line.update(extras)
         if not args.no_cpu_baseline and world == 1:  # the CPU leg is reported on rank 0 at N=1 only
             try:
                 v, s, desc = cpu_reference_sample(res, T, NS, L, cfg=args.cfg)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": desc}
             except Exception as exc:  # never lose the measured line to a host-side failure
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc!r}"}
-        print(json.dumps(line))
+
+    # ---- extra legs AFTER the headline numbers exist; a watchdog thread guarantees that the line is printed even if a leg
+    #      hangs (a multi-GPU leg whose ranks diverge blocks in a collective, out of reach of try / except) ----
+    printed = threading.Event()
+
+    def emit(extra: dict):
+        if printed.is_set():
+            return
+        printed.set()
+        if rank == 0:
+            line.update(extra)
+            print(json.dumps(line), flush=True)
+
+    def watchdog(limit_s: float):
+        if not printed.wait(limit_s):
+            emit({"extras_error": f"extra legs did not finish within {limit_s:.0f} s; headline numbers above are complete"})
+            os._exit(0)
+
+    if not args.no_extras and args.cache == "none":
+        threading.Thread(target=watchdog, args=(240.0 if world == 1 else 600.0,), daemon=True).start()
+        extras = {}
+        try:
+            if world == 1:
+                extras["gpu_eager_baseline"] = eager_gpu_baseline(pipe, lat_d, txt_d, grid, T, L, S_img, B)
+            else:
+                extras.update(multi_gpu_legs(args, pipe, world, rank, local_rank, dev, barrier))
+        except Exception as exc:
+            extras["extras_error"] = repr(exc)[:300]
+        emit(extras)
+    else:
+        emit({})
     if world > 1:
+        # leave together when possible, but never hang on a peer that a failed leg left behind
+        threading.Thread(target=lambda: (time.sleep(90.0), os._exit(0)), daemon=True).start()
         dist.barrier()
         dist.destroy_process_group()
 
