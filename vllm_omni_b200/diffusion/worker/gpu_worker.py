@@ -79,7 +79,8 @@ def batch_key(req: OmniDiffusionRequest):
         return None
     ne = req.negative_prompt_embeds
     return (req.height, req.width, req.num_inference_steps, req.true_cfg_scale, tuple(req.sigmas) if req.sigmas is not None else None,
-            req.output_type, pe.shape[1], None if ne is None else ne.shape[1], req.num_outputs_per_prompt)
+            req.output_type, pe.shape[1], None if ne is None else ne.shape[1], req.num_outputs_per_prompt,
+            req.prompt_attention_mask is None, req.negative_attention_mask is None, req.seed is None)
 
 
 def merge_requests(reqs: list[OmniDiffusionRequest]):
