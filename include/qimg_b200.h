@@ -63,9 +63,8 @@ int qimg_set_gemm_group_m(int tiles);
 int qimg_set_fmha_mode(int mode);
 int qimg_get_fmha_mode(void);
 /* Query tiling of the attention grid: 0 = one CTA per PAIR of 128-row query tiles (K/V fetched once per 256 rows),
- * 1 = one CTA per tile, -1 (default) = per tile when that needs fewer rounds of the grid x relative CTA time (small grids:
- * 204 pair CTAs on 148 SMs take 2 rounds, 396 tile CTAs 3 half-rounds), pairs otherwise.  Each row's result does not
- * depend on the tiling. */
+ * 1 = one CTA per tile, -1 (default) = per tile while tiles x B x H still fits ONE wave of SMs (e.g. the 3 local heads of an
+ * 8-way split at B = 1: 99 CTAs instead of 51), pairs otherwise.  Each row's result does not depend on the tiling. */
 int qimg_set_fmha_single_tile(int mode);
 
 /* ---- bandwidth-bound fused ops ------------------------------------------------------ */

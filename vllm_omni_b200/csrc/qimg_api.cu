@@ -468,6 +468,7 @@ template <uint32_t MASK>
 static int launch_fmha_inst(int pipeline, const CUtensorMap* tq, const CUtensorMap* tk, const CUtensorMap* tv,
                             const FmhaParams& prm, cudaStream_t st) {
   static bool done7[kMaxDevices] = {}, done9[kMaxDevices] = {};
+
   const int pairs = (prm.S + 255) / 256;
   const int grid = prm.single_tile ? ((prm.S + 127) / 128) * prm.B * prm.H : pairs * prm.B * prm.H;
   if (pipeline == 6) {
@@ -788,16 +789,13 @@ static int fmha_launch(const void* q, const void* k, const void* v, void* out_tx
     return fail("qimg_fmha_joint: null output");
   }
   prm.skip = launch_predicate();
-  {  // one query tile per CTA while that still fits a single wave (halves the critical path of small grids)
+  {
     const int sms = device_sm_count();
-    // rounds x relative CTA time: a one-tile CTA does half the work of a pair CTA at ~10 % lower efficiency (K/V fetched
-    // per 128 instead of 256 rows), so it wins when the pair grid wastes a large part of its last wave: 204 CTAs on 148
-    // SMs (12 local heads at B = 1) -> 2 rounds vs 3 x 0.55; each row's result is independent of the tiling
-    int single = 0;
-    if (sms > 0) {
-      const long long tiles = (long long)((S + 127) / 128) * B * H, prs = (long long)((S + 255) / 256) * B * H;
-      single = 0.55 * (double)((tiles + sms - 1) / sms) < (double)((prs + sms - 1) / sms) ? 1 : 0;
-    }
+    // one query tile per CTA only while that grid still fits ONE wave (e.g. the 3 local heads of an 8-way split at B = 1:
+    // 99 CTAs instead of 51): a one-tile CTA has no second tile whose MMAs could run under its softmax, so it takes ~0.8 of a
+    // pair CTA's time, not 0.5 — with more than one wave the pair grid wins (a "rounds x 0.55" rule chose one-tile CTAs at
+    // S = 1152, B = 4 and ran at 523 instead of 703 TFLOP/s, profiles/r02_fmha_sweep_4.log).  Results do not depend on it.
+    const int single = (sms > 0 && (long long)((S + 127) / 128) * B * H <= sms) ? 1 : 0;
     prm.single_tile = g_fmha_single_tile >= 0 ? g_fmha_single_tile : single;
   }
   prm.overflow = fmha_overflow_flag();
