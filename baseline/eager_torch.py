@@ -110,3 +110,59 @@ def time_forward(model, lat, txt, t, grid, T, attn_backend: str, warmup: int = 3
     except Exception as exc:  # backend missing / no kernel image for sm_100
         torch.cuda.synchronize()
         return None, repr(exc)[:200]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# VAE decode, TIMING ONLY: the op sequence AutoencoderKLQwenImage._decode dispatches on CUDA for one latent
+# frame (autoencoder_kl_qwenimage.py:839-862; fp32 module, cuDNN convolutions with torch's default allow_tf32 = True,
+# F.pad + Conv3d per causal convolution, F.scaled_dot_product_attention in the mid block).  Conv3d weights are used as the
+# reference holds them ([Co, Ci, 3, 3, 3] on a two-zero-frame padded input), so cuDNN does the work the reference makes it do.
+def _vae_causal_conv3d(x, w, b):
+    k = w.shape[2]
+    pad = (w.shape[4] // 2, w.shape[4] // 2, w.shape[3] // 2, w.shape[3] // 2, 2 * (k // 2), 0)  # (:74-82)
+    return F.conv3d(F.pad(x, pad), w, b)
+
+
+def _vae_rms(x, gamma):
+    return F.normalize(x, dim=1) * (x.shape[1] ** 0.5) * gamma
+
+
+def _vae_resblock(x, W, p):
+    h = _vae_causal_conv3d(x, W[p + ".conv_shortcut.weight"], W[p + ".conv_shortcut.bias"]) if (p + ".conv_shortcut.weight") in W else x
+    y = F.silu(_vae_rms(x, W[p + ".norm1.gamma"]))
+    y = _vae_causal_conv3d(y, W[p + ".conv1.weight"], W[p + ".conv1.bias"])
+    y = F.silu(_vae_rms(y, W[p + ".norm2.gamma"]))
+    return _vae_causal_conv3d(y, W[p + ".conv2.weight"], W[p + ".conv2.bias"]) + h
+
+
+def vae_decode_eager(z, W):
+    """z [B, 16, 1, h, w] fp32 on the GPU, W the reference-named fp32 state dict on the GPU -> [B, 3, 1, 8h, 8w]."""
+    x = _vae_causal_conv3d(z, W["post_quant_conv.weight"], W["post_quant_conv.bias"])
+    x = _vae_causal_conv3d(x, W["decoder.conv_in.weight"], W["decoder.conv_in.bias"])
+    x = _vae_resblock(x, W, "decoder.mid_block.resnets.0")
+    p = "decoder.mid_block.attentions.0"
+    B, C, T, h, w = x.shape
+    y = x.permute(0, 2, 1, 3, 4).reshape(B * T, C, h, w)
+    y = _vae_rms(y, W[p + ".norm.gamma"])
+    qkv = F.conv2d(y, W[p + ".to_qkv.weight"], W[p + ".to_qkv.bias"]).reshape(B * T, 1, 3 * C, -1).permute(0, 1, 3, 2).contiguous()
+    q, k, v = qkv.chunk(3, dim=-1)
+    a = F.scaled_dot_product_attention(q, k, v).squeeze(1).permute(0, 2, 1).reshape(B * T, C, h, w)
+    a = F.conv2d(a, W[p + ".proj.weight"], W[p + ".proj.bias"])
+    x = a.view(B, T, C, h, w).permute(0, 2, 1, 3, 4) + x
+    x = _vae_resblock(x, W, "decoder.mid_block.resnets.1")
+    i = 0
+    while f"decoder.up_blocks.{i}.resnets.0.norm1.gamma" in W:
+        r = 0
+        while f"decoder.up_blocks.{i}.resnets.{r}.norm1.gamma" in W:
+            x = _vae_resblock(x, W, f"decoder.up_blocks.{i}.resnets.{r}")
+            r += 1
+        up = f"decoder.up_blocks.{i}.upsamplers.0.resample.1"
+        if (up + ".weight") in W:
+            b_, c_, t_, h_, w_ = x.shape
+            y = x.permute(0, 2, 1, 3, 4).reshape(b_ * t_, c_, h_, w_)
+            y = F.interpolate(y.float(), scale_factor=(2.0, 2.0), mode="nearest-exact").type_as(y)
+            y = F.conv2d(y, W[up + ".weight"], W[up + ".bias"], padding=1)
+            x = y.view(b_, t_, y.shape[1], y.shape[2], y.shape[3]).permute(0, 2, 1, 3, 4)
+        i += 1
+    x = F.silu(_vae_rms(x, W["decoder.norm_out.gamma"]))
+    return _vae_causal_conv3d(x, W["decoder.conv_out.weight"], W["decoder.conv_out.bias"]).clamp(-1.0, 1.0)

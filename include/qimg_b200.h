@@ -331,6 +331,41 @@ int qimg_engine_set_blocks_predicate(qimg_engine* e, const int* skip_flag);
 size_t qimg_engine_ws_offset_img(const qimg_engine* e, int B, int S_img, int T);
 size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T);
 
+/* ---- VAE decode: the post-step of QwenImagePipeline.forward ------------------------------------------
+ * Replaces AutoencoderKLQwenImage._decode (vllm_omni/diffusion/models/qwen_image/autoencoder_kl_qwenimage.py:839-862; the
+ * pipeline calls it at pipeline_qwen_image.py:746) for single-frame latents.  ALL pointers in this section are fp32 device
+ * memory, activations are NHWC ([image, y, x, channel], `ld*` = floats between consecutive pixels).  The layer graph
+ * (residual blocks, mid-block attention, up blocks) is driven by the host mirror vllm_omni_b200/.../vae_decoder.py.
+ *
+ * qimg_conv2d_nhwc_tf32   stride-1 "same" convolution as an implicit GEMM on tcgen05 (kind::tf32, fp32 accumulate):
+ *     out[n,y,x,co] = bias[co] + res[n,y,x,co] + sum_{tap,ci} x[n, y+dy(tap), x+dx(tap), ci] * w[co, tap * Cin_pad + ci]
+ *   taps = 9: 3x3 (tap = 3 * (dy + 1) + (dx + 1)); this is QwenImageCausalConv3d(k=3) on the first frame — two zero frames
+ *   are padded in FRONT (:78-82), so only weight[:, :, 2] meets data — and nn.Conv2d(3, padding=1) of the resamplers (:150);
+ *   Cin % 32 == 0, Cin_pad = Cin.  taps = 1: 1x1 (conv_shortcut :235, to_qkv / proj :299-300) and plain GEMMs
+ *   (out[M = H*W pixels, Cout] = x[M, Cin] * w[Cout, Cin]^T: the attention's Q*K^T and P*V), Cin % 4 == 0, Cin >= 32.
+ *   bias / res may be NULL.  Needs H >= 8 and W >= 16 (one 16 x 8 pixel patch per accumulator tile); Cout % 4 == 0.
+ * qimg_vae_rms_act        QwenImageRMS_norm (:102-109) over the channel of each pixel, times gamma, optional SiLU (:246-247)
+ * qimg_vae_upsample2x     nearest-exact x2 (QwenImageUpsample, :112-124,149)
+ * qimg_vae_post_quant     post_quant_conv 1x1x1 (:848) on NCHW z [N, 16, H, W] -> NHWC [N, H, W, 32] (channels 16..31 zero:
+ *                         one K block of conv_in); w [16, 16], b [16]
+ * qimg_vae_conv_out       conv_out 3x3, C = 96 -> 3 (:656) on the normalised + SiLU input, clamp(-1, 1) (:857); w packed [3][9][C],
+ *                         FMA pipe (exact fp32).  out (optional): NCHW fp32 [N, 3, H, W], what vae.decode returns.  out_u8
+ *                         (optional): NHWC uint8 [N, H, W, 3] = the reference's post-process (VaeImageProcessor.postprocess
+ *                         behind get_qwen_image_post_process_func, pipeline_qwen_image.py:40-60: (x / 2 + 0.5).clamp(0, 1)
+ *                         * 255, round half to even) fused in — a quarter of the bytes for the device -> host copy
+ * qimg_vae_softmax_rows   in place: s[r, :cols] = softmax(scale * s[r, :cols])   (SDPA of the mid-block attention, :321)
+ * qimg_vae_transpose      out[c * rows + r] = in[r * ld_in + c] */
+int qimg_conv2d_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, const float* bias, const float* res, int ldr,
+                          float* out, int ldo, int N, int H, int W, int Cin, int Cout, int taps, qimg_stream_t stream);
+int qimg_vae_rms_act(const float* x, const float* gamma, float* y, long long rows, int C, int silu, qimg_stream_t stream);
+int qimg_vae_upsample2x(const float* x, float* out, int N, int H, int W, int C, qimg_stream_t stream);
+int qimg_vae_post_quant(const float* z, const float* w, const float* b, float* out, int N, int H, int W, int z_dim,
+                        qimg_stream_t stream);
+int qimg_vae_conv_out(const float* x, const float* w, const float* b, float* out, uint8_t* out_u8, int N, int H, int W, int C,
+                      qimg_stream_t stream);
+int qimg_vae_softmax_rows(float* s, int rows, int cols, long long ld, float scale, qimg_stream_t stream);
+int qimg_vae_transpose(const float* in, long long ld_in, float* out, int rows, int cols, qimg_stream_t stream);
+
 /* ---- self test ------------------------------------------------------------------------ */
 /* Raw tcgen05 probe used by tests: D[128,N] = A[128,K] B[N,K]^T through the same descriptors the
  * kernels use.  mode 0: A,B K-major from smem.  mode 1: B MN-major ([K,N] row-major in global).

@@ -156,6 +156,99 @@ def _install_diffusers_stub():
     sys.modules.update(mods)
 
 
+def _install_diffusers_vae_stub():
+    """diffusers symbols imported by the reference's vendored VAE (autoencoder_kl_qwenimage.py:27-34).  Only what the DECODE
+    path touches carries behaviour: `get_activation("silu")` = nn.SiLU() (published diffusers table), `apply_forward_hook`
+    = identity (accelerate offload hook), `register_to_config` keeps the constructor untouched; the mixins are empty bases."""
+    import torch.nn as nn
+
+    _install_diffusers_stub()
+    if "diffusers.models.autoencoders.vae" in sys.modules:
+        return
+
+    def mod(name, pkg=False):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        if pkg:
+            m.__path__ = []
+        sys.modules[name] = m
+        return m
+
+    class ConfigMixin:
+        pass
+
+    def register_to_config(init):
+        return init
+
+    class FromOriginalModelMixin:
+        pass
+
+    class AutoencoderMixin:
+        pass
+
+    class ModelMixin(nn.Module):
+        pass
+
+    class DecoderOutput:
+        def __init__(self, sample):
+            self.sample = sample
+
+    class AutoencoderKLOutput:
+        def __init__(self, latent_dist):
+            self.latent_dist = latent_dist
+
+    class DiagonalGaussianDistribution:  # encode side only; never constructed on the decode path
+        def __init__(self, parameters):
+            self.parameters = parameters
+
+    def get_activation(name):
+        if name in ("silu", "swish"):
+            return nn.SiLU()
+        raise ValueError(name)
+
+    class _Log:
+        @staticmethod
+        def get_logger(name):
+            import logging
+            return logging.getLogger(name)
+
+    mod("diffusers.configuration_utils").ConfigMixin = ConfigMixin
+    mod("diffusers.configuration_utils").register_to_config = register_to_config
+    mod("diffusers.loaders").FromOriginalModelMixin = FromOriginalModelMixin
+    mod("diffusers.models.activations").get_activation = get_activation
+    mod("diffusers.models.autoencoders", pkg=True)
+    v = mod("diffusers.models.autoencoders.vae")
+    v.AutoencoderMixin, v.DecoderOutput, v.DiagonalGaussianDistribution = AutoencoderMixin, DecoderOutput, DiagonalGaussianDistribution
+    mod("diffusers.models.modeling_outputs").AutoencoderKLOutput = AutoencoderKLOutput
+    mod("diffusers.models.modeling_utils").ModelMixin = ModelMixin
+    u = mod("diffusers.utils", pkg=True)
+    u.logging = _Log
+    mod("diffusers.utils.accelerate_utils").apply_forward_hook = lambda f: f
+
+
+def build_reference_vae(**kwargs):
+    """The reference's vendored AutoencoderKLQwenImage (vllm_omni/diffusion/models/qwen_image/autoencoder_kl_qwenimage.py:667),
+    unmodified, in fp32 on the CPU (the dtype `from_pretrained` without torch_dtype gives, pipeline_qwen_image.py:267)."""
+    import importlib.util
+
+    import torch
+
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    _install_diffusers_vae_stub()
+    path = os.path.join(REF_ROOT, "vllm_omni", "diffusion", "models", "qwen_image", "autoencoder_kl_qwenimage.py")
+    spec = importlib.util.spec_from_file_location("_ref_autoencoder_kl_qwenimage", path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    kwargs.setdefault("dim_mult", [1, 2, 4, 4])  # vae/config.json holds a LIST (the tuple default breaks `[1] + dim_mult`, :409)
+    try:
+        vae = m.AutoencoderKLQwenImage(**kwargs)
+    finally:
+        torch.set_default_dtype(prev)
+    return vae.eval()
+
+
 _STATE = {}
 
 

@@ -1,0 +1,185 @@
+"""GPU (-m gpu): the native VAE decode (csrc/qimg_vae.cu through the C-ABI) against the fp32 oracle
+(oracle/vae_oracle.py, pinned to the unmodified reference by oracle/make_golden_vae.py) and the reference's golden images.
+
+Tolerances.  The reference computes these convolutions on the GPU with TF32 inputs / fp32 accumulation (cuDNN,
+`torch.backends.cudnn.allow_tf32` default) — the arithmetic the native tcgen05 kind::tf32 kernels use — and the goldens are
+the reference in full fp32 on the CPU.  A CPU emulation of TF32 input rounding through the whole decoder sits at 1.2e-3
+relative Frobenius / 3e-3 max abs of the fp32 image; the bars below leave 3x headroom over that:
+  one convolution / GEMM    <= 2e-3 relative Frobenius of the fp32 result  (TF32: 10 mantissa bits)
+  whole decode              <= 4e-3 relative Frobenius, <= 1.5e-2 max abs, and after the pipeline's uint8 quantisation
+                            >= 85 % of the pixels identical, none off by more than one level
+  row kernels (norm, upsample, softmax, transpose, post-quant, conv_out)   fp32 round-off (<= 2e-5)
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vae_oracle
+from vllm_omni_b200 import lib as q
+from vllm_omni_b200 import synthetic
+from vllm_omni_b200.diffusion.models.qwen_image.vae_decoder import B200VaeDecoder, _pack3x3
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+TOL_TF32 = 2e-3
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def nhwc(t):  # [N, C, H, W] -> [N, H, W, C] contiguous
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout", [(1, 8, 16, 32, 128), (2, 19, 23, 96, 96), (1, 40, 36, 384, 192), (1, 16, 32, 192, 384)],
+                         ids=["one-tile", "ragged-96", "384to192", "192to384"])
+def test_conv3x3_tf32_vs_fp32(N, H, W, cin, cout):
+    g = gen(H * 1000 + W)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(N, cout, H, W, generator=g)
+    want = F.conv2d(x, w, b, padding=1)
+    got = q.conv2d_nhwc_tf32(nhwc(x).to(dev), _pack3x3(w).to(dev), b.to(dev), 9, cout)
+    assert rel(got.cpu().permute(0, 3, 1, 2), want) < TOL_TF32
+    got = q.conv2d_nhwc_tf32(nhwc(x).to(dev), _pack3x3(w).to(dev), b.to(dev), 9, cout, res=nhwc(res).to(dev))
+    assert rel(got.cpu().permute(0, 3, 1, 2), want + res) < TOL_TF32
+
+
+def test_conv3x3_padding_is_zero_fill_at_every_border():
+    """An all-ones image through an all-ones 3x3 kernel counts the taps that meet data: 4 in the corners, 6 on the edges,
+    9 inside — exact in TF32, so any tap read from outside the image (or from the neighbouring image of the batch) shows."""
+    N, H, W, C = 2, 11, 21, 32
+    x = torch.ones(N, H, W, C, device=dev)
+    w = torch.zeros(4, 9 * C, device=dev)
+    w[:, ::C] = 1.0  # channel 0 of every tap
+    got = q.conv2d_nhwc_tf32(x, w, None, 9, 4).cpu()
+    want = F.conv2d(torch.ones(N, 1, H, W), torch.ones(1, 1, 3, 3), padding=1).permute(0, 2, 3, 1).expand(N, H, W, 4)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("P_h,P_w,K,Nout", [(8, 16, 384, 1152), (18, 22, 396, 384), (16, 16, 64, 256)], ids=["qkv", "k-tail-396", "small"])
+def test_gemm_mode_1x1_vs_fp32(P_h, P_w, K, Nout):
+    """taps = 1: out[pixels, Nout] = x[pixels, K] w[Nout, K]^T, including a K that is no multiple of the 32-float K block
+    (the P*V product of a 18 x 22 latent: 396 keys) and strided operands (channel slices of a wider buffer)."""
+    g = gen(K)
+    P = P_h * P_w
+    xbuf = torch.randn(P, K + 8, generator=g)
+    wbuf = torch.randn(Nout, K + 4, generator=g) / K ** 0.5
+    res = torch.randn(P, Nout, generator=g)
+    want = xbuf[:, :K] @ wbuf[:, :K].T + res
+    xd = xbuf.to(dev).view(1, P_h, P_w, K + 8)[..., :K]
+    got = q.conv2d_nhwc_tf32(xd, wbuf.to(dev)[:, :K], None, 1, Nout, res=res.to(dev).view(1, P_h, P_w, Nout), cin=K)
+    assert rel(got.cpu().view(P, Nout), want) < TOL_TF32
+
+
+def test_row_kernels_match_torch():
+    g = gen(5)
+    for C in (96, 192, 384):
+        x = torch.randn(3, 9, 17, C, generator=g) * 3
+        gamma = 1 + 0.1 * torch.randn(C, generator=g)
+        for silu in (False, True):
+            want = F.normalize(x, dim=-1) * C ** 0.5 * gamma
+            want = F.silu(want) if silu else want
+            got = q.vae_rms_act(x.to(dev), gamma.to(dev), silu).cpu()
+            assert (got - want).abs().max().item() < 2e-5
+    x = torch.randn(2, 5, 7, 96, generator=g)
+    want = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=(2.0, 2.0), mode="nearest-exact").permute(0, 2, 3, 1)
+    assert torch.equal(q.vae_upsample2x(x.to(dev)).cpu(), want)
+    s = torch.randn(37, 396, generator=g) * 20
+    want = torch.softmax(s * 0.051, dim=-1)
+    assert (q.vae_softmax_rows(s.to(dev), 0.051).cpu() - want).abs().max().item() < 2e-6
+    t = torch.randn(70, 1152, generator=g)
+    assert torch.equal(q.vae_transpose(t.to(dev)[:, 768:]).cpu(), t[:, 768:].T.contiguous())
+    z = torch.randn(2, 16, 9, 13, generator=g)
+    w, b = torch.randn(16, 16, generator=g) / 4, torch.randn(16, generator=g)
+    got = q.vae_post_quant(z.to(dev), w.to(dev), b.to(dev)).cpu()
+    want = F.conv2d(z, w.view(16, 16, 1, 1), b).permute(0, 2, 3, 1)
+    assert (got[..., :16] - want).abs().max().item() < 2e-5 and not got[..., 16:].any()
+    y = torch.randn(2, 10, 37, 96, generator=g)
+    w3, b3 = torch.randn(3, 96, 3, 3, generator=g) / 30, torch.randn(3, generator=g) * 0.1
+    want = F.conv2d(y.permute(0, 3, 1, 2), w3, b3, padding=1).clamp(-1, 1)
+    got = q.vae_conv_out(y.to(dev), w3.permute(0, 2, 3, 1).contiguous().to(dev), b3.to(dev)).cpu()
+    assert (got - want).abs().max().item() < 2e-5
+
+
+def _check_image(got, want):
+    d = (got - want).abs()
+    u8 = lambda t: ((t * 0.5 + 0.5) * 255).round().clamp(0, 255)  # noqa: E731  (the post-process of pipeline_qwen_image.py:40-60)
+    lv = (u8(got) - u8(want)).abs()
+    stats = dict(rel=rel(got, want), max_abs=d.max().item(), same=(lv == 0).float().mean().item(), max_level=lv.max().item())
+    assert stats["rel"] < 4e-3 and stats["max_abs"] < 1.5e-2 and stats["same"] > 0.85 and stats["max_level"] <= 1, stats
+    return stats
+
+
+@pytest.mark.parametrize("name", ["vae_decode_ragged", "vae_decode_256px"])
+def test_decode_matches_reference_golden(golden_dir, name):
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"))
+    W = synthetic.synthetic_vae_decoder_weights(seed=gold["wseed"])
+    assert abs(sum(v.double().abs().sum() for v in W.values()).item() - gold["weights_checksum"]) < 1e-6 * gold["weights_checksum"]
+    vae = B200VaeDecoder(W, device=dev)
+    n0 = q.launch_count()
+    img = vae.decode(gold["z"].to(dev), return_dict=False)[0]
+    assert q.launch_count() - n0 > 60  # the sm_100a kernels ran (no torch fallback exists)
+    assert img.shape == gold["image"].shape and img.dtype == torch.float32
+    _check_image(img.cpu(), gold["image"])
+
+
+def test_decode_batch_items_are_independent_and_banded_attention_is_identical(monkeypatch):
+    W = synthetic.synthetic_vae_decoder_weights(seed=5)
+    vae = B200VaeDecoder(W, device=dev)
+    z = torch.randn(3, 16, 1, 16, 24, generator=gen(21)).to(dev)
+    full = vae.decode(z, return_dict=False)[0]
+    for i in range(3):
+        assert torch.equal(vae.decode(z[i:i + 1], return_dict=False)[0], full[i:i + 1])
+    import vllm_omni_b200.diffusion.models.qwen_image.vae_decoder as V
+    monkeypatch.setattr(V, "SCORES_BYTES_MAX", 4 * (16 * 24) * 24 * 8)  # 8 image rows per score band, two bands
+    assert torch.equal(vae.decode(z, return_dict=False)[0], full)
+
+
+def test_decode_to_uint8_is_the_reference_post_process_of_the_decoded_image():
+    """decode_to_uint8 == VaeImageProcessor.postprocess arithmetic (pipeline_qwen_image.py:40-60) applied to decode():
+    bit-exact, and the registry's post-process function turns both into the same PIL images."""
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image import get_qwen_image_post_process_func
+    vae = B200VaeDecoder(synthetic.synthetic_vae_decoder_weights(seed=8), device=dev)
+    z = torch.randn(2, 16, 1, 9 * 2, 16, generator=gen(51)).to(dev)
+    img = vae.decode(z, return_dict=False)[0][:, :, 0]
+    u8 = vae.decode_to_uint8(z)
+    want = ((img / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8)
+    assert u8.shape == (2, 144, 128, 3) and torch.equal(u8, want)
+    post = get_qwen_image_post_process_func(None)
+    a, b = post(img), post(u8)
+    assert len(a) == 2 and a[0].size == (128, 144) and all(x.tobytes() == y.tobytes() for x, y in zip(a, b))
+
+
+def test_decode_1024px_against_oracle():
+    """BASELINE configs[1] geometry (1024 x 1024: 128 x 128 latent grid, 16384 attention positions) against the fp32 oracle."""
+    W = synthetic.synthetic_vae_decoder_weights(seed=6)
+    z = torch.randn(1, 16, 1, 128, 128, generator=gen(31))
+    img = B200VaeDecoder(W, device=dev).decode(z.to(dev), return_dict=False)[0]
+    assert img.shape == (1, 3, 1, 1024, 1024)
+    want = vae_oracle.vae_decode(z, W)
+    _check_image(img.cpu(), want)
+
+
+def test_pipeline_decodes_through_the_native_vae():
+    """QwenImagePipeline.forward's post-step (pipeline_qwen_image.py:736-747) with the native decoder injected as `vae`:
+    unpack + de-normalise + decode, against the oracle on the same latents."""
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image import QwenImagePipeline
+    W = synthetic.synthetic_vae_decoder_weights(seed=7)
+    vae = B200VaeDecoder(W, device=dev)
+    h, w = 16, 32  # latent grid -> 128 x 256 px
+    lat = torch.randn(2, (h // 2) * (w // 2), 64, generator=gen(41))
+    unpacked = QwenImagePipeline._unpack_latents(lat, 8 * h, 8 * w, 8)
+    mean = torch.tensor(vae.config.latents_mean).view(1, 16, 1, 1, 1)
+    std = 1.0 / torch.tensor(vae.config.latents_std).view(1, 16, 1, 1, 1)
+    want = vae_oracle.vae_decode(unpacked / std + mean, W)[:, :, 0]
+    got = QwenImagePipeline.decode_latents(vae, lat.to(dev), 8 * h, 8 * w)
+    _check_image(got.cpu(), want)

@@ -474,3 +474,53 @@ def test_two_stage_pipeline_overlaps_and_matches_serial():
     den_spans = {rid: (a, b) for s, rid, a, b in p.timeline if s == "denoise"}
     assert enc_spans["req-2"][0] < den_spans["req-1"][1], "request 2 must be encoded while request 1 is being denoised"
     assert t_par < t_serial - 0.1   # 4 x (0.05 [+0.05] + 0.15) serial vs ~0.1 + 4 x 0.15 overlapped
+
+
+def test_vae_weight_packing_is_the_implicit_gemm_layout():
+    """The native convolution computes out[pixel, co] = sum_{tap, ci} x[pixel + (tap / 3 - 1, tap % 3 - 1), ci] * w[co, tap * Cp + ci]
+    (include/qimg_b200.h).  Check on the CPU that `_pack3x3` of a reference Conv3d weight — last temporal tap, channels padded —
+    gives exactly that matrix: an explicit im2col GEMM with it equals F.conv2d with weight[:, :, 2]."""
+    import torch.nn.functional as F
+    from vllm_omni_b200.diffusion.models.qwen_image.vae_decoder import B200VaeDecoder, _pack3x3
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 16, 5, 7, generator=g)
+    w3d = torch.randn(8, 16, 3, 3, 3, generator=g)
+    packed = _pack3x3(w3d, cin_pad=32)
+    assert packed.shape == (8, 9 * 32)
+    xp = F.pad(x, (1, 1, 1, 1)).permute(0, 2, 3, 1)[0]  # [H + 2, W + 2, C]
+    cols = []
+    for tap in range(9):
+        dy, dx = tap // 3 - 1, tap % 3 - 1
+        patch = xp[1 + dy:1 + dy + 5, 1 + dx:1 + dx + 7]  # x[pixel + (dy, dx)]
+        cols.append(F.pad(patch, (0, 16)))                # channels padded to 32 with zeros
+    A = torch.cat(cols, dim=-1).reshape(35, 9 * 32)
+    want = F.conv2d(x, w3d[:, :, 2], padding=1)[0].permute(1, 2, 0).reshape(35, 8)
+    assert (A @ packed.T - want).abs().max().item() < 1e-4
+    # the decoder object: reference checkpoint keys in, packed fp32 matrices out; time_conv (never run for one frame) dropped
+    from vllm_omni_b200 import synthetic
+    dec = B200VaeDecoder(synthetic.synthetic_vae_decoder_weights(seed=1), device="cpu")
+    assert dec.w["decoder.conv_in.weight"].shape == (384, 9 * 32) and dec.w["decoder.conv_out.weight"].shape == (3, 3, 3, 96)
+    assert dec.w["decoder.up_blocks.1.resnets.0.conv_shortcut.weight"].shape == (384, 192)
+    assert not any("time_conv" in k for k in dec.w) and dec.num_up_blocks == 4 and dec.num_res == 3
+    assert dec.dtype == torch.float32 and dec.config.z_dim == 16 and len(dec.config.latents_mean) == 16
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        dec.decode(torch.zeros(1, 16, 1, 8, 16))
+    with pytest.raises(ValueError):
+        B200VaeDecoder({"encoder.conv_in.weight": torch.zeros(1)}, device="cpu")
+
+
+def test_post_process_func_is_the_reference_image_arithmetic():
+    """(x / 2 + 0.5).clamp(0, 1) * 255, rounded half to even, NHWC uint8 -> PIL (VaeImageProcessor.postprocess behind the
+    reference's get_qwen_image_post_process_func, pipeline_qwen_image.py:40-60); latents pass through untouched."""
+    import numpy as np
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image import get_qwen_image_post_process_func
+    post = get_qwen_image_post_process_func(None)
+    lat = torch.zeros(2, 16, 64)
+    assert post(lat) is lat
+    img = torch.tensor([-1.5, -1.0, -0.5, 0.0, 1 / 255, 0.5, 1.0, 2.0]).view(1, 1, 2, 4).expand(1, 3, 2, 4).contiguous()
+    out = post(img)
+    assert len(out) == 1 and out[0].size == (4, 2) and out[0].mode == "RGB"
+    want = np.array([0, 0, 64, 128, 128, 191, 255, 255], dtype=np.uint8).reshape(2, 4)  # 63.75 -> 64, 127.5 -> 128 (even), 191.25
+    assert (np.asarray(out[0])[..., 0] == want).all()
+    u8 = torch.arange(24, dtype=torch.uint8).view(1, 2, 4, 3)
+    assert (np.asarray(post(u8)[0]) == u8[0].numpy()).all()

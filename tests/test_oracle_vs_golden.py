@@ -134,3 +134,17 @@ def test_oracle_diffuse_matches_reference_loop(golden_dir, cfg):
     out = O.diffuse(w, dims, fx["latents0"].clone(), fx["prompt_embeds"], fx["negative_prompt_embeds"] if cfg else None,
                     fx["sigmas"], (1,) + tuple(c["grid"]), c["true_cfg_scale"])
     assert torch.equal(out, fx["cfg" if cfg else "nocfg"])
+
+
+@pytest.mark.parametrize("name", ["vae_decode_ragged", "vae_decode_256px"])
+def test_vae_oracle_matches_reference_golden(golden_dir, name):
+    """oracle/vae_oracle.py (the single-frame restatement) against the unmodified reference VAE's decode
+    (autoencoder_kl_qwenimage.py:865, fixtures by oracle/make_golden_vae.py): fp32 round-off only."""
+    from oracle import vae_oracle
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"))
+    W = synthetic.synthetic_vae_decoder_weights(seed=gold["wseed"])
+    chk = float(sum(v.double().abs().sum() for v in W.values()))
+    assert abs(chk - gold["weights_checksum"]) < 1e-6 * gold["weights_checksum"], "synthetic VAE weights drifted from the fixture's"
+    img = vae_oracle.vae_decode(gold["z"], W)
+    assert img.shape == gold["image"].shape
+    assert (img - gold["image"]).abs().max().item() < 1e-4

@@ -12,7 +12,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libqimg_b200.so")
-SOURCES = ["qimg_api.cu", "qimg_engine.cu", "qimg_tp_p2p.cu"]
+SOURCES = ["qimg_api.cu", "qimg_engine.cu", "qimg_tp_p2p.cu", "qimg_vae.cu"]
 HEADERS = ["qimg_common.cuh", "qimg_elementwise.cuh", "qimg_gemm.cuh", "qimg_gemm2.cuh", "qimg_fmha.cuh", "qimg_fmha4.cuh",
            "qimg_fmha6.cuh", "qimg_host.cuh", "qimg_tp.h", os.path.join("..", "..", "include", "qimg_b200.h")]
 FLAGS_STAMP = LIB_PATH + ".flags"  # the optional build flags the existing .so was compiled with

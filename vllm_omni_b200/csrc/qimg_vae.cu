@@ -1,0 +1,616 @@
+// VAE decoder kernels for sm_100a: the post-step of QwenImagePipeline.forward
+// (pipeline_qwen_image.py:736-747 -> AutoencoderKLQwenImage._decode, autoencoder_kl_qwenimage.py:839-862), single-frame latents.
+//
+// The reference runs this in fp32 with cuDNN (TF32 tensor-core convolutions by default) over NCHW tensors, ~70 separate ATen
+// / cuDNN launches with an fp32 pad + conv per layer.  Here:
+//   * activations live in HBM as fp32 NHWC ([image, y, x, channel]); a 3x3 "same" convolution is an implicit GEMM
+//       out[pixel, co] = sum_{tap, ci} x[pixel + tap, ci] * w[co, tap, ci]
+//     on the 5th-gen tensor cores (tcgen05.mma kind::tf32, fp32 accumulators in TMEM): one CTA owns a 16 x 8 pixel patch
+//     (128 accumulator rows) x 128 output channels; per K block the producer warp issues ONE 4-D TMA box load
+//     {32 channels, 16 x, 8 y, 1 image} at the tap's shifted coordinates — the zero padding of the convolution is TMA's
+//     out-of-bounds fill, no padded copy, no im2col buffer — plus the weight tile; SWIZZLE_128B, 5-stage mbarrier ring,
+//     two TMEM accumulator stages so the epilogue (bias + residual add, fp32, coalesced NHWC stores) of tile i overlaps the
+//     main loop of tile i+1.  1x1 convolutions and the three attention GEMMs of the mid block use the same kernel (taps = 1).
+//   * TF32 inputs / fp32 accumulation is the arithmetic the reference's own GPU path uses for these layers
+//     (torch.backends.cudnn.allow_tf32 defaults to True), so parity against the fp32 oracle is at the reference's own level.
+//   * the bandwidth-bound pieces are single-pass row kernels: RMS-norm (+ SiLU), nearest x2 upsample, row softmax, the
+//     16 -> 16 post_quant_conv fused with the NCHW -> NHWC layout change, and conv_out (96 -> 3 channels: FMA-pipe direct
+//     convolution fused with the clamp and the NHWC -> NCHW change; N = 3 is no tensor-core shape).
+#include "../../include/qimg_b200.h"
+
+#include <cstring>
+
+#include "qimg_common.cuh"
+#include "qimg_host.cuh"
+
+namespace qimg {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tcgen05 kind::tf32 + 4-D TMA
+// ---------------------------------------------------------------------------------------------------------------------
+// instruction descriptor: [4,6) c_format = 1 (F32), [7,10) a_format = 2 (TF32), [10,13) b_format = 2, K-major A and B,
+// [17,23) N >> 3, [24,29) M >> 4   (cute/arch/mma_sm100_desc.hpp, F16F32Format::TF32 = 2)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem], 128 x N x 8 per instruction
+__device__ __forceinline__ void umma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+constexpr int CONV_BM = 128;       // 16 x 8 pixel patch
+constexpr int CONV_PX = 16;
+constexpr int CONV_PY = 8;
+constexpr int CONV_BN = 128;       // output channels per tile
+constexpr int CONV_BK = 32;        // fp32 elements per K block = one 128-byte swizzle row
+constexpr int CONV_STAGES = 5;
+constexpr int CONV_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int CONV_A_BYTES = CONV_BM * CONV_BK * 4;
+constexpr int CONV_B_BYTES = CONV_BN * CONV_BK * 4;
+constexpr int CONV_STAGE_BYTES = CONV_A_BYTES + CONV_B_BYTES;
+constexpr int CONV_EPI_BYTES = 8 * 32 * 128;
+constexpr int CONV_SMEM_BYTES = CONV_STAGES * CONV_STAGE_BYTES + CONV_EPI_BYTES + 1024 + 256;
+
+struct ConvParams {
+  int N, H, W;       // images, rows, columns (output = input geometry: stride 1, "same" padding)
+  int cin_blocks;    // ceil(Cin / 32)
+  int taps;          // 9 = 3x3, 1 = 1x1
+  int Cout;
+  int ldo, ldr;      // pixel strides (floats) of out / res
+  int tiles_x, tiles_y, n_tiles, total_tiles;
+  const float* bias; // [Cout] or nullptr
+  const float* res;  // [N, H, W, ldr] or nullptr: out = conv + bias + res
+  float* out;        // [N, H, W, ldo]
+};
+
+struct ConvTile {
+  int n, x0, y0, n_blk;
+};
+__device__ __forceinline__ ConvTile conv_decode_tile(const ConvParams& P, int tile) {
+  ConvTile t;
+  const int m_tile = tile / P.n_tiles;  // the n tiles of one pixel patch are adjacent: they run concurrently and share A in L2
+  t.n_blk = tile - m_tile * P.n_tiles;
+  const int per_img = P.tiles_x * P.tiles_y;
+  t.n = m_tile / per_img;
+  const int rem = m_tile - t.n * per_img;
+  const int ty = rem / P.tiles_x;
+  t.y0 = ty * CONV_PY;
+  t.x0 = (rem - ty * P.tiles_x) * CONV_PX;
+  return t;
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvParams P) {
+  constexpr int TMEM_COLS = 2 * CONV_BN;
+  constexpr uint32_t IDESC = make_idesc_tf32(CONV_BM, CONV_BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_epi = smem + CONV_STAGES * CONV_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + CONV_EPI_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + CONV_STAGES;
+  uint64_t* tmem_full = bars + 2 * CONV_STAGES;
+  uint64_t* tmem_empty = bars + 2 * CONV_STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * CONV_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < CONV_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int kblocks = P.taps * P.cin_blocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const ConvTile t = conv_decode_tile(P, tile);
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * CONV_STAGE_BYTES;
+          uint8_t* sb = sa + CONV_A_BYTES;
+          const int dy = P.taps == 9 ? tap / 3 - 1 : 0;
+          const int dx = P.taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
+          mbar_arrive_expect_tx(&full_bar[stage], CONV_STAGE_BYTES);
+          // rows of the box: channel fastest, then x, then y -> 128 rows of 128 B = the K-major SWIZZLE_128B A tile;
+          // coordinates outside the image (negative or >= W / H) are zero-filled by TMA: the convolution's padding
+          tma_load_4d(sa, &tmA, &full_bar[stage], cb * CONV_BK, t.x0 + dx, t.y0 + dy, t.n);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * CONV_BK, t.n_blk * CONV_BN);
+        }
+        __syncwarp();
+        if (++cb == P.cin_blocks) {
+          cb = 0;
+          ++tap;
+        }
+        if (++stage == CONV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * CONV_BN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * CONV_STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + CONV_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < CONV_BK / 8; ++k)  // K = 8 tf32 = 32 B per instruction inside the 128 B swizzle row
+            umma_ss_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kb == kblocks - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == CONV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps: warp (q, half) owns accumulator rows q*32..+32, columns half*64..+64 =========
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    const uint32_t stg = smem_u32(smem_epi + ew * 4096);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const ConvTile t = conv_decode_tile(P, tile);
+      // the 8 rows this lane stores (tile-local row q*32 + it*4 + lane/8): pixel index, -1 when outside the image
+      long long pix[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rl = q * 32 + it * 4 + (lane >> 3);
+        const int x = t.x0 + (rl & (CONV_PX - 1)), y = t.y0 + (rl >> 4);
+        pix[it] = (x < P.W && y < P.H) ? ((long long)t.n * P.H + y) * P.W + x : -1;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CONV_BN;
+#pragma unroll 1
+      for (int step = 0; step < 2; ++step) {
+        const int col = half * 64 + step * 32;
+        const int n0 = t.n_blk * CONV_BN + col;
+        if (n0 >= P.Cout) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + col, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(r[j * 4], r[j * 4 + 1], r[j * 4 + 2], r[j * 4 + 3]));
+        __syncwarp();
+        const int c16 = lane & 7;
+        const int gn = n0 + c16 * 4;
+        if (gn < P.Cout) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (P.bias) bv = __ldg(reinterpret_cast<const float4*>(P.bias + gn));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3);
+            const uint4 v = lds_v4(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+            if (pix[it] >= 0) {
+              float4 o = make_float4(__uint_as_float(v.x) + bv.x, __uint_as_float(v.y) + bv.y, __uint_as_float(v.z) + bv.z,
+                                     __uint_as_float(v.w) + bv.w);
+              if (P.res) {
+                const float4 rv = *reinterpret_cast<const float4*>(P.res + (size_t)pix[it] * P.ldr + gn);
+                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+              }
+              *reinterpret_cast<float4*>(P.out + (size_t)pix[it] * P.ldo + gn) = o;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// bandwidth-bound row kernels (fp32)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
+
+// QwenImageRMS_norm (autoencoder_kl_qwenimage.py:102-109): F.normalize(x, dim=channel) * sqrt(C) * gamma, then optional SiLU
+// (:246-247,262-263,640-641).  One warp per pixel, C <= 32 * 12.
+__global__ void vae_rms_act_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ y,
+                                   long long rows, int C, int silu) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * C;
+  float v[12];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < C ? xr[c] : 0.f;
+    ss = fmaf(v[i], v[i], ss);
+  }
+  ss = warp_sum(ss);
+  const float s = sqrtf((float)C) / fmaxf(sqrtf(ss), 1e-12f);
+  float* yr = y + row * C;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      const float o = v[i] * s * __ldg(gamma + c);
+      yr[c] = silu ? silu_exact(o) : o;
+    }
+  }
+}
+
+// nearest-exact x2 (QwenImageUpsample, :147-156): out[n, y, x, :] = in[n, y / 2, x / 2, :]; one float4 per thread
+__global__ void vae_upsample2x_kernel(const float4* __restrict__ in, float4* __restrict__ out, int N, int H, int W, int C4) {
+  const long long total = (long long)N * (2 * H) * (2 * W) * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long p = i / C4;
+    const int x = (int)(p % (2 * W));
+    p /= 2 * W;
+    const int y = (int)(p % (2 * H));
+    const int n = (int)(p / (2 * H));
+    out[i] = in[(((long long)n * H + (y >> 1)) * W + (x >> 1)) * C4 + c];
+  }
+}
+
+// post_quant_conv (1x1x1, z_dim -> z_dim, :848) fused with NCHW -> NHWC; output padded to 32 channels (one K block of the
+// conv_in implicit GEMM), channels >= Z written as zero.  One thread per pixel.
+template <int Z>
+__global__ void vae_post_quant_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
+                                      float* __restrict__ out, int N, int HW) {
+  __shared__ float sw[Z * Z + Z];
+  for (int i = threadIdx.x; i < Z * Z + Z; i += blockDim.x) sw[i] = i < Z * Z ? w[i] : b[i - Z * Z];
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)N * HW) return;
+  const int n = (int)(p / HW), i = (int)(p - (long long)n * HW);
+  float v[Z];
+#pragma unroll
+  for (int c = 0; c < Z; ++c) v[c] = z[((long long)n * Z + c) * HW + i];
+  float4* o = reinterpret_cast<float4*>(out + p * 32);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c4 * 4 < Z) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int co = c4 * 4 + e;
+        float a = sw[Z * Z + co];
+#pragma unroll
+        for (int ci = 0; ci < Z; ++ci) a = fmaf(sw[co * Z + ci], v[ci], a);
+        r[e] = a;
+      }
+    }
+    o[c4] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// conv_out (:656; 3x3, C -> 3 channels) + clamp(-1, 1) (:857) + NHWC -> NCHW.  x is the normalised, SiLU-activated input.
+// FMA pipe, exact fp32: one thread per output pixel, weights [3][9][C] in shared memory.
+template <int C>
+__global__ void vae_conv_out_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                    float* __restrict__ out, uint8_t* __restrict__ out_u8, int N, int H, int W) {
+  __shared__ float4 sw[3 * 9 * C / 4];
+  for (int i = threadIdx.x; i < 3 * 9 * C / 4; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
+  __syncthreads();
+  const int xx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int yy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  if (xx >= W || yy >= H) return;
+  float a0 = b[0], a1 = b[1], a2 = b[2];
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int y = yy + tap / 3 - 1, xq = xx + tap % 3 - 1;
+    if (y < 0 || y >= H || xq < 0 || xq >= W) continue;
+    const float4* xp = reinterpret_cast<const float4*>(x + (((long long)n * H + y) * W + xq) * C);
+    const float4* w0 = sw + (0 * 9 + tap) * (C / 4);
+    const float4* w1 = sw + (1 * 9 + tap) * (C / 4);
+    const float4* w2 = sw + (2 * 9 + tap) * (C / 4);
+#pragma unroll 4
+    for (int c = 0; c < C / 4; ++c) {
+      const float4 v = __ldg(xp + c);
+      const float4 u0 = w0[c], u1 = w1[c], u2 = w2[c];
+      a0 = fmaf(v.x, u0.x, fmaf(v.y, u0.y, fmaf(v.z, u0.z, fmaf(v.w, u0.w, a0))));
+      a1 = fmaf(v.x, u1.x, fmaf(v.y, u1.y, fmaf(v.z, u1.z, fmaf(v.w, u1.w, a1))));
+      a2 = fmaf(v.x, u2.x, fmaf(v.y, u2.y, fmaf(v.z, u2.z, fmaf(v.w, u2.w, a2))));
+    }
+  }
+  a0 = fminf(fmaxf(a0, -1.f), 1.f);
+  a1 = fminf(fmaxf(a1, -1.f), 1.f);
+  a2 = fminf(fmaxf(a2, -1.f), 1.f);
+  const long long hw = (long long)H * W, pix = (long long)yy * W + xx;
+  if (out) {
+    const long long o = (long long)n * 3 * hw + pix;
+    out[o] = a0;
+    out[o + hw] = a1;
+    out[o + 2 * hw] = a2;
+  }
+  if (out_u8) {
+    // VaeImageProcessor.postprocess (the reference's post_process_func, pipeline_qwen_image.py:40-60): denormalise
+    // (x / 2 + 0.5).clamp(0, 1), NHWC, (x * 255).round() -> uint8; the same fp32 operations, rint = numpy's half-to-even
+    uint8_t* o = out_u8 + ((long long)n * hw + pix) * 3;
+    o[0] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a0, 0.5f), 0.5f), 0.f), 1.f), 255.f));
+    o[1] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a1, 0.5f), 0.5f), 0.f), 1.f), 255.f));
+    o[2] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a2, 0.5f), 0.5f), 0.f), 1.f), 255.f));
+  }
+}
+
+// in-place row softmax of fp32 scores (F.scaled_dot_product_attention of the mid-block attention, :321): one CTA per row
+__global__ void vae_softmax_rows_kernel(float* __restrict__ s, int cols, long long ld, float scale) {
+  float* row = s + (long long)blockIdx.x * ld;
+  __shared__ float red[32];
+  __shared__ float bc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, row[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < nw ? red[lane] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) bc = v;
+  }
+  __syncthreads();
+  m = bc;
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float e = expf((row[c] - m) * scale);
+    row[c] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < nw ? red[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) bc = v;
+  }
+  __syncthreads();
+  const float inv = 1.0f / bc;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) row[c] *= inv;
+}
+
+// out[c, r] = in[r * ld_in + c]  (V^T for the P*V GEMM: both tcgen05 operands K-major)
+__global__ void vae_transpose_kernel(const float* __restrict__ in, long long ld_in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float t[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(long long)c * rows + r] = t[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn vae_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode_f32(CUtensorMap* tm, int rank, const void* ptr, const cuuint64_t* gdim, const cuuint64_t* gstride_bytes,
+                      const cuuint32_t* box) {
+  EncodeTiledFn enc = vae_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver / no GPU)");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "CUresult %d (rank %d, dims %llu %llu %llu %llu)", (int)r, rank, (unsigned long long)gdim[0],
+             (unsigned long long)gdim[1], rank > 2 ? (unsigned long long)gdim[2] : 0ull, rank > 3 ? (unsigned long long)gdim[3] : 0ull);
+    return fail("cuTensorMapEncodeTiled(fp32)", buf);
+  }
+  return 0;
+}
+
+static int conv_smem_attr() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail("no CUDA device");
+  if (!done[dev]) {
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(conv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
+    done[dev] = true;
+  }
+  return 0;
+}
+
+}  // namespace qimg
+
+using namespace qimg;
+
+extern "C" {
+
+int qimg_conv2d_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, const float* bias, const float* res, int ldr,
+                          float* out, int ldo, int N, int H, int W, int Cin, int Cout, int taps, qimg_stream_t stream) {
+  if (!x || !w || !out) return fail("qimg_conv2d_nhwc_tf32: null pointer");
+  if (taps != 1 && taps != 9) return fail("qimg_conv2d_nhwc_tf32: taps must be 1 (1x1) or 9 (3x3)");
+  if (N < 1 || H < CONV_PY || W < CONV_PX) return fail("qimg_conv2d_nhwc_tf32: needs H >= 8 and W >= 16 (one 16 x 8 pixel patch)");
+  if (Cin < 32 || (Cin & 3) || (taps == 9 && (Cin & 31)))
+    return fail("qimg_conv2d_nhwc_tf32: Cin must be >= 32, a multiple of 4 (1x1) / of 32 (3x3: pad the channels)");
+  if (Cout < 1 || (Cout & 3)) return fail("qimg_conv2d_nhwc_tf32: Cout must be a multiple of 4");
+  const int cin_blocks = (Cin + CONV_BK - 1) / CONV_BK;
+  const long long kcols = taps == 9 ? 9ll * cin_blocks * CONV_BK : Cin;
+  if (ldx < Cin || (ldx & 3) || ldw < kcols || (ldw & 3) || ldo < Cout || (ldo & 3) || (res && (ldr < Cout || (ldr & 3))))
+    return fail("qimg_conv2d_nhwc_tf32: leading dimensions must cover the row and be multiples of 4 floats");
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(bias)) & 15)
+    return fail("qimg_conv2d_nhwc_tf32: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+    cuuint32_t box[4] = {CONV_BK, CONV_PX, CONV_PY, 1};
+    if (encode_f32(&tmA, 4, x, gdim, gstr, box)) return 1;
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)kcols, (cuuint64_t)Cout};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldw * 4};
+    cuuint32_t box[2] = {CONV_BK, CONV_BN};
+    if (encode_f32(&tmB, 2, w, gdim, gstr, box)) return 1;
+  }
+  ConvParams P;
+  memset(&P, 0, sizeof P);
+  P.N = N; P.H = H; P.W = W;
+  P.cin_blocks = cin_blocks;
+  P.taps = taps;
+  P.Cout = Cout;
+  P.ldo = ldo; P.ldr = ldr;
+  P.tiles_x = (W + CONV_PX - 1) / CONV_PX;
+  P.tiles_y = (H + CONV_PY - 1) / CONV_PY;
+  P.n_tiles = (Cout + CONV_BN - 1) / CONV_BN;
+  const long long total = (long long)N * P.tiles_x * P.tiles_y * P.n_tiles;
+  if (total > 0x7fffffffll) return fail("qimg_conv2d_nhwc_tf32: too many tiles");
+  P.total_tiles = (int)total;
+  P.bias = bias; P.res = res; P.out = out;
+  if (conv_smem_attr()) return 1;
+  const int sms = device_sm_count();
+  if (sms <= 0) return fail("no CUDA device");
+  const int grid = P.total_tiles < sms ? P.total_tiles : sms;
+  conv_tf32_kernel<<<grid, CONV_THREADS, CONV_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, P);
+  QIMG_LAUNCH_CHECK("conv_tf32_kernel");
+  return 0;
+}
+
+int qimg_vae_rms_act(const float* x, const float* gamma, float* y, long long rows, int C, int silu, qimg_stream_t stream) {
+  if (!x || !gamma || !y || rows < 1 || C < 1 || C > 384) return fail("qimg_vae_rms_act: bad arguments (C <= 384)");
+  const int wpb = 8;
+  const long long blocks = (rows + wpb - 1) / wpb;
+  if (blocks > 0x7fffffffll) return fail("qimg_vae_rms_act: too many rows");
+  vae_rms_act_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(x, gamma, y, rows, C, silu);
+  QIMG_LAUNCH_CHECK("vae_rms_act_kernel");
+  return 0;
+}
+
+int qimg_vae_upsample2x(const float* x, float* out, int N, int H, int W, int C, qimg_stream_t stream) {
+  if (!x || !out || N < 1 || H < 1 || W < 1 || C < 4 || (C & 3)) return fail("qimg_vae_upsample2x: bad arguments (C % 4 == 0)");
+  const long long total = (long long)N * 4 * H * W * (C / 4);
+  long long blocks = (total + 255) / 256;
+  const int sms = device_sm_count();
+  if (sms > 0 && blocks > (long long)sms * 32) blocks = (long long)sms * 32;
+  vae_upsample2x_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x),
+                                                                             reinterpret_cast<float4*>(out), N, H, W, C / 4);
+  QIMG_LAUNCH_CHECK("vae_upsample2x_kernel");
+  return 0;
+}
+
+int qimg_vae_post_quant(const float* z, const float* w, const float* b, float* out, int N, int H, int W, int z_dim,
+                        qimg_stream_t stream) {
+  if (!z || !w || !b || !out || N < 1 || H < 1 || W < 1) return fail("qimg_vae_post_quant: bad arguments");
+  if (z_dim != 16) return fail("qimg_vae_post_quant: z_dim must be 16 (AutoencoderKLQwenImage)");
+  const long long px = (long long)N * H * W;
+  vae_post_quant_kernel<16><<<(unsigned)((px + 127) / 128), 128, 0, (cudaStream_t)stream>>>(z, w, b, out, N, H * W);
+  QIMG_LAUNCH_CHECK("vae_post_quant_kernel");
+  return 0;
+}
+
+int qimg_vae_conv_out(const float* x, const float* w, const float* b, float* out, uint8_t* out_u8, int N, int H, int W, int C,
+                      qimg_stream_t stream) {
+  if (!x || !w || !b || (!out && !out_u8) || N < 1 || H < 1 || W < 1) return fail("qimg_vae_conv_out: bad arguments");
+  if (C != 96) return fail("qimg_vae_conv_out: C must be 96 (base_dim of AutoencoderKLQwenImage)");
+  if (N > 65535) return fail("qimg_vae_conv_out: N too large");
+  dim3 grid((W + 31) / 32, (H + 7) / 8, N);
+  vae_conv_out_kernel<96><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, out_u8, N, H, W);
+  QIMG_LAUNCH_CHECK("vae_conv_out_kernel");
+  return 0;
+}
+
+int qimg_vae_softmax_rows(float* s, int rows, int cols, long long ld, float scale, qimg_stream_t stream) {
+  if (!s || rows < 1 || cols < 1 || ld < cols) return fail("qimg_vae_softmax_rows: bad arguments");
+  vae_softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(s, cols, ld, scale);
+  QIMG_LAUNCH_CHECK("vae_softmax_rows_kernel");
+  return 0;
+}
+
+int qimg_vae_transpose(const float* in, long long ld_in, float* out, int rows, int cols, qimg_stream_t stream) {
+  if (!in || !out || rows < 1 || cols < 1 || ld_in < cols) return fail("qimg_vae_transpose: bad arguments");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  if (grid.y > 65535) return fail("qimg_vae_transpose: too many rows");
+  vae_transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, ld_in, out, rows, cols);
+  QIMG_LAUNCH_CHECK("vae_transpose_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -470,17 +470,34 @@ class QwenImagePipeline(nn.Module):
         self._current_timestep = None
         if output_type == "latent" or self.vae is None:
             return DiffusionOutput(output=latents)
-        lat = self._unpack_latents(latents, height, width, self.vae_scale_factor).to(self.vae.dtype)
-        z = self.vae.config.z_dim
-        mean = torch.tensor(self.vae.config.latents_mean).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
-        std = 1.0 / torch.tensor(self.vae.config.latents_std).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
-        image = self.vae.decode(lat / std + mean, return_dict=False)[0][:, :, 0]
-        return DiffusionOutput(output=image)
+        return DiffusionOutput(output=self.decode_latents(self.vae, latents, height, width, self.vae_scale_factor,
+                                                          uint8=getattr(self, "uint8_output", False)))
+
+    @staticmethod
+    def decode_latents(vae, latents, height, width, vae_scale_factor: int = 8, uint8: bool = False):
+        """The reference's post-step (:736-747): unpack, cast to the VAE's dtype, undo the latent normalisation, decode, keep
+        frame 0.  `vae` is anything with the AutoencoderKLQwenImage decode surface — the native `B200VaeDecoder`
+        (vae_decoder.py: tcgen05 TF32 convolutions) or a torch module."""
+        lat = QwenImagePipeline._unpack_latents(latents, height, width, vae_scale_factor).to(vae.dtype)
+        z = vae.config.z_dim
+        mean = torch.tensor(vae.config.latents_mean).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
+        std = 1.0 / torch.tensor(vae.config.latents_std).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
+        if uint8 and hasattr(vae, "decode_to_uint8"):  # native decoder: post-process arithmetic fused into its last kernel
+            return vae.decode_to_uint8(lat / std + mean)
+        return vae.decode(lat / std + mean, return_dict=False)[0][:, :, 0]
 
 
 def get_qwen_image_post_process_func(od_config: OmniDiffusionConfig):
-    """Looked up by name by the registry (reference registry.py:97-139, pipeline :40-60).  With no VAE in
-    scope the native pipeline returns latents; the post-process is the identity."""
+    """Looked up by name by the registry (reference registry.py:97-139).  The reference's function is
+    `VaeImageProcessor.postprocess` (pipeline :40-60, diffusers): (x / 2 + 0.5).clamp(0, 1) -> NHWC -> (x * 255).round()
+    -> uint8 -> PIL.  Here: latents ([B, S, 64], no VAE in the worker) pass through; a decoded image [B, 3, H, W] in
+    [-1, 1] gets that arithmetic; a uint8 [B, H, W, 3] tensor (B200VaeDecoder.decode_to_uint8: the arithmetic already done on
+    the device) is only copied to the host."""
     def post_process_func(images: torch.Tensor):
-        return images
+        if not torch.is_tensor(images) or images.dim() != 4:
+            return images
+        if images.dtype != torch.uint8:
+            images = ((images.float() / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8)
+        from PIL import Image
+        return [Image.fromarray(a) for a in images.cpu().numpy()]
     return post_process_func

@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = [
     "qimg_fmha_joint_mode", "qimg_fmha_overflow", "qimg_cfg_euler_step_dev", "qimg_set_euler_dt_fp32",
     "qimg_set_nvtx", "qimg_set_gemm_group_m", "qimg_set_fmha_single_tile", "qimg_ln_modulate_rows", "qimg_fmha_joint_sp",
     "qimg_engine_set_sp_p2p", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
+    "qimg_conv2d_nhwc_tf32", "qimg_vae_rms_act", "qimg_vae_upsample2x", "qimg_vae_post_quant", "qimg_vae_conv_out",
+    "qimg_vae_softmax_rows", "qimg_vae_transpose",
 ]
 
 
@@ -139,6 +141,13 @@ def load():
     lib.qimg_tea_residual.argtypes = [vp, vp, vp, ll, vp, vp]
     lib.qimg_engine_set_blocks_predicate.argtypes = [vp, vp]
     lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
+    lib.qimg_conv2d_nhwc_tf32.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, i, i, vp]
+    lib.qimg_vae_rms_act.argtypes = [vp, vp, vp, ll, i, i, vp]
+    lib.qimg_vae_upsample2x.argtypes = [vp, vp, i, i, i, i, vp]
+    lib.qimg_vae_post_quant.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
+    lib.qimg_vae_conv_out.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
+    lib.qimg_vae_softmax_rows.argtypes = [vp, i, i, ll, f, vp]
+    lib.qimg_vae_transpose.argtypes = [vp, ll, vp, i, i, vp]
     lib.qimg_set_gemm_mode.argtypes = [i]
     lib.qimg_set_gemm_group_m.argtypes = [i]
     lib.qimg_set_fmha_mode.argtypes = [i]
@@ -406,3 +415,89 @@ def bf16_sub(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
 def bf16_add_inplace(x: torch.Tensor, r: torch.Tensor):
     _bf16c(x), _bf16c(r)
     check(load().qimg_bf16_add_inplace(_p(x), _p(r), x.numel(), stream_ptr()), "qimg_bf16_add_inplace")
+
+
+# ---- VAE decode (fp32 NHWC; include/qimg_b200.h "VAE decode") ---------------------------------------------------------
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.is_cuda, f"expected a CUDA fp32 tensor, got {t.dtype} on {t.device}"
+    return t
+
+
+def conv2d_nhwc_tf32(x: torch.Tensor, w: torch.Tensor, bias, taps: int, cout: int, res=None, out=None, cin: int | None = None):
+    """x [N, H, W, ldx] fp32 (a channel-sliced view with stride-1 channels is fine: ldx = pixel stride, `cin` = channels used);
+    w [cout, ldw] packed (co, tap * cin + ci); returns out [N, H, W, cout] = conv + bias (+ res)."""
+    _f32(x), _f32(w)
+    N, H, W = x.shape[0], x.shape[1], x.shape[2]
+    cin = x.shape[3] if cin is None else cin
+    ldx = x.stride(2)
+    assert x.stride(3) == 1 and x.stride(1) == W * ldx and (N == 1 or x.stride(0) == H * W * ldx), "x must be NHWC with dense pixels"
+    if out is None:
+        out = torch.empty((N, H, W, cout), dtype=torch.float32, device=x.device)
+    assert out.stride(3) == 1 and out.stride(1) == W * out.stride(2)
+    ldr = 0
+    if res is not None:
+        _f32(res)
+        assert res.shape[:3] == out.shape[:3] and res.stride(3) == 1 and res.stride(1) == W * res.stride(2)
+        ldr = res.stride(2)
+    check(load().qimg_conv2d_nhwc_tf32(_p(x), ldx, _p(w), w.stride(0), _p(bias), _p(res), ldr, _p(out), out.stride(2), N, H, W,
+                                       cin, cout, taps, stream_ptr()), "qimg_conv2d_nhwc_tf32")
+    return out
+
+
+def vae_rms_act(x: torch.Tensor, gamma: torch.Tensor, silu: bool, out=None):
+    _f32(x), _f32(gamma)
+    assert x.is_contiguous()
+    C_ = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    check(load().qimg_vae_rms_act(_p(x), _p(gamma), _p(out), x.numel() // C_, C_, 1 if silu else 0, stream_ptr()), "qimg_vae_rms_act")
+    return out
+
+
+def vae_upsample2x(x: torch.Tensor):
+    _f32(x)
+    assert x.is_contiguous()
+    N, H, W, C_ = x.shape
+    out = torch.empty((N, 2 * H, 2 * W, C_), dtype=torch.float32, device=x.device)
+    check(load().qimg_vae_upsample2x(_p(x), _p(out), N, H, W, C_, stream_ptr()), "qimg_vae_upsample2x")
+    return out
+
+
+def vae_post_quant(z: torch.Tensor, w: torch.Tensor, b: torch.Tensor):
+    """z [N, 16, H, W] fp32 NCHW -> [N, H, W, 32] NHWC (channels 16.. zero)."""
+    _f32(z), _f32(w), _f32(b)
+    assert z.is_contiguous() and w.is_contiguous()
+    N, Z, H, W = z.shape
+    out = torch.empty((N, H, W, 32), dtype=torch.float32, device=z.device)
+    check(load().qimg_vae_post_quant(_p(z), _p(w), _p(b), _p(out), N, H, W, Z, stream_ptr()), "qimg_vae_post_quant")
+    return out
+
+
+def vae_conv_out(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, uint8: bool = False):
+    """x [N, H, W, 96] (normalised + SiLU) -> clamp(conv3x3 -> 3 channels); w packed [3, 9, 96].  Returns NCHW fp32
+    [N, 3, H, W], or with `uint8` the post-processed NHWC uint8 image [N, H, W, 3]."""
+    _f32(x), _f32(w), _f32(b)
+    assert x.is_contiguous() and w.is_contiguous()
+    N, H, W, C_ = x.shape
+    if uint8:
+        out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=x.device)
+        check(load().qimg_vae_conv_out(_p(x), _p(w), _p(b), None, _p(out), N, H, W, C_, stream_ptr()), "qimg_vae_conv_out")
+    else:
+        out = torch.empty((N, 3, H, W), dtype=torch.float32, device=x.device)
+        check(load().qimg_vae_conv_out(_p(x), _p(w), _p(b), _p(out), None, N, H, W, C_, stream_ptr()), "qimg_vae_conv_out")
+    return out
+
+
+def vae_softmax_rows(s: torch.Tensor, scale: float):
+    _f32(s)
+    assert s.dim() == 2 and s.stride(1) == 1
+    check(load().qimg_vae_softmax_rows(_p(s), s.shape[0], s.shape[1], s.stride(0), float(scale), stream_ptr()), "qimg_vae_softmax_rows")
+    return s
+
+
+def vae_transpose(x: torch.Tensor):
+    """x [rows, cols] fp32 (row stride arbitrary) -> contiguous [cols, rows]."""
+    _f32(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty((x.shape[1], x.shape[0]), dtype=torch.float32, device=x.device)
+    check(load().qimg_vae_transpose(_p(x), x.stride(0), _p(out), x.shape[0], x.shape[1], stream_ptr()), "qimg_vae_transpose")
+    return out

@@ -111,3 +111,74 @@ def synthetic_inputs(batch: int, height_px: int, width_px: int, txt_len: int, jo
         g = torch.Generator().manual_seed(44)
         out.append(torch.randn((batch, txt_len, joint_dim), generator=g, dtype=torch.float32).to(dtype))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# VAE decoder.  Names and shapes are the reference's `AutoencoderKLQwenImage` state dict restricted to the
+# decode path (`post_quant_conv.*`, `decoder.*`; autoencoder_kl_qwenimage.py:549-612,707-710).
+def vae_decoder_param_shapes(base_dim: int = 96, z_dim: int = 16, dim_mult=(1, 2, 4, 4), num_res_blocks: int = 2,
+                             temporal_upsample=(True, True, False), out_channels: int = 3) -> dict[str, tuple]:
+    dims = [base_dim * u for u in [dim_mult[-1]] + list(dim_mult[::-1])]  # (:578)
+    s: dict[str, tuple] = {
+        "post_quant_conv.weight": (z_dim, z_dim, 1, 1, 1), "post_quant_conv.bias": (z_dim,),
+        "decoder.conv_in.weight": (dims[0], z_dim, 3, 3, 3), "decoder.conv_in.bias": (dims[0],),
+    }
+
+    def resblock(prefix, cin, cout):
+        s[f"{prefix}.norm1.gamma"] = (cin, 1, 1, 1)
+        s[f"{prefix}.conv1.weight"] = (cout, cin, 3, 3, 3)
+        s[f"{prefix}.conv1.bias"] = (cout,)
+        s[f"{prefix}.norm2.gamma"] = (cout, 1, 1, 1)
+        s[f"{prefix}.conv2.weight"] = (cout, cout, 3, 3, 3)
+        s[f"{prefix}.conv2.bias"] = (cout,)
+        if cin != cout:
+            s[f"{prefix}.conv_shortcut.weight"] = (cout, cin, 1, 1, 1)
+            s[f"{prefix}.conv_shortcut.bias"] = (cout,)
+
+    d0 = dims[0]
+    resblock("decoder.mid_block.resnets.0", d0, d0)
+    s["decoder.mid_block.attentions.0.norm.gamma"] = (d0, 1, 1)
+    s["decoder.mid_block.attentions.0.to_qkv.weight"] = (3 * d0, d0, 1, 1)
+    s["decoder.mid_block.attentions.0.to_qkv.bias"] = (3 * d0,)
+    s["decoder.mid_block.attentions.0.proj.weight"] = (d0, d0, 1, 1)
+    s["decoder.mid_block.attentions.0.proj.bias"] = (d0,)
+    resblock("decoder.mid_block.resnets.1", d0, d0)
+    out_dim = d0
+    for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+        if i > 0:
+            in_dim = in_dim // 2
+        cur = in_dim
+        for r in range(num_res_blocks + 1):
+            resblock(f"decoder.up_blocks.{i}.resnets.{r}", cur, out_dim)
+            cur = out_dim
+        if i != len(dim_mult) - 1:
+            s[f"decoder.up_blocks.{i}.upsamplers.0.resample.1.weight"] = (out_dim // 2, out_dim, 3, 3)
+            s[f"decoder.up_blocks.{i}.upsamplers.0.resample.1.bias"] = (out_dim // 2,)
+            if temporal_upsample[i]:  # present in the checkpoint, never executed for a single frame (:166-169)
+                s[f"decoder.up_blocks.{i}.upsamplers.0.time_conv.weight"] = (out_dim * 2, out_dim, 3, 1, 1)
+                s[f"decoder.up_blocks.{i}.upsamplers.0.time_conv.bias"] = (out_dim * 2,)
+    s["decoder.norm_out.gamma"] = (out_dim, 1, 1, 1)
+    s["decoder.conv_out.weight"] = (out_channels, out_dim, 3, 3, 3)
+    s["decoder.conv_out.bias"] = (out_channels,)
+    return s
+
+
+def synthetic_vae_decoder_weights(seed: int = 0, **arch) -> dict[str, torch.Tensor]:
+    """fp32 (the dtype the reference loads the VAE in): conv weights N(0, 1/fan_in) so activations stay O(1), biases
+    N(0, 0.05^2), RMS gammas 1 + N(0, 0.1^2); each tensor seeded from crc32(name) like the DiT weights."""
+    out = {}
+    for name, shape in vae_decoder_param_shapes(**arch).items():
+        g = torch.Generator(device="cpu")
+        g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+        t = torch.randn(shape, generator=g, dtype=torch.float32)
+        if name.endswith(".gamma"):
+            t = 1.0 + 0.1 * t
+        elif name.endswith(".bias"):
+            t = 0.05 * t
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = t * (1.0 / fan_in) ** 0.5 * (3.0 ** 0.5 if len(shape) == 5 and shape[2] == 3 else 1.0)  # 1 of 3 time taps is live
+        out[name] = t
+    return out
