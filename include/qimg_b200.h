@@ -357,6 +357,11 @@ size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T);
  * qimg_vae_transpose      out[c * rows + r] = in[r * ld_in + c] */
 int qimg_conv2d_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, const float* bias, const float* res, int ldr,
                           float* out, int ldo, int N, int H, int W, int Cin, int Cout, int taps, qimg_stream_t stream);
+/* Kernel variant of qimg_conv2d_nhwc_tf32: 0 (default) = one TMA box per (horizontal tap, channel block) shared by the three
+ * vertical taps as shifted descriptor views + 16 x 16 pixel patches per CTA (2.3x fewer operand bytes per MAC);
+ * 1 = one box per tap, 16 x 8 patches (the first version, kept for A/B).  Env QIMG_VAE_CONV.  Same results up to fp32
+ * summation order. */
+int qimg_set_vae_conv_variant(int variant);
 int qimg_vae_rms_act(const float* x, const float* gamma, float* y, long long rows, int C, int silu, qimg_stream_t stream);
 int qimg_vae_upsample2x(const float* x, float* out, int N, int H, int W, int C, qimg_stream_t stream);
 int qimg_vae_post_quant(const float* z, const float* w, const float* b, float* out, int N, int H, int W, int z_dim,

@@ -38,9 +38,20 @@ def nhwc(t):  # [N, C, H, W] -> [N, H, W, C] contiguous
     return t.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.mark.parametrize("N,H,W,cin,cout", [(1, 8, 16, 32, 128), (2, 19, 23, 96, 96), (1, 40, 36, 384, 192), (1, 16, 32, 192, 384)],
-                         ids=["one-tile", "ragged-96", "384to192", "192to384"])
-def test_conv3x3_tf32_vs_fp32(N, H, W, cin, cout):
+@pytest.fixture(params=[0, 1], ids=["shared-dy-taps", "box-per-tap"])
+def conv_variant(request):
+    """Both implicit-GEMM kernels: the default (one TMA box per horizontal tap shared by the three vertical taps, 16 x 16
+    pixel patches) and the first version (one box per tap, 16 x 8 patches)."""
+    q.set_vae_conv_variant(request.param)
+    yield request.param
+    q.set_vae_conv_variant(0)
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout", [(1, 8, 16, 32, 128), (2, 19, 23, 96, 96), (1, 40, 36, 384, 192), (1, 16, 32, 192, 384),
+                                            (4, 128, 160, 32, 96), (4, 128, 160, 32, 192), (4, 122, 166, 32, 128)],
+                         ids=["one-tile", "ragged-96", "384to192", "192to384", "256px-tiles-n96", "256px-tiles-n192-one-acc-stage",
+                              "256px-tiles-n128-ragged"])
+def test_conv3x3_tf32_vs_fp32(N, H, W, cin, cout, conv_variant):
     g = gen(H * 1000 + W)
     x = torch.randn(N, cin, H, W, generator=g)
     w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
@@ -53,20 +64,30 @@ def test_conv3x3_tf32_vs_fp32(N, H, W, cin, cout):
     assert rel(got.cpu().permute(0, 3, 1, 2), want + res) < TOL_TF32
 
 
-def test_conv3x3_padding_is_zero_fill_at_every_border():
+def test_conv3x3_padding_is_zero_fill_at_every_border(conv_variant):
     """An all-ones image through an all-ones 3x3 kernel counts the taps that meet data: 4 in the corners, 6 on the edges,
     9 inside — exact in TF32, so any tap read from outside the image (or from the neighbouring image of the batch) shows."""
-    N, H, W, C = 2, 11, 21, 32
-    x = torch.ones(N, H, W, C, device=dev)
-    w = torch.zeros(4, 9 * C, device=dev)
-    w[:, ::C] = 1.0  # channel 0 of every tap
+    for N, H, W, C in ((2, 11, 21, 32), (4, 120, 170, 32)):  # the second shape is large enough for 16 x 16 patches per CTA
+        x = torch.ones(N, H, W, C, device=dev)
+        w = torch.zeros(4, 9 * C, device=dev)
+        w[:, ::C] = 1.0  # channel 0 of every tap
+        got = q.conv2d_nhwc_tf32(x, w, None, 9, 4).cpu()
+        want = F.conv2d(torch.ones(N, 1, H, W), torch.ones(1, 1, 3, 3), padding=1).permute(0, 2, 3, 1).expand(N, H, W, 4)
+        assert torch.equal(got, want)
+    # a kernel that distinguishes the taps: tap t weighs 2^t, so the sum names exactly which taps met data
+    x = torch.ones(1, 24, 40, 32, device=dev)
+    w = torch.zeros(4, 9 * 32, device=dev)
+    for t in range(9):
+        w[:, t * 32] = 2.0 ** t
     got = q.conv2d_nhwc_tf32(x, w, None, 9, 4).cpu()
-    want = F.conv2d(torch.ones(N, 1, H, W), torch.ones(1, 1, 3, 3), padding=1).permute(0, 2, 3, 1).expand(N, H, W, 4)
+    kern = (2.0 ** torch.arange(9.0)).view(1, 1, 3, 3)
+    want = F.conv2d(torch.ones(1, 1, 24, 40), kern, padding=1).permute(0, 2, 3, 1).expand(1, 24, 40, 4)
     assert torch.equal(got, want)
 
 
-@pytest.mark.parametrize("P_h,P_w,K,Nout", [(8, 16, 384, 1152), (18, 22, 396, 384), (16, 16, 64, 256)], ids=["qkv", "k-tail-396", "small"])
-def test_gemm_mode_1x1_vs_fp32(P_h, P_w, K, Nout):
+@pytest.mark.parametrize("P_h,P_w,K,Nout", [(8, 16, 384, 1152), (18, 22, 396, 384), (16, 16, 64, 256), (64, 64, 200, 4096)],
+                         ids=["qkv", "k-tail-396", "small", "scores-256px-tiles"])
+def test_gemm_mode_1x1_vs_fp32(P_h, P_w, K, Nout, conv_variant):
     """taps = 1: out[pixels, Nout] = x[pixels, K] w[Nout, K]^T, including a K that is no multiple of the 32-float K block
     (the P*V product of a 18 x 22 latent: 396 keys) and strided operands (channel slices of a wider buffer)."""
     g = gen(K)
@@ -93,9 +114,10 @@ def test_row_kernels_match_torch():
     x = torch.randn(2, 5, 7, 96, generator=g)
     want = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=(2.0, 2.0), mode="nearest-exact").permute(0, 2, 3, 1)
     assert torch.equal(q.vae_upsample2x(x.to(dev)).cpu(), want)
-    s = torch.randn(37, 396, generator=g) * 20
-    want = torch.softmax(s * 0.051, dim=-1)
-    assert (q.vae_softmax_rows(s.to(dev), 0.051).cpu() - want).abs().max().item() < 2e-6
+    for cols in (396, 397, 30000):  # float4 rows in shared memory, scalar rows, rows too long for shared memory
+        s = torch.randn(37, cols, generator=g) * 20
+        want = torch.softmax(s * 0.051, dim=-1)
+        assert (q.vae_softmax_rows(s.to(dev), 0.051).cpu() - want).abs().max().item() < 2e-6
     t = torch.randn(70, 1152, generator=g)
     assert torch.equal(q.vae_transpose(t.to(dev)[:, 768:]).cpu(), t[:, 768:].T.contiguous())
     z = torch.randn(2, 16, 9, 13, generator=g)

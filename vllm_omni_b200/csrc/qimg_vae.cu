@@ -18,6 +18,7 @@
 //     convolution fused with the clamp and the NHWC -> NCHW change; N = 3 is no tensor-core shape).
 #include "../../include/qimg_b200.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "qimg_common.cuh"
@@ -265,35 +266,309 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// v2: the same implicit GEMM with 2.3x fewer operand bytes per MAC.  v1 above is bound by L2 -> shared-memory operand
+// delivery (~14.5 TB/s at every layer shape, profiles/r02_vae_ncu_summary.md): every tap re-fetches the activation patch and
+// every 128-pixel tile re-streams the weights.  Here
+//   * ONE TMA box {32 channels, 8 x, 18 y} per (horizontal tap, channel block) serves all THREE vertical taps: rows of the
+//     box are ordered x fastest, so every image row is one 8-row SWIZZLE_128B group (1024 B) and the view shifted by dy is
+//     simply the K-major descriptor started (dy + 1) * 1024 B further — no copy, no extra load;
+//   * a CTA owns MT = 2 such 8 x 16 pixel blocks (a 16 x 16 patch, two TMEM accumulators per stage) that share every weight
+//     tile in shared memory, so weights are streamed once per 256 pixels.
+//   * the tile is BN = 96 / 128 / 192 output channels wide — the decoder's layers are 96, 192 and 384 wide, so no MMA column
+//     is padding (at BN = 128 a 96-wide layer wastes a quarter and a 192-wide layer a third of the tensor-pipe time).
+//   Rings: weight tiles in an NB-slot mbarrier ring (5 x 16 KB, or 4 x 24 KB at BN = 192), one slot per (tap, channel block)
+//   unit; activation boxes in an NA-slot ring (3, or 2 at BN = 192) filled together with the first unit of their group
+//   (dy = -1) and released implicitly: unit u waits for the completion of unit u - NB before its slot is refilled, and
+//   tcgen05.commit orders all earlier MMAs, so when group g's boxes are loaded every MMA of group g - NA has retired
+//   (its last unit 3 (g - NA) + 2 <= 3 g - NB  <=>  NB <= 3 NA - 2).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int C2_NB_MAX = 5;
+constexpr int C2_BOX9_BYTES = 18 * 8 * CONV_BK * 4;    // 18 KB: {32 ch, 8 x, 18 y}
+constexpr int C2_BOX1_BYTES = 16 * 8 * CONV_BK * 4;    // 16 KB: {32 ch, 8 x, 16 y}
+// ring sizes by tile width: weight slots of BN x 128 B; BN = 192 trades one slot of each ring for the wider tile
+// (4 <= 3 * 2 - 2 keeps the implicit release of the activation slots valid, see above)
+__host__ __device__ constexpr int c2_b_slot(int BN) { return (BN > 128 ? 192 : 128) * CONV_BK * 4; }
+__host__ __device__ constexpr int c2_nb(int BN) { return BN > 128 ? 4 : 5; }
+__host__ __device__ constexpr int c2_na(int BN) { return BN > 128 ? 2 : 3; }
+__host__ __device__ constexpr int c2_a_region(int BN) { return c2_na(BN) * 2 * C2_BOX9_BYTES; }
+__host__ __device__ constexpr int c2_smem_bytes(int BN) {
+  return c2_a_region(BN) + c2_nb(BN) * c2_b_slot(BN) + CONV_EPI_BYTES + 1024 + 256;
+}
+static_assert(c2_smem_bytes(128) <= 232448 && c2_smem_bytes(192) <= 232448, "shared memory");
+
+struct Conv2Tile {
+  int n, x0, y0, n_blk;
+};
+template <int MT>
+__device__ __forceinline__ Conv2Tile conv2_decode_tile(const ConvParams& P, int tile) {
+  Conv2Tile t;
+  const int m_tile = tile / P.n_tiles;
+  t.n_blk = tile - m_tile * P.n_tiles;
+  const int per_img = P.tiles_x * P.tiles_y;
+  t.n = m_tile / per_img;
+  const int rem = m_tile - t.n * per_img;
+  const int ty = rem / P.tiles_x;
+  t.y0 = ty * 16;
+  t.x0 = (rem - ty * P.tiles_x) * (8 * MT);
+  return t;
+}
+
+// BN = output channels per tile = N of the MMA (96 / 128 / 192: the decoder's widths are 96, 192, 384 — no padded columns);
+// ACC = TMEM accumulator stages (2 = the epilogue of tile i overlaps the main loop of tile i + 1; MT * BN * ACC <= 512).
+template <int MT, int BN, int ACC>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvParams P) {
+  static_assert(BN % 32 == 0 && BN <= 192 && MT * BN * ACC <= 512, "tile");
+  constexpr int TMEM_COLS = (MT * BN * ACC <= 256) ? 256 : 512;
+  constexpr uint32_t IDESC = make_idesc_tf32(CONV_BM, BN);
+  constexpr int B_TILE_BYTES = BN * CONV_BK * 4;
+  constexpr int B_SLOT = c2_b_slot(BN), NB9 = c2_nb(BN), NA9 = c2_na(BN), A_REGION = c2_a_region(BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + A_REGION;
+  uint8_t* smem_epi = smem_b + NB9 * B_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + CONV_EPI_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C2_NB_MAX;
+  uint64_t* tmem_full = bars + 2 * C2_NB_MAX;
+  uint64_t* tmem_empty = bars + 2 * C2_NB_MAX + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C2_NB_MAX + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C2_NB_MAX; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // ring geometry (see the header comment): 3x3 -> groups of G = 3 units sharing one activation slot; 1x1 -> G = 1
+  const bool k3 = P.taps == 9;
+  const int G = k3 ? 3 : 1;
+  const int a_box = k3 ? C2_BOX9_BYTES : C2_BOX1_BYTES;
+  const int a_slot = MT * a_box;
+  const int na1 = A_REGION / a_slot < NB9 ? A_REGION / a_slot : NB9;
+  const int NA = k3 ? NA9 : na1;
+  const int NB = k3 ? NB9 : na1;  // G = 1: a unit's activation slot is free once unit u - NB retired -> NB <= NA
+  const int ngroups = G * P.cin_blocks;  // 3x3: (dx, channel block); 1x1: channel block
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int bs = 0, as = 0;
+    uint32_t bph = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const Conv2Tile t = conv2_decode_tile<MT>(P, tile);
+      int dxi = 0, cb = 0;
+      for (int g = 0; g < ngroups; ++g) {
+        for (int d = 0; d < G; ++d) {
+          mbar_wait(&empty_bar[bs], bph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[bs], B_TILE_BYTES + (d == 0 ? a_slot : 0));
+            if (d == 0) {
+              uint8_t* sa = smem_a + as * a_slot;
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                tma_load_4d(sa + m * a_box, &tmA, &full_bar[bs], cb * CONV_BK, t.x0 + 8 * m + (k3 ? dxi - 1 : 0),
+                            t.y0 - (k3 ? 1 : 0), t.n);
+            }
+            const int tap = k3 ? d * 3 + dxi : 0;  // (ky, kx) = (d, dxi)
+            tma_load_2d(smem_b + bs * B_SLOT, &tmB, &full_bar[bs], (tap * P.cin_blocks + cb) * CONV_BK, t.n_blk * BN);
+          }
+          __syncwarp();
+          if (++bs == NB) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
+        if (++as == NA) as = 0;
+        if (++cb == P.cin_blocks) {
+          cb = 0;
+          ++dxi;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int bs = 0, as = 0;
+    uint32_t bph = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * MT * BN;
+      for (int g = 0; g < ngroups; ++g) {
+        for (int d = 0; d < G; ++d) {
+          mbar_wait(&full_bar[bs], bph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem_a + as * a_slot) + (k3 ? d * 1024 : 0);  // the dy view: one image row = 1024 B
+            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem_b + bs * B_SLOT));
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              const uint64_t adesc = make_kmajor_sw128_desc(sa + m * a_box);
+#pragma unroll
+              for (int k = 0; k < CONV_BK / 8; ++k)
+                umma_ss_tf32(d_tmem + m * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (g | d | k) != 0);
+            }
+            umma_commit(&empty_bar[bs]);
+            if (g == ngroups - 1 && d == G - 1) umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++bs == NB) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
+        if (++as == NA) as = 0;
+      }
+      if (++acc == ACC) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps: warp (q, half) owns accumulator rows q*32..+32 and half of the 32-column steps ====
+    constexpr int STEPS = BN / 32, STEPS0 = (STEPS + 1) / 2;
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    const int step_lo = half ? STEPS0 : 0, step_hi = half ? STEPS : STEPS0;
+    const uint32_t stg = smem_u32(smem_epi + ew * 4096);
+    const float* __restrict__ resp = P.res;
+    float* __restrict__ outp = P.out;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const Conv2Tile t = conv2_decode_tile<MT>(P, tile);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        // the 8 rows this lane stores: accumulator row r = q*32 + it*4 + lane/8 is pixel (x0 + 8m + r % 8, y0 + r / 8)
+        int pix[8];  // N * H * W < 2^31 (checked by the launcher)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rl = q * 32 + it * 4 + (lane >> 3);
+          const int x = t.x0 + 8 * m + (rl & 7), y = t.y0 + (rl >> 3);
+          pix[it] = (x < P.W && y < P.H) ? (t.n * P.H + y) * P.W + x : -1;
+        }
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MT + m) * BN;
+#pragma unroll 1
+        for (int step = step_lo; step < step_hi; ++step) {
+          const int col = step * 32;
+          const int n0 = t.n_blk * BN + col;
+          if (n0 >= P.Cout) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + col, r);
+          const int c16 = lane & 7;
+          const int gn = n0 + c16 * 4;
+          const bool cok = gn < P.Cout;
+          // residual rows are fetched while the TMEM read is in flight, all eight before any store (independent loads)
+          float4 rv[8];
+          if (resp) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              rv[it] = (cok && pix[it] >= 0) ? __ldg(reinterpret_cast<const float4*>(resp + (size_t)pix[it] * P.ldr + gn))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (P.bias && cok) bv = __ldg(reinterpret_cast<const float4*>(P.bias + gn));
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(r[j * 4], r[j * 4 + 1], r[j * 4 + 2], r[j * 4 + 3]));
+          __syncwarp();
+          if (cok) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3);
+              const uint4 v = lds_v4(stg + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+              if (pix[it] >= 0) {
+                float4 o = make_float4(__uint_as_float(v.x) + bv.x, __uint_as_float(v.y) + bv.y, __uint_as_float(v.z) + bv.z,
+                                       __uint_as_float(v.w) + bv.w);
+                if (resp) {
+                  o.x += rv[it].x; o.y += rv[it].y; o.z += rv[it].z; o.w += rv[it].w;
+                }
+                *reinterpret_cast<float4*>(outp + (size_t)pix[it] * P.ldo + gn) = o;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // bandwidth-bound row kernels (fp32)
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
 
 // QwenImageRMS_norm (autoencoder_kl_qwenimage.py:102-109): F.normalize(x, dim=channel) * sqrt(C) * gamma, then optional SiLU
-// (:246-247,262-263,640-641).  One warp per pixel, C <= 32 * 12.
-__global__ void vae_rms_act_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ y,
-                                   long long rows, int C, int silu) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+// (:246-247,262-263,640-641).  A warp normalises 12 / CPL pixels per iteration (CPL = C / 32 values per lane and pixel):
+// always 12 independent 128-byte-per-warp loads in flight per thread (one pixel at a time ran at 40 % of HBM bandwidth).
+template <int CPL>
+__global__ void __launch_bounds__(256) vae_rms_act_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          float* __restrict__ y, long long rows, int silu) {
+  constexpr int C = CPL * 32, PIX = 12 / CPL;
   const int lane = threadIdx.x & 31;
-  const float* xr = x + row * C;
-  float v[12];
-  float ss = 0.f;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float g[CPL];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    const int c = lane + i * 32;
-    v[i] = c < C ? xr[c] : 0.f;
-    ss = fmaf(v[i], v[i], ss);
-  }
-  ss = warp_sum(ss);
-  const float s = sqrtf((float)C) / fmaxf(sqrtf(ss), 1e-12f);
-  float* yr = y + row * C;
+  for (int i = 0; i < CPL; ++i) g[i] = __ldg(gamma + lane + i * 32);
+  const float sc = sqrtf((float)C);
+  for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PIX; r0 < rows; r0 += nwarps * PIX) {
+    float v[PIX][CPL];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    const int c = lane + i * 32;
-    if (c < C) {
-      const float o = v[i] * s * __ldg(gamma + c);
-      yr[c] = silu ? silu_exact(o) : o;
+    for (int p = 0; p < PIX; ++p)
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[p][i] = (r0 + p < rows) ? x[(r0 + p) * C + lane + i * 32] : 0.f;
+#pragma unroll
+    for (int p = 0; p < PIX; ++p) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) ss = fmaf(v[p][i], v[p][i], ss);
+      ss = warp_sum(ss);
+      const float s = sc / fmaxf(sqrtf(ss), 1e-12f);
+      if (r0 + p < rows) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const float o = v[p][i] * s * g[i];
+          y[(r0 + p) * C + lane + i * 32] = silu ? silu_exact(o) : o;
+        }
+      }
     }
   }
 }
@@ -344,64 +619,133 @@ __global__ void vae_post_quant_kernel(const float* __restrict__ z, const float* 
   }
 }
 
-// conv_out (:656; 3x3, C -> 3 channels) + clamp(-1, 1) (:857) + NHWC -> NCHW.  x is the normalised, SiLU-activated input.
-// FMA pipe, exact fp32: one thread per output pixel, weights [3][9][C] in shared memory.
+// conv_out (:656; 3x3, C -> 3 channels) + clamp(-1, 1) (:857) + NHWC -> NCHW (and / or the uint8 post-process).  x is the
+// normalised, SiLU-activated input.  FMA pipe, exact fp32 (three output channels are no tensor-core shape).  A block of 128
+// threads owns a 32 x 16 pixel tile; per 32-channel chunk the (32 + 2) x (16 + 2) input patch is staged in shared memory
+// (pixel stride 36 floats: conflict-free 128-bit reads across a quarter warp) with that chunk's weights [3][9][32]; a thread
+// computes 4 vertically adjacent pixels x 3 channels (12 accumulators), holding the 9 weight vectors of one kernel column in
+// registers while it walks the 6 input rows: 9.6 FMA per shared-memory load.
+constexpr int CO_TX = 32, CO_TY = 16, CO_PITCH = 36;
+constexpr int CO_PATCH = (CO_TX + 2) * (CO_TY + 2);
+constexpr int CO_SMEM_BYTES = CO_PATCH * CO_PITCH * 4 + 3 * 9 * 32 * 4;
+
 template <int C>
-__global__ void vae_conv_out_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                    float* __restrict__ out, uint8_t* __restrict__ out_u8, int N, int H, int W) {
-  __shared__ float4 sw[3 * 9 * C / 4];
-  for (int i = threadIdx.x; i < 3 * 9 * C / 4; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
-  __syncthreads();
-  const int xx = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int yy = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int n = blockIdx.z;
-  if (xx >= W || yy >= H) return;
-  float a0 = b[0], a1 = b[1], a2 = b[2];
+__global__ void __launch_bounds__(128) vae_conv_out_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float* __restrict__ out,
+                                                           uint8_t* __restrict__ out_u8, int N, int H, int W) {
+  extern __shared__ float4 co_smem[];
+  float* sx = reinterpret_cast<float*>(co_smem);             // [CO_PATCH][CO_PITCH]
+  float* sw = sx + CO_PATCH * CO_PITCH;                      // [3][9][32]
+  const int tid = threadIdx.x, tx = tid & 31, ty4 = tid >> 5;
+  const int x0 = blockIdx.x * CO_TX, y0 = blockIdx.y * CO_TY, n = blockIdx.z;
+  float acc[4][3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    acc[j][0] = b[0];
+    acc[j][1] = b[1];
+    acc[j][2] = b[2];
+  }
 #pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int y = yy + tap / 3 - 1, xq = xx + tap % 3 - 1;
-    if (y < 0 || y >= H || xq < 0 || xq >= W) continue;
-    const float4* xp = reinterpret_cast<const float4*>(x + (((long long)n * H + y) * W + xq) * C);
-    const float4* w0 = sw + (0 * 9 + tap) * (C / 4);
-    const float4* w1 = sw + (1 * 9 + tap) * (C / 4);
-    const float4* w2 = sw + (2 * 9 + tap) * (C / 4);
-#pragma unroll 4
-    for (int c = 0; c < C / 4; ++c) {
-      const float4 v = __ldg(xp + c);
-      const float4 u0 = w0[c], u1 = w1[c], u2 = w2[c];
-      a0 = fmaf(v.x, u0.x, fmaf(v.y, u0.y, fmaf(v.z, u0.z, fmaf(v.w, u0.w, a0))));
-      a1 = fmaf(v.x, u1.x, fmaf(v.y, u1.y, fmaf(v.z, u1.z, fmaf(v.w, u1.w, a1))));
-      a2 = fmaf(v.x, u2.x, fmaf(v.y, u2.y, fmaf(v.z, u2.z, fmaf(v.w, u2.w, a2))));
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    __syncthreads();  // previous chunk fully consumed
+    for (int i = tid; i < CO_PATCH * 8; i += 128) {
+      const int p = i >> 3, c4 = i & 7;
+      const int py = p / (CO_TX + 2), px = p - py * (CO_TX + 2);
+      const int gy = y0 + py - 1, gx = x0 + px - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = __ldg(reinterpret_cast<const float4*>(x + (((long long)n * H + gy) * W + gx) * C + c0) + c4);
+      *reinterpret_cast<float4*>(sx + p * CO_PITCH + c4 * 4) = v;
+    }
+    for (int i = tid; i < 3 * 9 * 32; i += 128) {
+      const int co_tap = i >> 5, c = i & 31;
+      sw[i] = w[co_tap * C + c0 + c];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c4 = 0; c4 < 8; ++c4) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float4 wv[3][3];  // [ky][co]
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int co = 0; co < 3; ++co)
+            wv[ky][co] = *reinterpret_cast<const float4*>(sw + ((co * 9 + ky * 3 + kx) << 5) + c4 * 4);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const float4 v = *reinterpret_cast<const float4*>(sx + ((ty4 * 4 + r) * (CO_TX + 2) + tx + kx) * CO_PITCH + c4 * 4);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int j = r - ky;
+            if (j >= 0 && j < 4) {
+#pragma unroll
+              for (int co = 0; co < 3; ++co) {
+                const float4 u = wv[ky][co];
+                acc[j][co] = fmaf(v.x, u.x, fmaf(v.y, u.y, fmaf(v.z, u.z, fmaf(v.w, u.w, acc[j][co]))));
+              }
+            }
+          }
+        }
+      }
     }
   }
-  a0 = fminf(fmaxf(a0, -1.f), 1.f);
-  a1 = fminf(fmaxf(a1, -1.f), 1.f);
-  a2 = fminf(fmaxf(a2, -1.f), 1.f);
-  const long long hw = (long long)H * W, pix = (long long)yy * W + xx;
-  if (out) {
-    const long long o = (long long)n * 3 * hw + pix;
-    out[o] = a0;
-    out[o + hw] = a1;
-    out[o + 2 * hw] = a2;
-  }
-  if (out_u8) {
-    // VaeImageProcessor.postprocess (the reference's post_process_func, pipeline_qwen_image.py:40-60): denormalise
-    // (x / 2 + 0.5).clamp(0, 1), NHWC, (x * 255).round() -> uint8; the same fp32 operations, rint = numpy's half-to-even
-    uint8_t* o = out_u8 + ((long long)n * hw + pix) * 3;
-    o[0] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a0, 0.5f), 0.5f), 0.f), 1.f), 255.f));
-    o[1] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a1, 0.5f), 0.5f), 0.f), 1.f), 255.f));
-    o[2] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a2, 0.5f), 0.5f), 0.f), 1.f), 255.f));
+  const int xx = x0 + tx;
+  if (xx >= W) return;
+  const long long hw = (long long)H * W;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yy = y0 + ty4 * 4 + j;
+    if (yy >= H) break;
+    const float a0 = fminf(fmaxf(acc[j][0], -1.f), 1.f);
+    const float a1 = fminf(fmaxf(acc[j][1], -1.f), 1.f);
+    const float a2 = fminf(fmaxf(acc[j][2], -1.f), 1.f);
+    const long long pix = (long long)yy * W + xx;
+    if (out) {
+      const long long o = (long long)n * 3 * hw + pix;
+      out[o] = a0;
+      out[o + hw] = a1;
+      out[o + 2 * hw] = a2;
+    }
+    if (out_u8) {
+      // VaeImageProcessor.postprocess (the reference's post_process_func, pipeline_qwen_image.py:40-60): denormalise
+      // (x / 2 + 0.5).clamp(0, 1), NHWC, (x * 255).round() -> uint8; the same fp32 operations, rint = numpy's half-to-even
+      uint8_t* o = out_u8 + ((long long)n * hw + pix) * 3;
+      o[0] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a0, 0.5f), 0.5f), 0.f), 1.f), 255.f));
+      o[1] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a1, 0.5f), 0.5f), 0.f), 1.f), 255.f));
+      o[2] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(a2, 0.5f), 0.5f), 0.f), 1.f), 255.f));
+    }
   }
 }
 
-// in-place row softmax of fp32 scores (F.scaled_dot_product_attention of the mid-block attention, :321): one CTA per row
+// in-place row softmax of fp32 scores (F.scaled_dot_product_attention of the mid-block attention, :321): one CTA per row.
+// SMEM = 1: the row is staged in shared memory (one global read, one write); SMEM = 0: three passes over global memory
+// (rows longer than the shared memory holds).  T = float4 when the row length and stride allow it.
+__device__ __forceinline__ float vmax(float v) { return v; }
+__device__ __forceinline__ float vmax(float4 v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
+__device__ __forceinline__ float vexp(float& v, float m, float sc) { v = expf((v - m) * sc); return v; }
+__device__ __forceinline__ float vexp(float4& v, float m, float sc) {
+  v.x = expf((v.x - m) * sc); v.y = expf((v.y - m) * sc); v.z = expf((v.z - m) * sc); v.w = expf((v.w - m) * sc);
+  return (v.x + v.y) + (v.z + v.w);
+}
+__device__ __forceinline__ float vscale(float v, float a) { return v * a; }
+__device__ __forceinline__ float4 vscale(float4 v, float a) { return make_float4(v.x * a, v.y * a, v.z * a, v.w * a); }
+
+template <int SMEM, typename T>
 __global__ void vae_softmax_rows_kernel(float* __restrict__ s, int cols, long long ld, float scale) {
-  float* row = s + (long long)blockIdx.x * ld;
+  extern __shared__ float4 srow4[];
+  T* srow = reinterpret_cast<T*>(srow4);
+  T* row = reinterpret_cast<T*>(s + (long long)blockIdx.x * ld);
+  const int n = cols / (int)(sizeof(T) / 4);
   __shared__ float red[32];
   __shared__ float bc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float m = -INFINITY;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, row[c]);
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const T v = row[c];
+    if (SMEM) srow[c] = v;
+    m = fmaxf(m, vmax(v));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if (lane == 0) red[warp] = m;
@@ -415,10 +759,10 @@ __global__ void vae_softmax_rows_kernel(float* __restrict__ s, int cols, long lo
   __syncthreads();
   m = bc;
   float sum = 0.f;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float e = expf((row[c] - m) * scale);
-    row[c] = e;
-    sum += e;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {  // every thread revisits the elements it staged itself
+    T v = SMEM ? srow[c] : row[c];
+    sum += vexp(v, m, scale);
+    if (SMEM) srow[c] = v; else row[c] = v;
   }
   sum = warp_sum(sum);
   __syncthreads();
@@ -431,7 +775,7 @@ __global__ void vae_softmax_rows_kernel(float* __restrict__ s, int cols, long lo
   }
   __syncthreads();
   const float inv = 1.0f / bc;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) row[c] *= inv;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) row[c] = vscale(SMEM ? srow[c] : row[c], inv);
 }
 
 // out[c, r] = in[r * ld_in + c]  (V^T for the P*V GEMM: both tcgen05 operands K-major)
@@ -486,15 +830,25 @@ static int encode_f32(CUtensorMap* tm, int rank, const void* ptr, const cuuint64
   return 0;
 }
 
-static int conv_smem_attr() {
-  static bool done[64] = {};
+template <typename K>
+static int conv_smem_attr(K kernel, int bytes, bool (&done)[64]) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail("no CUDA device");
   if (!done[dev]) {
-    QIMG_CUDA_CHECK(cudaFuncSetAttribute(conv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
+    QIMG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     done[dev] = true;
   }
   return 0;
+}
+
+// 0 = v2 (shared vertical taps + 256-pixel tiles; default), 1 = v1 (one box per tap, 128-pixel tiles): env QIMG_VAE_CONV
+static int g_conv_variant = -1;
+static int conv_variant() {
+  if (g_conv_variant < 0) {
+    const char* e = getenv("QIMG_VAE_CONV");
+    g_conv_variant = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return g_conv_variant;
 }
 
 }  // namespace qimg
@@ -518,17 +872,28 @@ int qimg_conv2d_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, cons
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out) |
        reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(bias)) & 15)
     return fail("qimg_conv2d_nhwc_tf32: pointers must be 16-byte aligned");
+  const int sms = device_sm_count();
+  if (sms <= 0) return fail("no CUDA device");
+  const int variant = conv_variant();
+  // v2 tile: BN output channels (96 / 192 for the decoder's 96-, 192- and 384-wide layers: no padded MMA columns; 128 for
+  // everything else), MT 8 x 16 pixel blocks per CTA (2 = a 16 x 16 patch sharing every weight tile, while that still gives
+  // two waves of tiles)
+  const int BN = variant == 1 ? CONV_BN : (Cout == 96 ? 96 : ((Cout == 192 || Cout == 384) ? 192 : CONV_BN));
+  const int n_tiles = (Cout + BN - 1) / BN;
+  const long long m2 = (long long)N * ((W + 15) / 16) * ((H + 15) / 16);
+  const int MT = (variant == 0 && m2 * n_tiles >= 2ll * sms) ? 2 : 1;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstr[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
-    cuuint32_t box[4] = {CONV_BK, CONV_PX, CONV_PY, 1};
-    if (encode_f32(&tmA, 4, x, gdim, gstr, box)) return 1;
+    cuuint32_t box1[4] = {CONV_BK, CONV_PX, CONV_PY, 1};
+    cuuint32_t box2[4] = {CONV_BK, 8, (cuuint32_t)(taps == 9 ? 18 : 16), 1};
+    if (encode_f32(&tmA, 4, x, gdim, gstr, variant == 1 ? box1 : box2)) return 1;
   }
   {
     cuuint64_t gdim[2] = {(cuuint64_t)kcols, (cuuint64_t)Cout};
     cuuint64_t gstr[1] = {(cuuint64_t)ldw * 4};
-    cuuint32_t box[2] = {CONV_BK, CONV_BN};
+    cuuint32_t box[2] = {CONV_BK, (cuuint32_t)BN};
     if (encode_f32(&tmB, 2, w, gdim, gstr, box)) return 1;
   }
   ConvParams P;
@@ -538,28 +903,60 @@ int qimg_conv2d_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, cons
   P.taps = taps;
   P.Cout = Cout;
   P.ldo = ldo; P.ldr = ldr;
-  P.tiles_x = (W + CONV_PX - 1) / CONV_PX;
-  P.tiles_y = (H + CONV_PY - 1) / CONV_PY;
-  P.n_tiles = (Cout + CONV_BN - 1) / CONV_BN;
+  if (variant == 1) {
+    P.tiles_x = (W + CONV_PX - 1) / CONV_PX;
+    P.tiles_y = (H + CONV_PY - 1) / CONV_PY;
+  } else {
+    P.tiles_x = (W + 8 * MT - 1) / (8 * MT);
+    P.tiles_y = (H + 15) / 16;
+  }
+  P.n_tiles = n_tiles;
   const long long total = (long long)N * P.tiles_x * P.tiles_y * P.n_tiles;
-  if (total > 0x7fffffffll) return fail("qimg_conv2d_nhwc_tf32: too many tiles");
+  if (total > 0x7fffffffll || (long long)N * H * W > 0x7fffffffll) return fail("qimg_conv2d_nhwc_tf32: too many tiles / pixels");
   P.total_tiles = (int)total;
   P.bias = bias; P.res = res; P.out = out;
-  if (conv_smem_attr()) return 1;
-  const int sms = device_sm_count();
-  if (sms <= 0) return fail("no CUDA device");
   const int grid = P.total_tiles < sms ? P.total_tiles : sms;
-  conv_tf32_kernel<<<grid, CONV_THREADS, CONV_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, P);
+  cudaStream_t st = (cudaStream_t)stream;
+#define QIMG_CONV2_LAUNCH(MT_, BN_, ACC_)                                                                  \
+  do {                                                                                                     \
+    static bool done[64] = {};                                                                             \
+    if (conv_smem_attr(conv2_tf32_kernel<MT_, BN_, ACC_>, c2_smem_bytes(BN_), done)) return 1;             \
+    conv2_tf32_kernel<MT_, BN_, ACC_><<<grid, CONV_THREADS, c2_smem_bytes(BN_), st>>>(tmA, tmB, P);        \
+  } while (0)
+  if (variant == 1) {
+    static bool done[64] = {};
+    if (conv_smem_attr(conv_tf32_kernel, CONV_SMEM_BYTES, done)) return 1;
+    conv_tf32_kernel<<<grid, CONV_THREADS, CONV_SMEM_BYTES, st>>>(tmA, tmB, P);
+  } else if (BN == 96) {
+    if (MT == 2) QIMG_CONV2_LAUNCH(2, 96, 2); else QIMG_CONV2_LAUNCH(1, 96, 2);
+  } else if (BN == 192) {
+    if (MT == 2) QIMG_CONV2_LAUNCH(2, 192, 1); else QIMG_CONV2_LAUNCH(1, 192, 2);  // 2 x 192 x 2 columns exceed TMEM: one stage
+  } else {
+    if (MT == 2) QIMG_CONV2_LAUNCH(2, 128, 2); else QIMG_CONV2_LAUNCH(1, 128, 2);
+  }
+#undef QIMG_CONV2_LAUNCH
   QIMG_LAUNCH_CHECK("conv_tf32_kernel");
   return 0;
 }
 
+int qimg_set_vae_conv_variant(int variant) {
+  if (variant < 0 || variant > 1) return fail("qimg_set_vae_conv_variant: 0 (shared vertical taps, 256-pixel tiles) or 1 (one box per tap)");
+  g_conv_variant = variant;
+  return 0;
+}
+
 int qimg_vae_rms_act(const float* x, const float* gamma, float* y, long long rows, int C, int silu, qimg_stream_t stream) {
-  if (!x || !gamma || !y || rows < 1 || C < 1 || C > 384) return fail("qimg_vae_rms_act: bad arguments (C <= 384)");
-  const int wpb = 8;
-  const long long blocks = (rows + wpb - 1) / wpb;
-  if (blocks > 0x7fffffffll) return fail("qimg_vae_rms_act: too many rows");
-  vae_rms_act_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(x, gamma, y, rows, C, silu);
+  if (!x || !gamma || !y || rows < 1) return fail("qimg_vae_rms_act: bad arguments");
+  if (C != 96 && C != 192 && C != 384) return fail("qimg_vae_rms_act: C must be 96, 192 or 384 (the decoder's channel widths)");
+  const int sms = device_sm_count();
+  if (sms <= 0) return fail("no CUDA device");
+  const int pix = 12 / (C / 32);
+  long long blocks = (rows + 8ll * pix - 1) / (8ll * pix);
+  if (blocks > 8ll * sms) blocks = 8ll * sms;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 96) vae_rms_act_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, y, rows, silu);
+  else if (C == 192) vae_rms_act_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, y, rows, silu);
+  else vae_rms_act_kernel<12><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, y, rows, silu);
   QIMG_LAUNCH_CHECK("vae_rms_act_kernel");
   return 0;
 }
@@ -591,15 +988,33 @@ int qimg_vae_conv_out(const float* x, const float* w, const float* b, float* out
   if (!x || !w || !b || (!out && !out_u8) || N < 1 || H < 1 || W < 1) return fail("qimg_vae_conv_out: bad arguments");
   if (C != 96) return fail("qimg_vae_conv_out: C must be 96 (base_dim of AutoencoderKLQwenImage)");
   if (N > 65535) return fail("qimg_vae_conv_out: N too large");
-  dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-  vae_conv_out_kernel<96><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, out_u8, N, H, W);
+  static bool done[64] = {};
+  if (conv_smem_attr(vae_conv_out_kernel<96>, CO_SMEM_BYTES, done)) return 1;
+  dim3 grid((W + CO_TX - 1) / CO_TX, (H + CO_TY - 1) / CO_TY, N);
+  vae_conv_out_kernel<96><<<grid, 128, CO_SMEM_BYTES, (cudaStream_t)stream>>>(x, w, b, out, out_u8, N, H, W);
   QIMG_LAUNCH_CHECK("vae_conv_out_kernel");
   return 0;
 }
 
 int qimg_vae_softmax_rows(float* s, int rows, int cols, long long ld, float scale, qimg_stream_t stream) {
   if (!s || rows < 1 || cols < 1 || ld < cols) return fail("qimg_vae_softmax_rows: bad arguments");
-  vae_softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(s, cols, ld, scale);
+  const size_t bytes = (size_t)cols * 4;
+  const bool vec = !(cols & 3) && !(ld & 3) && !(reinterpret_cast<uintptr_t>(s) & 15);
+  const bool in_smem = bytes <= 100 * 1024;  // two rows per SM
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_smem && vec) {
+    static bool done[64] = {};
+    if (conv_smem_attr(vae_softmax_rows_kernel<1, float4>, 100 * 1024, done)) return 1;
+    vae_softmax_rows_kernel<1, float4><<<rows, 1024, bytes, st>>>(s, cols, ld, scale);
+  } else if (in_smem) {
+    static bool done[64] = {};
+    if (conv_smem_attr(vae_softmax_rows_kernel<1, float>, 100 * 1024, done)) return 1;
+    vae_softmax_rows_kernel<1, float><<<rows, 1024, bytes, st>>>(s, cols, ld, scale);
+  } else if (vec) {
+    vae_softmax_rows_kernel<0, float4><<<rows, 1024, 0, st>>>(s, cols, ld, scale);
+  } else {
+    vae_softmax_rows_kernel<0, float><<<rows, 1024, 0, st>>>(s, cols, ld, scale);
+  }
   QIMG_LAUNCH_CHECK("vae_softmax_rows_kernel");
   return 0;
 }

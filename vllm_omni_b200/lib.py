@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "qimg_set_nvtx", "qimg_set_gemm_group_m", "qimg_set_fmha_single_tile", "qimg_ln_modulate_rows", "qimg_fmha_joint_sp",
     "qimg_engine_set_sp_p2p", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
     "qimg_conv2d_nhwc_tf32", "qimg_vae_rms_act", "qimg_vae_upsample2x", "qimg_vae_post_quant", "qimg_vae_conv_out",
-    "qimg_vae_softmax_rows", "qimg_vae_transpose",
+    "qimg_vae_softmax_rows", "qimg_vae_transpose", "qimg_set_vae_conv_variant",
 ]
 
 
@@ -143,6 +143,7 @@ def load():
     lib.qimg_umma_probe.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.qimg_conv2d_nhwc_tf32.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, i, i, vp]
     lib.qimg_vae_rms_act.argtypes = [vp, vp, vp, ll, i, i, vp]
+    lib.qimg_set_vae_conv_variant.argtypes = [i]
     lib.qimg_vae_upsample2x.argtypes = [vp, vp, i, i, i, i, vp]
     lib.qimg_vae_post_quant.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     lib.qimg_vae_conv_out.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
@@ -442,6 +443,10 @@ def conv2d_nhwc_tf32(x: torch.Tensor, w: torch.Tensor, bias, taps: int, cout: in
     check(load().qimg_conv2d_nhwc_tf32(_p(x), ldx, _p(w), w.stride(0), _p(bias), _p(res), ldr, _p(out), out.stride(2), N, H, W,
                                        cin, cout, taps, stream_ptr()), "qimg_conv2d_nhwc_tf32")
     return out
+
+
+def set_vae_conv_variant(variant: int):
+    check(load().qimg_set_vae_conv_variant(int(variant)), "qimg_set_vae_conv_variant")
 
 
 def vae_rms_act(x: torch.Tensor, gamma: torch.Tensor, silu: bool, out=None):
