@@ -417,6 +417,7 @@ def main():
         try:
             if world == 1:
                 extras["gpu_eager_baseline"] = eager_gpu_baseline(pipe, lat_d, txt_d, grid, T, L, S_img, B)
+                extras["vae_decode"] = vae_decode_leg(B, res, dev, ms_dev / args.steps)
             else:
                 extras.update(multi_gpu_legs(args, pipe, world, rank, local_rank, dev, barrier))
         except Exception as exc:
@@ -464,6 +465,54 @@ def eager_gpu_baseline(pipe, lat_d, txt_d, grid, T, L, S_img, B) -> dict:
                 out[key.replace("_ms", "_rel_fro_native")] = rel_fro(nat, res_)
         best = min(v for v in (out.get("sdpa_ms"), out.get("flash_attn_ms")) if v)
         out["speedup_vs_best_eager"] = best / out["native_ms"]
+    except Exception as exc:  # never lose the measured line
+        out["error"] = repr(exc)[:300]
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# N = 1: the post-step of the same request — VAE decode of the B images, native tcgen05 TF32 convolutions
+# next to the reference's eager CUDA op sequence (cuDNN TF32 + SDPA, baseline/eager_torch.py) on the same weights / latents
+# --------------------------------------------------------------------------------------------
+def vae_decode_leg(B, res, dev, denoise_ms) -> dict:
+    out = {"workload": f"AutoencoderKLQwenImage decode of {B} latents {res // 8}x{res // 8} -> {res}x{res} px, fp32 NHWC, TF32 tensor "
+                       "cores, synthetic weights; 2 warm-up + 5 timed decodes each"}
+    try:
+        from baseline import eager_torch
+        from vllm_omni_b200 import lib as qlib
+        from vllm_omni_b200 import synthetic
+        from vllm_omni_b200.diffusion.models.qwen_image.vae_decoder import B200VaeDecoder
+        W = synthetic.synthetic_vae_decoder_weights(seed=6)
+        vae = B200VaeDecoder(W, device=dev)
+        z = torch.randn(B, 16, 1, res // 8, res // 8, generator=torch.Generator().manual_seed(1)).to(dev)
+
+        def timed(fn, iters=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters
+
+        n0 = qlib.launch_count()
+        img = vae.decode(z, return_dict=False)[0]
+        out["launches_per_decode"] = qlib.launch_count() - n0
+        out["native_ms"] = timed(lambda: vae.decode(z, return_dict=False))
+        out["native_uint8_ms"] = timed(lambda: vae.decode_to_uint8(z))
+        out["gflop_per_image"] = 4710.2 * (res / 1024) ** 2  # convolution + attention FLOPs (attention part scales faster; 1024 px value)
+        out["native_tflops"] = B * out["gflop_per_image"] / out["native_ms"]
+        out["share_of_request_time"] = out["native_ms"] / (out["native_ms"] + denoise_ms)
+        Wd = {k: v.to(dev) for k, v in W.items()}
+        with torch.no_grad():
+            ref = eager_torch.vae_decode_eager(z, Wd)
+            out["eager_cudnn_tf32_ms"] = timed(lambda: eager_torch.vae_decode_eager(z, Wd))
+        out["speedup_vs_eager"] = out["eager_cudnn_tf32_ms"] / out["native_ms"]
+        out["max_abs_vs_eager"] = float((img - ref).abs().max())
     except Exception as exc:  # never lose the measured line
         out["error"] = repr(exc)[:300]
     torch.cuda.empty_cache()

@@ -282,18 +282,22 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //   tcgen05.commit orders all earlier MMAs, so when group g's boxes are loaded every MMA of group g - NA has retired
 //   (its last unit 3 (g - NA) + 2 <= 3 g - NB  <=>  NB <= 3 NA - 2).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int C2_NB_MAX = 5;
+constexpr int C2_NB_MAX = 7;
 constexpr int C2_BOX9_BYTES = 18 * 8 * CONV_BK * 4;    // 18 KB: {32 ch, 8 x, 18 y}
 constexpr int C2_BOX1_BYTES = 16 * 8 * CONV_BK * 4;    // 16 KB: {32 ch, 8 x, 16 y}
-// ring sizes by tile width: weight slots of BN x 128 B; BN = 192 trades one slot of each ring for the wider tile
-// (4 <= 3 * 2 - 2 keeps the implicit release of the activation slots valid, see above)
-__host__ __device__ constexpr int c2_b_slot(int BN) { return (BN > 128 ? 192 : 128) * CONV_BK * 4; }
-__host__ __device__ constexpr int c2_nb(int BN) { return BN > 128 ? 4 : 5; }
+// Ring sizes by tile width (weight slots of BN x 128 B).  The main loop is bound by TMA round-trip latency x ring depth
+// (~2-3 k cycles under load, profiles/r02_vae_ncu_summary.md), so every configuration fills the 227 KB: BN = 96 -> 7 x 12 KB
+// weight slots + 3 activation slots, BN = 128 -> 5 x 16 KB + 3, BN = 192 -> 4 x 24 KB + 2.  NB <= 3 NA - 2 keeps the
+// implicit release of the activation slots valid (see above).
+__host__ __device__ constexpr int c2_b_slot(int BN) { return BN * CONV_BK * 4; }
+__host__ __device__ constexpr int c2_nb(int BN) { return BN > 128 ? 4 : (BN > 96 ? 5 : 7); }
 __host__ __device__ constexpr int c2_na(int BN) { return BN > 128 ? 2 : 3; }
 __host__ __device__ constexpr int c2_a_region(int BN) { return c2_na(BN) * 2 * C2_BOX9_BYTES; }
 __host__ __device__ constexpr int c2_smem_bytes(int BN) {
   return c2_a_region(BN) + c2_nb(BN) * c2_b_slot(BN) + CONV_EPI_BYTES + 1024 + 256;
 }
+static_assert(c2_smem_bytes(96) <= 232448, "shared memory");
+static_assert(c2_nb(96) <= 3 * c2_na(96) - 2 && c2_nb(128) <= 3 * c2_na(128) - 2 && c2_nb(192) <= 3 * c2_na(192) - 2, "rings");
 static_assert(c2_smem_bytes(128) <= 232448 && c2_smem_bytes(192) <= 232448, "shared memory");
 
 struct Conv2Tile {
