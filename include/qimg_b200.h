@@ -357,6 +357,16 @@ size_t qimg_engine_ws_offset_txt(const qimg_engine* e, int B, int S_img, int T);
  * qimg_vae_transpose      out[c * rows + r] = in[r * ld_in + c] */
 int qimg_conv2d_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, const float* bias, const float* res, int ldr,
                           float* out, int ldo, int N, int H, int W, int Cin, int Cout, int taps, qimg_stream_t stream);
+/* VAE ENCODE side (the edit pipelines' condition image, pipeline_qwen_image_edit.py:458-480 -> AutoencoderKLQwenImage._encode,
+ * autoencoder_kl_qwenimage.py:793-812); it reuses the kernels above plus
+ *   qimg_conv2d_down2_nhwc_tf32   the resamplers of the encoder, nn.ZeroPad2d((0, 1, 0, 1)) + nn.Conv2d(C, C, 3, stride=2)
+ *                                 (:157-161): out[n, y, x, co] = bias + sum_{ky, kx, ci} x[n, 2y + ky, 2x + kx, ci] * w[co, (3 ky + kx) Cin + ci],
+ *                                 input rows / columns beyond the image read as zero.  The TMA descriptor walks x and y with
+ *                                 element stride 2, so the gather costs nothing.  H_in, W_in even; output [N, H_in/2, W_in/2, Cout].
+ *   qimg_vae_image_to_nhwc        NCHW image [N, C <= 32, H, W] -> NHWC [N, H, W, 32], channels >= C zero (K block of conv_in) */
+int qimg_conv2d_down2_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, const float* bias, float* out, int ldo, int N,
+                                int H_in, int W_in, int Cin, int Cout, qimg_stream_t stream);
+int qimg_vae_image_to_nhwc(const float* img, float* out, int N, int C, int H, int W, qimg_stream_t stream);
 /* Kernel variant of qimg_conv2d_nhwc_tf32: 0 (default) = one TMA box per (horizontal tap, channel block) shared by the three
  * vertical taps as shifted descriptor views + 16 x 16 pixel patches per CTA (2.3x fewer operand bytes per MAC);
  * 1 = one box per tap, 16 x 8 patches (the first version, kept for A/B).  Env QIMG_VAE_CONV.  Same results up to fp32

@@ -27,6 +27,12 @@ CASES = {
 }
 
 
+# encode side (edit pipelines' condition image): image size (H, W) with H/8 x W/8 >= 8 x 16
+ENC_CASES = {
+    "vae_encode_ragged": dict(B=2, size=(144, 176), wseed=13, xseed=21),
+}
+
+
 def weights_checksum(w: dict) -> float:
     return float(sum(v.double().abs().sum() for _, v in sorted(w.items())))
 
@@ -49,6 +55,22 @@ def main():
         torch.save({"z": z, "image": ref, "wseed": c["wseed"], "weights_checksum": weights_checksum(W), "oracle_max_abs_err": err},
                    os.path.join(GOLDEN_DIR, name + ".pt"))
         print(f"{name}: image {tuple(ref.shape)} |x| mean {ref.abs().mean():.3f} clamped {clamped:.3f}  oracle-vs-reference max abs {err:.2e}")
+    for name, c in ENC_CASES.items():
+        W = synthetic.synthetic_vae_encoder_weights(seed=c["wseed"])
+        vae = ref_shim.build_reference_vae()
+        missing, unexpected = vae.load_state_dict(W, strict=False)
+        assert not unexpected and all(k.startswith(("decoder.", "post_quant_conv.")) for k in missing), (missing, unexpected)
+        g = torch.Generator().manual_seed(c["xseed"])
+        x = torch.rand(c["B"], 3, 1, *c["size"], generator=g) * 2 - 1
+        with torch.no_grad():
+            dist = vae.encode(x, return_dict=False)[0]  # the reference's own DiagonalGaussianDistribution wrapper is a diffusers class
+        ref = dist.parameters
+        ora = vae_oracle.vae_encode(x, W)
+        err = (ref - ora).abs().max().item()
+        assert err < 1e-4, f"{name}: restatement deviates from the reference by {err}"
+        torch.save({"x": x, "params": ref, "wseed": c["wseed"], "weights_checksum": weights_checksum(W), "oracle_max_abs_err": err},
+                   os.path.join(GOLDEN_DIR, name + ".pt"))
+        print(f"{name}: posterior parameters {tuple(ref.shape)} |mean| {ref[:, :16].abs().mean():.3f}  oracle-vs-reference max abs {err:.2e}")
 
 
 if __name__ == "__main__":

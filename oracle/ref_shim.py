@@ -196,9 +196,14 @@ def _install_diffusers_vae_stub():
         def __init__(self, latent_dist):
             self.latent_dist = latent_dist
 
-    class DiagonalGaussianDistribution:  # encode side only; never constructed on the decode path
+    class DiagonalGaussianDistribution:  # published diffusers semantics: parameters = (mean, logvar) on the channel axis
         def __init__(self, parameters):
+            import torch
             self.parameters = parameters
+            self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+
+        def mode(self):
+            return self.mean
 
     def get_activation(name):
         if name in ("silu", "swish"):

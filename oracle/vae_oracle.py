@@ -74,3 +74,29 @@ def vae_decode(z: torch.Tensor, W: dict, num_up_blocks: int = 4, num_res_blocks:
     x = F.silu(_rms(x, W["decoder.norm_out.gamma"]))
     x = _conv3(x, W["decoder.conv_out.weight"], W["decoder.conv_out.bias"])
     return x.clamp(-1.0, 1.0).unsqueeze(2)
+
+
+def vae_encode(x: torch.Tensor, W: dict, num_down_blocks: int = 11) -> torch.Tensor:
+    """x [B, 3, 1, H, W] image in [-1, 1] -> posterior parameters [B, 2 z_dim, 1, H/8, W/8] (`AutoencoderKLQwenImage._encode`,
+    autoencoder_kl_qwenimage.py:793-812): mean = channels [:z_dim] (what `latent_dist.mode()` / sample_mode="argmax"
+    returns, pipeline_qwen_image_edit.py:467), logvar = the rest.
+
+    One frame, restated like the decode: causal 3x3x3 convolutions reduce to 2-D 3x3 with weight[:, :, 2]; both
+    `downsample2d` and `downsample3d` are ZeroPad2d((0, 1, 0, 1)) + Conv2d(3, stride 2) on the first frame — the time conv
+    of `downsample3d` needs a cached previous frame (:200-211) and the first frame only fills the cache."""
+    assert x.dim() == 5 and x.shape[2] == 1
+    W = {k: v.float() for k, v in W.items()}
+    h = _conv3(x[:, :, 0].float(), W["encoder.conv_in.weight"], W["encoder.conv_in.bias"])
+    for i in range(num_down_blocks):
+        p = f"encoder.down_blocks.{i}"
+        if (p + ".norm1.gamma") in W:
+            h = _resblock(h, W, p)
+        elif (p + ".resample.1.weight") in W:
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), W[p + ".resample.1.weight"], W[p + ".resample.1.bias"], stride=2)
+    h = _resblock(h, W, "encoder.mid_block.resnets.0")
+    h = _attention(h, W, "encoder.mid_block.attentions.0")
+    h = _resblock(h, W, "encoder.mid_block.resnets.1")
+    h = F.silu(_rms(h, W["encoder.norm_out.gamma"]))
+    h = _conv3(h, W["encoder.conv_out.weight"], W["encoder.conv_out.bias"])
+    h = _conv3(h, W["quant_conv.weight"], W["quant_conv.bias"])
+    return h.unsqueeze(2)

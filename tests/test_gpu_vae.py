@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from oracle import vae_oracle
 from vllm_omni_b200 import lib as q
 from vllm_omni_b200 import synthetic
-from vllm_omni_b200.diffusion.models.qwen_image.vae_decoder import B200VaeDecoder, _pack3x3
+from vllm_omni_b200.diffusion.models.qwen_image.vae_decoder import B200AutoencoderKLQwenImage, B200VaeDecoder, _pack3x3
 
 pytestmark = pytest.mark.gpu
 dev = "cuda"
@@ -205,3 +205,124 @@ def test_pipeline_decodes_through_the_native_vae():
     want = vae_oracle.vae_decode(unpacked / std + mean, W)[:, :, 0]
     got = QwenImagePipeline.decode_latents(vae, lat.to(dev), 8 * h, 8 * w)
     _check_image(got.cpu(), want)
+
+
+def test_forward_produces_an_image_end_to_end():
+    """`QwenImagePipeline.forward` from prompt embeddings to pixels with every stage native: DiT denoise (engine) -> unpack
+    -> de-normalise -> VAE decode -> (optionally) the uint8 post-process.  The image equals the fp32 oracle's decode of the
+    latents the same request returns with output_type="latent" (the DiT side has its own goldens)."""
+    from vllm_omni_b200.diffusion.data import OmniDiffusionConfig, TransformerConfig
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image import QwenImagePipeline, get_qwen_image_post_process_func
+    from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+    L, H, joint = 2, 2, 256
+    od = OmniDiffusionConfig(tf_model_config=TransformerConfig.from_dict({"num_layers": L}))
+    W = synthetic.synthetic_vae_decoder_weights(seed=9)
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(dev):
+            pipe = QwenImagePipeline(od_config=od, transformer_kwargs=dict(num_attention_heads=H, joint_attention_dim=joint),
+                                     vae=B200VaeDecoder(W, device=dev))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    pipe.transformer.load_weights(dict(synthetic.synthetic_weights(L, seed=43, norm_jitter=0.1, num_heads=H, joint_dim=joint)).items())
+    g = gen(44)
+    B, hh, ww, T = 2, 8, 16, 24   # 128 x 256 px: latent grid 16 x 32
+    lat = torch.randn(B, hh * ww, 64, generator=g).bfloat16()
+    pe = torch.randn(B, T, joint, generator=g).bfloat16()
+    kw = dict(prompt_embeds=pe, latents=lat, height=hh * 16, width=ww * 16, num_inference_steps=3, true_cfg_scale=1.0)
+    final = pipe.forward(OmniDiffusionRequest(output_type="latent", **kw)).output
+    out = pipe.forward(OmniDiffusionRequest(output_type="pil", **kw))
+    assert out.error is None and out.output.shape == (B, 3, hh * 16, ww * 16) and out.output.dtype == torch.float32
+    unpacked = QwenImagePipeline._unpack_latents(final.cpu(), hh * 16, ww * 16, 8).float()
+    mean = torch.tensor(pipe.vae.config.latents_mean).view(1, 16, 1, 1, 1)
+    std = 1.0 / torch.tensor(pipe.vae.config.latents_std).view(1, 16, 1, 1, 1)
+    want = vae_oracle.vae_decode(unpacked / std + mean, W)[:, :, 0]
+    _check_image(out.output.cpu(), want)
+    pipe.uint8_output = True
+    u8 = pipe.forward(OmniDiffusionRequest(output_type="pil", **kw)).output
+    assert u8.dtype == torch.uint8 and u8.shape == (B, hh * 16, ww * 16, 3)
+    post = get_qwen_image_post_process_func(od)
+    imgs, imgs_u8 = post(out.output), post(u8)
+    assert len(imgs) == B and imgs[0].size == (ww * 16, hh * 16) and all(a.tobytes() == b.tobytes() for a, b in zip(imgs, imgs_u8))
+
+
+# ---- encode side (the edit pipelines' condition image) -----------------------------------------------------------------
+@pytest.mark.parametrize("N,H,W,cin,cout", [(1, 16, 32, 32, 96), (2, 36, 44, 96, 96), (1, 72, 88, 192, 192)],
+                         ids=["one-tile", "ragged", "192"])
+def test_conv3x3_stride2_vs_fp32(N, H, W, cin, cout):
+    """The encoder's resamplers: ZeroPad2d((0, 1, 0, 1)) + Conv2d(3, stride 2) (autoencoder_kl_qwenimage.py:157-161); the
+    stride-2 gather is the TMA descriptor's element stride."""
+    g = gen(H + W)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    want = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+    got = q.conv2d_down2_nhwc_tf32(nhwc(x).to(dev), _pack3x3(w).to(dev), b.to(dev), cout)
+    assert got.shape == (N, H // 2, W // 2, cout)
+    assert rel(got.cpu().permute(0, 3, 1, 2), want) < TOL_TF32
+    # which input pixels a tap meets: weights 2^tap on channel 0, input = a per-pixel code that is exact in TF32
+    xs = torch.zeros(1, 32, 16, 32)
+    xs[0, 0] = (torch.arange(16).view(16, 1) * 32 + torch.arange(32).view(1, 32)).float()  # <= 511: exact in TF32
+    wt = torch.zeros(4, 32, 3, 3)
+    for t in range(9):
+        wt[:, 0, t // 3, t % 3] = 2.0 ** t
+    want = F.conv2d(F.pad(xs, (0, 1, 0, 1)), wt, None, stride=2).permute(0, 2, 3, 1)
+    assert torch.equal(q.conv2d_down2_nhwc_tf32(nhwc(xs).to(dev), _pack3x3(wt).to(dev), None, 4).cpu(), want)
+
+
+def test_image_to_nhwc():
+    img = torch.randn(2, 3, 9, 13, generator=gen(3))
+    got = q.vae_image_to_nhwc(img.to(dev)).cpu()
+    assert torch.equal(got[..., :3], img.permute(0, 2, 3, 1)) and not got[..., 3:].any()
+
+
+def test_encode_matches_reference_golden(golden_dir):
+    """Posterior parameters of the native encoder against the unmodified reference VAE's `encode` (fp32, CPU): TF32 level."""
+    gold = torch.load(os.path.join(golden_dir, "vae_encode_ragged.pt"))
+    W = {**synthetic.synthetic_vae_decoder_weights(seed=1), **synthetic.synthetic_vae_encoder_weights(seed=gold["wseed"])}
+    vae = B200AutoencoderKLQwenImage(W, device=dev)
+    n0 = q.launch_count()
+    dist = vae.encode(gold["x"].to(dev)).latent_dist
+    assert q.launch_count() - n0 > 50
+    assert dist.parameters.shape == gold["params"].shape
+    assert rel(dist.parameters.cpu(), gold["params"]) < 4e-3
+    assert rel(dist.mode().cpu(), gold["params"][:, :16]) < 4e-3
+    # batch items are independent
+    assert torch.equal(vae.encode(gold["x"][1:].to(dev)).latent_dist.parameters, dist.parameters[1:])
+
+
+def test_edit_request_with_a_pixel_image_equals_the_same_request_with_its_latents():
+    """QwenImageEditPipeline.forward with req.extra['image'] (native VAE encode -> normalise -> pack) is bit-identical to the
+    request that carries the condition latents the encoder produces; the latents match the oracle's encode of the image."""
+    from vllm_omni_b200.diffusion.data import OmniDiffusionConfig, TransformerConfig
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image_edit import QwenImageEditPipeline
+    from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+    L, H, joint = 2, 2, 256
+    od = OmniDiffusionConfig(tf_model_config=TransformerConfig.from_dict({"num_layers": L}))
+    W = {**synthetic.synthetic_vae_decoder_weights(seed=1), **synthetic.synthetic_vae_encoder_weights(seed=2)}
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(dev):
+            pipe = QwenImageEditPipeline(od_config=od, transformer_kwargs=dict(num_attention_heads=H, joint_attention_dim=joint),
+                                         vae=B200AutoencoderKLQwenImage(W, device=dev))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    pipe.transformer.load_weights(dict(synthetic.synthetic_weights(L, seed=45, norm_jitter=0.1, num_heads=H, joint_dim=joint)).items())
+    g = gen(46)
+    B, hh, ww, T = 1, 8, 16, 24
+    img = torch.rand(1, 3, 64, 128, generator=g) * 2 - 1      # condition image: latent 8 x 16 -> 4 x 8 patches
+    lat = torch.randn(B, hh * ww, 64, generator=g).bfloat16()
+    pe = torch.randn(B, T, joint, generator=g).bfloat16()
+    kw = dict(prompt_embeds=pe, latents=lat, height=hh * 16, width=ww * 16, num_inference_steps=2, true_cfg_scale=1.0,
+              output_type="latent")
+    out_px = pipe.forward(OmniDiffusionRequest(extra={"image": img}, **kw))
+    assert out_px.error is None
+    il, grid = pipe._encode_vae_image(img)
+    assert grid == (4, 8) and il.shape == (1, 32, 64)
+    out_lat = pipe.forward(OmniDiffusionRequest(extra={"image_latents": il, "image_latent_grid": grid}, **kw))
+    assert torch.equal(out_px.output, out_lat.output)
+    params = vae_oracle.vae_encode(img.unsqueeze(2), W)
+    mean = torch.tensor(pipe.vae.config.latents_mean).view(1, 16, 1, 1, 1)
+    std = torch.tensor(pipe.vae.config.latents_std).view(1, 16, 1, 1, 1)
+    want = QwenImageEditPipeline._pack_latents((params[:, :16] - mean) / std, 1, 16, 8, 16)
+    assert rel(il.float().cpu(), want) < 6e-3  # TF32 convolutions + the bf16 rounding of the packed latents

@@ -524,3 +524,38 @@ def test_post_process_func_is_the_reference_image_arithmetic():
     assert (np.asarray(out[0])[..., 0] == want).all()
     u8 = torch.arange(24, dtype=torch.uint8).view(1, 2, 4, 3)
     assert (np.asarray(post(u8)[0]) == u8[0].numpy()).all()
+
+
+def test_edit_pipeline_encodes_pixel_images_like_the_reference_glue():
+    """`_encode_vae_image` (reference pipeline_qwen_image_edit.py:458-480: posterior mode, (x - mean) / std) followed by
+    `_pack_latents` (:519-522), with a stand-in VAE on the CPU: the packed condition latents and their RoPE grid."""
+    from types import SimpleNamespace
+    from vllm_omni_b200.diffusion.models.qwen_image.pipeline_qwen_image_edit import QwenImageEditPipeline, QwenImageEditPlusPipeline
+    from vllm_omni_b200.diffusion.models.qwen_image.vae_decoder import LATENTS_MEAN, LATENTS_STD, _DiagonalGaussian
+    from vllm_omni_b200.diffusion.request import OmniDiffusionRequest
+
+    class StubVae:
+        config = SimpleNamespace(z_dim=16, latents_mean=LATENTS_MEAN, latents_std=LATENTS_STD)
+
+        def encode(self, x):  # parameters = a fixed function of the image: [B, 32, 1, H/8, W/8]
+            b, _, _, h, w = x.shape
+            p = torch.nn.functional.avg_pool2d(x[:, :, 0], 8).mean(1, keepdim=True).repeat(1, 32, 1, 1)
+            p = p * torch.linspace(0.5, 2.0, 32).view(1, 32, 1, 1)
+            return SimpleNamespace(latent_dist=_DiagonalGaussian(p.unsqueeze(2)))
+
+    pipe = SimpleNamespace(vae=StubVae(), device=torch.device("cpu"), _pack_latents=QwenImageEditPipeline._pack_latents)
+    pipe._encode_vae_image = lambda im: QwenImageEditPipeline._encode_vae_image(pipe, im)
+    img = torch.rand(2, 3, 64, 96) * 2 - 1
+    il, grid = pipe._encode_vae_image(img)
+    assert il.shape == (2, 4 * 6, 64) and il.dtype == torch.bfloat16 and grid == (4, 6)
+    mode = StubVae().encode(img.unsqueeze(2)).latent_dist.mode()
+    want = (mode - torch.tensor(LATENTS_MEAN).view(1, 16, 1, 1, 1)) / torch.tensor(LATENTS_STD).view(1, 16, 1, 1, 1)
+    want = want.view(2, 16, 4, 2, 6, 2).permute(0, 2, 4, 1, 3, 5).reshape(2, 24, 64).bfloat16()
+    assert torch.equal(il, want)
+    shapes = [[(1, 8, 6)]] * 2
+    out, sh = QwenImageEditPipeline._condition_latents(pipe, OmniDiffusionRequest(extra={"image": img}), 2, shapes)
+    assert torch.equal(out, want) and sh == [[(1, 8, 6), (1, 4, 6)]] * 2
+    out, sh = QwenImageEditPlusPipeline._condition_latents(pipe, OmniDiffusionRequest(extra={"image": [img, img[:, :, :32]]}), 2, shapes)
+    assert out.shape == (2, 24 + 12, 64) and sh == [[(1, 8, 6), (1, 4, 6), (1, 2, 6)]] * 2 and torch.equal(out[:, :24], want)
+    with pytest.raises(ValueError, match="can encode"):
+        QwenImageEditPipeline._encode_vae_image(SimpleNamespace(vae=None), img)

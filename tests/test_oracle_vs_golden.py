@@ -148,3 +148,16 @@ def test_vae_oracle_matches_reference_golden(golden_dir, name):
     img = vae_oracle.vae_decode(gold["z"], W)
     assert img.shape == gold["image"].shape
     assert (img - gold["image"]).abs().max().item() < 1e-4
+
+
+def test_vae_encode_oracle_matches_reference_golden(golden_dir):
+    """oracle/vae_oracle.py::vae_encode against the unmodified reference VAE's `encode` (posterior parameters,
+    autoencoder_kl_qwenimage.py:793-836; fixture by oracle/make_golden_vae.py)."""
+    from oracle import vae_oracle
+    gold = torch.load(os.path.join(golden_dir, "vae_encode_ragged.pt"))
+    W = synthetic.synthetic_vae_encoder_weights(seed=gold["wseed"])
+    chk = float(sum(v.double().abs().sum() for v in W.values()))
+    assert abs(chk - gold["weights_checksum"]) < 1e-6 * gold["weights_checksum"]
+    p = vae_oracle.vae_encode(gold["x"], W)
+    assert p.shape == gold["params"].shape == (2, 32, 1, 18, 22)
+    assert (p - gold["params"]).abs().max().item() < 1e-4

@@ -65,6 +65,7 @@ struct ConvParams {
   int N, H, W;       // images, rows, columns (output = input geometry: stride 1, "same" padding)
   int cin_blocks;    // ceil(Cin / 32)
   int taps;          // 9 = 3x3, 1 = 1x1
+  int stride;        // 1, or 2 (v1 kernel only: 3x3 over an input zero-padded by one row / column at the bottom / right)
   int Cout;
   int ldo, ldr;      // pixel strides (floats) of out / res
   int tiles_x, tiles_y, n_tiles, total_tiles;
@@ -139,12 +140,15 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
           uint8_t* sa = smem + stage * CONV_STAGE_BYTES;
           uint8_t* sb = sa + CONV_A_BYTES;
-          const int dy = P.taps == 9 ? tap / 3 - 1 : 0;
-          const int dx = P.taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
+          // stride 1: taps at -1..1 ("same" padding); stride 2: taps at 0..2 of the input pixel (2x, 2y) — the reference's
+          // ZeroPad2d((0, 1, 0, 1)) + Conv2d(3, stride 2) — the tensor map then walks x and y with element stride 2
+          const int off = (P.taps == 9 && P.stride == 1) ? -1 : 0;
+          const int dy = P.taps == 9 ? tap / 3 + off : 0;
+          const int dx = P.taps == 9 ? tap - (tap / 3) * 3 + off : 0;
           mbar_arrive_expect_tx(&full_bar[stage], CONV_STAGE_BYTES);
           // rows of the box: channel fastest, then x, then y -> 128 rows of 128 B = the K-major SWIZZLE_128B A tile;
           // coordinates outside the image (negative or >= W / H) are zero-filled by TMA: the convolution's padding
-          tma_load_4d(sa, &tmA, &full_bar[stage], cb * CONV_BK, t.x0 + dx, t.y0 + dy, t.n);
+          tma_load_4d(sa, &tmA, &full_bar[stage], cb * CONV_BK, t.x0 * P.stride + dx, t.y0 * P.stride + dy, t.n);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * CONV_BK, t.n_blk * CONV_BN);
         }
         __syncwarp();
@@ -623,6 +627,19 @@ __global__ void vae_post_quant_kernel(const float* __restrict__ z, const float* 
   }
 }
 
+// encoder input: NCHW image [N, C <= 32, H, W] -> NHWC [N, H, W, 32] with channels >= C zero (one K block of conv_in)
+__global__ void vae_image_to_nhwc_kernel(const float* __restrict__ img, float* __restrict__ out, int N, int C, int HW) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)N * HW) return;
+  const int n = (int)(p / HW), i = (int)(p - (long long)n * HW);
+  float v[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) v[c] = c < C ? img[((long long)n * C + c) * HW + i] : 0.f;
+  float4* o = reinterpret_cast<float4*>(out + p * 32);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) o[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+}
+
 // conv_out (:656; 3x3, C -> 3 channels) + clamp(-1, 1) (:857) + NHWC -> NCHW (and / or the uint8 post-process).  x is the
 // normalised, SiLU-activated input.  FMA pipe, exact fp32 (three output channels are no tensor-core shape).  A block of 128
 // threads owns a 32 x 16 pixel tile; per 32-channel chunk the (32 + 2) x (16 + 2) input patch is staged in shared memory
@@ -818,10 +835,11 @@ static EncodeTiledFn vae_encode_fn() {
 }
 
 static int encode_f32(CUtensorMap* tm, int rank, const void* ptr, const cuuint64_t* gdim, const cuuint64_t* gstride_bytes,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, int pixel_stride = 1) {
   EncodeTiledFn enc = vae_encode_fn();
   if (!enc) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver / no GPU)");
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // element strides: a box dimension of n * s elements walked with stride s loads n elements (dims 1, 2 = x, y of a 4-D map)
+  cuuint32_t estr[4] = {1, (cuuint32_t)pixel_stride, (cuuint32_t)pixel_stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -905,6 +923,7 @@ int qimg_conv2d_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, cons
   P.N = N; P.H = H; P.W = W;
   P.cin_blocks = cin_blocks;
   P.taps = taps;
+  P.stride = 1;
   P.Cout = Cout;
   P.ldo = ldo; P.ldr = ldr;
   if (variant == 1) {
@@ -940,6 +959,66 @@ int qimg_conv2d_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, cons
   }
 #undef QIMG_CONV2_LAUNCH
   QIMG_LAUNCH_CHECK("conv_tf32_kernel");
+  return 0;
+}
+
+int qimg_conv2d_down2_nhwc_tf32(const float* x, int ldx, const float* w, int ldw, const float* bias, float* out, int ldo, int N,
+                                int H_in, int W_in, int Cin, int Cout, qimg_stream_t stream) {
+  if (!x || !w || !out) return fail("qimg_conv2d_down2_nhwc_tf32: null pointer");
+  if (N < 1 || (H_in & 1) || (W_in & 1) || H_in < 2 * CONV_PY || W_in < 2 * CONV_PX)
+    return fail("qimg_conv2d_down2_nhwc_tf32: needs even H_in >= 16 and W_in >= 32");
+  if (Cin < 32 || (Cin & 31)) return fail("qimg_conv2d_down2_nhwc_tf32: Cin must be a multiple of 32");
+  if (Cout < 1 || (Cout & 3)) return fail("qimg_conv2d_down2_nhwc_tf32: Cout must be a multiple of 4");
+  const int H = H_in / 2, W = W_in / 2, cin_blocks = Cin / CONV_BK;
+  const long long kcols = 9ll * Cin;
+  if (ldx < Cin || (ldx & 3) || ldw < kcols || (ldw & 3) || ldo < Cout || (ldo & 3))
+    return fail("qimg_conv2d_down2_nhwc_tf32: leading dimensions must cover the row and be multiples of 4 floats");
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(bias)) & 15)
+    return fail("qimg_conv2d_down2_nhwc_tf32: pointers must be 16-byte aligned");
+  const int sms = device_sm_count();
+  if (sms <= 0) return fail("no CUDA device");
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W_in, (cuuint64_t)H_in, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W_in * ldx * 4, (cuuint64_t)H_in * W_in * ldx * 4};
+    cuuint32_t box[4] = {CONV_BK, 2 * CONV_PX, 2 * CONV_PY, 1};  // 16 x 8 pixels at element stride 2
+    if (encode_f32(&tmA, 4, x, gdim, gstr, box, 2)) return 1;
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)kcols, (cuuint64_t)Cout};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldw * 4};
+    cuuint32_t box[2] = {CONV_BK, CONV_BN};
+    if (encode_f32(&tmB, 2, w, gdim, gstr, box)) return 1;
+  }
+  ConvParams P;
+  memset(&P, 0, sizeof P);
+  P.N = N; P.H = H; P.W = W;
+  P.cin_blocks = cin_blocks;
+  P.taps = 9;
+  P.stride = 2;
+  P.Cout = Cout;
+  P.ldo = ldo;
+  P.tiles_x = (W + CONV_PX - 1) / CONV_PX;
+  P.tiles_y = (H + CONV_PY - 1) / CONV_PY;
+  P.n_tiles = (Cout + CONV_BN - 1) / CONV_BN;
+  const long long total = (long long)N * P.tiles_x * P.tiles_y * P.n_tiles;
+  if (total > 0x7fffffffll) return fail("qimg_conv2d_down2_nhwc_tf32: too many tiles");
+  P.total_tiles = (int)total;
+  P.bias = bias; P.out = out;
+  static bool done[64] = {};
+  if (conv_smem_attr(conv_tf32_kernel, CONV_SMEM_BYTES, done)) return 1;
+  const int grid = P.total_tiles < sms ? P.total_tiles : sms;
+  conv_tf32_kernel<<<grid, CONV_THREADS, CONV_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, P);
+  QIMG_LAUNCH_CHECK("conv_tf32_kernel(stride 2)");
+  return 0;
+}
+
+int qimg_vae_image_to_nhwc(const float* img, float* out, int N, int C, int H, int W, qimg_stream_t stream) {
+  if (!img || !out || N < 1 || C < 1 || C > 32 || H < 1 || W < 1) return fail("qimg_vae_image_to_nhwc: bad arguments (C <= 32)");
+  const long long px = (long long)N * H * W;
+  vae_image_to_nhwc_kernel<<<(unsigned)((px + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, out, N, C, H * W);
+  QIMG_LAUNCH_CHECK("vae_image_to_nhwc_kernel");
   return 0;
 }
 

@@ -4,11 +4,14 @@ VAE latents of the condition image are appended to the noisy latents on the sequ
 `img_shapes` carries two grids per sample (:753-758) so RoPE gives the condition image frame index 1, and only the noisy
 rows of the prediction are kept (:617,632).
 
-Scope: the DiT side.  The VAE encode of the input image (`_encode_vae_image` :455-480) and the
-Qwen2.5-VL prompt encode are outside the native engine; the request carries the already packed, already normalised
-condition latents:
+Scope.  The Qwen2.5-VL prompt encode is outside the native engine.  The condition image comes either
+already encoded —
     req.extra["image_latents"]      [B or 1, S2, 64] bf16 (what `prepare_latents` returns as `image_latents`, :519-522)
     req.extra["image_latent_grid"]  (h2, w2) latent-patch grid with h2 * w2 == S2
+— or as pixels, when the injected `vae` can encode (`B200AutoencoderKLQwenImage`: native tcgen05 encoder):
+    req.extra["image"]              [B or 1, 3, H, W] (or [.., 3, 1, H, W]) in [-1, 1], H and W multiples of 16: the output
+                                    of the reference's pre-process (`VaeImageProcessor.preprocess`, :86-92)
+which runs `_encode_vae_image` (:458-480: posterior mode, latent normalisation) and `_pack_latents` (:519-522).
 """
 from __future__ import annotations
 
@@ -28,11 +31,31 @@ class QwenImageEditPipeline(QwenImagePipeline):
                              img_shapes, txt_seq_lens, negative_txt_seq_lens, timesteps, do_true_cfg, guidance, true_cfg_scale,
                              image_latents=image_latents)
 
+    def _encode_vae_image(self, image: torch.Tensor):
+        """Reference `_encode_vae_image` (:458-480) + `_pack_latents` (:519-522): image -> ([B, S2, 64] bf16, (h2, w2))."""
+        if self.vae is None or not hasattr(self.vae, "encode"):
+            raise ValueError("req.extra['image'] needs a VAE that can encode (B200AutoencoderKLQwenImage); pass image_latents instead")
+        if image.dim() == 4:
+            image = image.unsqueeze(2)
+        lat = self.vae.encode(image.to(self.device)).latent_dist.mode()  # sample_mode="argmax" [B, 16, 1, h, w]
+        z = self.vae.config.z_dim
+        mean = torch.tensor(self.vae.config.latents_mean).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
+        std = torch.tensor(self.vae.config.latents_std).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
+        lat = (lat - mean) / std
+        b, _, _, h, w = lat.shape
+        if h % 2 or w % 2:
+            raise ValueError("image height and width must be multiples of 16")
+        return self._pack_latents(lat, b, z, h, w).to(torch.bfloat16), (h // 2, w // 2)
+
     def _condition_latents(self, req: OmniDiffusionRequest, batch: int, img_shapes):
-        il = (req.extra or {}).get("image_latents")
+        ex = req.extra or {}
+        il = ex.get("image_latents")
+        if il is None and ex.get("image") is not None:
+            il, grid = self._encode_vae_image(ex["image"])
+            ex = {**ex, "image_latent_grid": grid}
         if il is None:
             return None, img_shapes  # behaves as text-to-image, like the reference when `image` is None (:600-602)
-        grid = (req.extra or {}).get("image_latent_grid")
+        grid = ex.get("image_latent_grid")
         if grid is None or int(grid[0]) * int(grid[1]) != il.shape[1]:
             raise ValueError("req.extra['image_latent_grid'] = (h2, w2) with h2 * w2 == image_latents.shape[1] is required")
         if il.shape[0] != batch:
@@ -54,7 +77,10 @@ class QwenImageEditPlusPipeline(QwenImageEditPipeline):
     def _condition_latents(self, req: OmniDiffusionRequest, batch: int, img_shapes):
         ex = req.extra or {}
         il, grids = ex.get("image_latents"), ex.get("image_latent_grids")
-        if il is None:
+        if il is None and isinstance(ex.get("image"), (list, tuple)):  # several condition images as pixels: encode each (:436-464)
+            enc = [self._encode_vae_image(im) for im in ex["image"]]
+            il, grids = [e[0] for e in enc], [e[1] for e in enc]
+        if il is None and ex.get("image") is None:
             return None, img_shapes
         if grids is None:
             return super()._condition_latents(req, batch, img_shapes)

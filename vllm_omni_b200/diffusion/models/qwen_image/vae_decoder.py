@@ -43,26 +43,26 @@ def _pack1x1(w: torch.Tensor) -> torch.Tensor:
 
 
 class B200VaeDecoder:
+    PREFIXES = ("decoder.", "post_quant_conv.")
+
     def __init__(self, state_dict: dict, device="cuda", latents_mean=None, latents_std=None, z_dim: int = 16):
         self.device = torch.device(device)
         self.dtype = torch.float32  # what the pipeline casts the latents to (:737); the reference loads the VAE in fp32
         self.config = SimpleNamespace(z_dim=z_dim, latents_mean=list(latents_mean or LATENTS_MEAN),
                                       latents_std=list(latents_std or LATENTS_STD))
-        sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()
-              if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
+        self.temperal_downsample = [False, True, True]  # read by the edit pipelines for vae_scale_factor (:235)
+        sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items() if k.startswith(self.PREFIXES)}
         if "decoder.conv_in.weight" not in sd:
             raise ValueError("state dict holds no `decoder.*` / `post_quant_conv.*` tensors (AutoencoderKLQwenImage checkpoint keys)")
         self.w: dict[str, torch.Tensor] = {}
         for k, v in sd.items():
             if ".time_conv." in k:
-                continue  # never executed for a single frame (autoencoder_kl_qwenimage.py:166-169)
+                continue  # never executed for a single frame (autoencoder_kl_qwenimage.py:166-169,200-211)
             if k.endswith(".gamma"):
                 self.w[k] = v.reshape(-1).contiguous()
             elif k.endswith(".bias"):
                 self.w[k] = v.contiguous()
-            elif k == "post_quant_conv.weight":
-                self.w[k] = _pack1x1(v)
-            elif k == "decoder.conv_in.weight":
+            elif k in ("decoder.conv_in.weight", "encoder.conv_in.weight"):
                 self.w[k] = _pack3x3(v, cin_pad=32)
             elif k == "decoder.conv_out.weight":
                 self.w[k] = v[:, :, -1].permute(0, 2, 3, 1).contiguous()  # [3, ky, kx, C]
@@ -150,6 +150,69 @@ class B200VaeDecoder:
         [B, 8h, 8w, 3] uint8 on the device, ready for `PIL.Image.fromarray` after one small device -> host copy."""
         y = self._features(z)
         return qlib.vae_conv_out(y, self.w["decoder.conv_out.weight"], self.w["decoder.conv_out.bias"], uint8=True)
+
+
+class B200AutoencoderKLQwenImage(B200VaeDecoder):
+    """Decode AND encode: adds `encode(x).latent_dist.mode()` — what the edit pipelines call on their condition image
+    (pipeline_qwen_image_edit.py:458-480 -> AutoencoderKLQwenImage._encode, autoencoder_kl_qwenimage.py:793-812) — on the
+    same kernels; the three resamplers are 3x3 stride-2 convolutions whose gather is the TMA descriptor's element stride."""
+    PREFIXES = ("decoder.", "post_quant_conv.", "encoder.", "quant_conv.")
+
+    def __init__(self, state_dict: dict, **kw):
+        super().__init__(state_dict, **kw)
+        if "encoder.conv_in.weight" not in self.w:
+            raise ValueError("state dict holds no `encoder.*` tensors")
+        self.num_down = 1 + max(int(k.split(".")[2]) for k in self.w if k.startswith("encoder.down_blocks."))
+
+    @torch.no_grad()
+    def _encode(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B, 3, 1, H, W] (or [B, 3, H, W]) in [-1, 1] -> posterior parameters [B, 2 z_dim, 1, H/8, W/8] fp32."""
+        if x.dim() == 5:
+            if x.shape[2] != 1:
+                raise ValueError("single-frame images only")
+            x = x[:, :, 0]
+        if not x.is_cuda:
+            raise RuntimeError("B200AutoencoderKLQwenImage needs CUDA tensors: there is no CPU path")
+        B, C, H, W = x.shape
+        if H % 8 or W % 8 or H < 64 or W < 128:
+            raise ValueError("image height / width must be multiples of 8, at least 64 x 128")
+        h = qlib.vae_image_to_nhwc(x.to(torch.float32).contiguous())
+        h = self._conv3(h, "encoder.conv_in")
+        for i in range(self.num_down):
+            p = f"encoder.down_blocks.{i}"
+            if (p + ".norm1.gamma") in self.w:
+                h = self._resblock(h, p)
+            else:  # downsample2d / downsample3d on the first frame (:190-199): zero-pad right / bottom, 3x3 stride 2
+                w = self.w[p + ".resample.1.weight"]
+                h = qlib.conv2d_down2_nhwc_tf32(h, w, self.w[p + ".resample.1.bias"], w.shape[0])
+        h = self._resblock(h, "encoder.mid_block.resnets.0")
+        h = self._attention(h, "encoder.mid_block.attentions.0")
+        h = self._resblock(h, "encoder.mid_block.resnets.1")
+        h = qlib.vae_rms_act(h, self.w["encoder.norm_out.gamma"], True, out=h)
+        h = self._conv3(h, "encoder.conv_out")
+        h = self._conv1(h, "quant_conv")                      # [B, H/8, W/8, 2 z]
+        return h.permute(0, 3, 1, 2).unsqueeze(2).contiguous()  # the reference's NCHW(T) layout: 32 floats per latent pixel
+
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        dist = _DiagonalGaussian(self._encode(x))
+        return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
+
+
+class _DiagonalGaussian:
+    """diffusers' DiagonalGaussianDistribution as far as the pipelines use it: `mode()` (sample_mode="argmax") and `sample`."""
+
+    def __init__(self, parameters: torch.Tensor):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device if generator is None else generator.device,
+                            dtype=self.mean.dtype).to(self.mean.device)
+        return self.mean + torch.exp(0.5 * self.logvar) * noise
 
 
 def _rows(k: torch.Tensor, P: int) -> torch.Tensor:

@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "qimg_engine_set_sp_p2p", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
     "qimg_conv2d_nhwc_tf32", "qimg_vae_rms_act", "qimg_vae_upsample2x", "qimg_vae_post_quant", "qimg_vae_conv_out",
     "qimg_vae_softmax_rows", "qimg_vae_transpose", "qimg_set_vae_conv_variant",
+    "qimg_conv2d_down2_nhwc_tf32", "qimg_vae_image_to_nhwc",
 ]
 
 
@@ -144,6 +145,8 @@ def load():
     lib.qimg_conv2d_nhwc_tf32.argtypes = [vp, i, vp, i, vp, vp, i, vp, i, i, i, i, i, i, i, vp]
     lib.qimg_vae_rms_act.argtypes = [vp, vp, vp, ll, i, i, vp]
     lib.qimg_set_vae_conv_variant.argtypes = [i]
+    lib.qimg_conv2d_down2_nhwc_tf32.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i, i, i, vp]
+    lib.qimg_vae_image_to_nhwc.argtypes = [vp, vp, i, i, i, i, vp]
     lib.qimg_vae_upsample2x.argtypes = [vp, vp, i, i, i, i, vp]
     lib.qimg_vae_post_quant.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     lib.qimg_vae_conv_out.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
@@ -447,6 +450,27 @@ def conv2d_nhwc_tf32(x: torch.Tensor, w: torch.Tensor, bias, taps: int, cout: in
 
 def set_vae_conv_variant(variant: int):
     check(load().qimg_set_vae_conv_variant(int(variant)), "qimg_set_vae_conv_variant")
+
+
+def conv2d_down2_nhwc_tf32(x: torch.Tensor, w: torch.Tensor, bias, cout: int):
+    """ZeroPad2d((0, 1, 0, 1)) + Conv2d(3, stride 2): x [N, H, W, C] contiguous fp32 -> [N, H/2, W/2, cout]."""
+    _f32(x), _f32(w)
+    assert x.is_contiguous()
+    N, H, W, C_ = x.shape
+    out = torch.empty((N, H // 2, W // 2, cout), dtype=torch.float32, device=x.device)
+    check(load().qimg_conv2d_down2_nhwc_tf32(_p(x), C_, _p(w), w.stride(0), _p(bias), _p(out), cout, N, H, W, C_, cout, stream_ptr()),
+          "qimg_conv2d_down2_nhwc_tf32")
+    return out
+
+
+def vae_image_to_nhwc(img: torch.Tensor):
+    """img [N, C <= 32, H, W] fp32 NCHW -> [N, H, W, 32] NHWC (zero-padded channels)."""
+    _f32(img)
+    assert img.is_contiguous()
+    N, C_, H, W = img.shape
+    out = torch.empty((N, H, W, 32), dtype=torch.float32, device=img.device)
+    check(load().qimg_vae_image_to_nhwc(_p(img), _p(out), N, C_, H, W, stream_ptr()), "qimg_vae_image_to_nhwc")
+    return out
 
 
 def vae_rms_act(x: torch.Tensor, gamma: torch.Tensor, silu: bool, out=None):

@@ -182,3 +182,70 @@ def synthetic_vae_decoder_weights(seed: int = 0, **arch) -> dict[str, torch.Tens
             t = t * (1.0 / fan_in) ** 0.5 * (3.0 ** 0.5 if len(shape) == 5 and shape[2] == 3 else 1.0)  # 1 of 3 time taps is live
         out[name] = t
     return out
+
+
+def vae_encoder_param_shapes(base_dim: int = 96, z_dim: int = 16, dim_mult=(1, 2, 4, 4), num_res_blocks: int = 2,
+                             temperal_downsample=(False, True, True), in_channels: int = 3) -> dict[str, tuple]:
+    """`encoder.*` + `quant_conv.*` of AutoencoderKLQwenImage (autoencoder_kl_qwenimage.py:372-444,706): the encode side the
+    edit pipelines run on their condition image (pipeline_qwen_image_edit.py:458-480)."""
+    dims = [base_dim * u for u in [1] + list(dim_mult)]  # (:409)
+    s: dict[str, tuple] = {"encoder.conv_in.weight": (dims[0], in_channels, 3, 3, 3), "encoder.conv_in.bias": (dims[0],)}
+
+    def resblock(prefix, cin, cout):
+        s[f"{prefix}.norm1.gamma"] = (cin, 1, 1, 1)
+        s[f"{prefix}.conv1.weight"] = (cout, cin, 3, 3, 3)
+        s[f"{prefix}.conv1.bias"] = (cout,)
+        s[f"{prefix}.norm2.gamma"] = (cout, 1, 1, 1)
+        s[f"{prefix}.conv2.weight"] = (cout, cout, 3, 3, 3)
+        s[f"{prefix}.conv2.bias"] = (cout,)
+        if cin != cout:
+            s[f"{prefix}.conv_shortcut.weight"] = (cout, cin, 1, 1, 1)
+            s[f"{prefix}.conv_shortcut.bias"] = (cout,)
+
+    idx = 0  # down_blocks is ONE flat ModuleList of residual blocks and resamplers (:415-427)
+    out_dim = dims[0]
+    for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(num_res_blocks):
+            resblock(f"encoder.down_blocks.{idx}", in_dim, out_dim)
+            in_dim = out_dim
+            idx += 1
+        if i != len(dim_mult) - 1:
+            s[f"encoder.down_blocks.{idx}.resample.1.weight"] = (out_dim, out_dim, 3, 3)
+            s[f"encoder.down_blocks.{idx}.resample.1.bias"] = (out_dim,)
+            if temperal_downsample[i]:  # in the checkpoint, never executed for a single frame (:200-211)
+                s[f"encoder.down_blocks.{idx}.time_conv.weight"] = (out_dim, out_dim, 3, 1, 1)
+                s[f"encoder.down_blocks.{idx}.time_conv.bias"] = (out_dim,)
+            idx += 1
+    resblock("encoder.mid_block.resnets.0", out_dim, out_dim)
+    s["encoder.mid_block.attentions.0.norm.gamma"] = (out_dim, 1, 1)
+    s["encoder.mid_block.attentions.0.to_qkv.weight"] = (3 * out_dim, out_dim, 1, 1)
+    s["encoder.mid_block.attentions.0.to_qkv.bias"] = (3 * out_dim,)
+    s["encoder.mid_block.attentions.0.proj.weight"] = (out_dim, out_dim, 1, 1)
+    s["encoder.mid_block.attentions.0.proj.bias"] = (out_dim,)
+    resblock("encoder.mid_block.resnets.1", out_dim, out_dim)
+    s["encoder.norm_out.gamma"] = (out_dim, 1, 1, 1)
+    s["encoder.conv_out.weight"] = (2 * z_dim, out_dim, 3, 3, 3)
+    s["encoder.conv_out.bias"] = (2 * z_dim,)
+    s["quant_conv.weight"] = (2 * z_dim, 2 * z_dim, 1, 1, 1)
+    s["quant_conv.bias"] = (2 * z_dim,)
+    return s
+
+
+def synthetic_vae_encoder_weights(seed: int = 0, **arch) -> dict[str, torch.Tensor]:
+    """Same recipe as `synthetic_vae_decoder_weights` for the encode side."""
+    out = {}
+    for name, shape in vae_encoder_param_shapes(**arch).items():
+        g = torch.Generator(device="cpu")
+        g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+        t = torch.randn(shape, generator=g, dtype=torch.float32)
+        if name.endswith(".gamma"):
+            t = 1.0 + 0.1 * t
+        elif name.endswith(".bias"):
+            t = 0.05 * t
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = t * (1.0 / fan_in) ** 0.5 * (3.0 ** 0.5 if len(shape) == 5 and shape[2] == 3 else 1.0)
+        out[name] = t
+    return out
