@@ -74,6 +74,14 @@ int qimg_set_fmha_single_tile(int mode);
  * consecutive batches of shift/scale (0 => one modulation row shared by the whole batch). */
 int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
                      long long mod_stride, float eps, qimg_stream_t stream);
+/* Per-token modulation select — AdaLayerNorm.preprocess / forward with `index` (layers/adalayernorm.py:31-54,94-102; the
+ * reference builds the index for `zero_cond_t` models, qwen_image_transformer.py:748-754): shift / scale hold 2 * index_batch
+ * modulation rows, token r (int32 index[r], device) of batch b uses row b when index[r] == 0 and row index_batch + b otherwise.
+ * qimg_select_rows gathers the matching per-token gate rows: out[r, :] = src[(index[r] ? index_batch : 0) + r / rows_per_batch, :]. */
+int qimg_ln_modulate_indexed(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
+                             long long mod_stride, float eps, const int* index, int index_batch, qimg_stream_t stream);
+int qimg_select_rows(const void* src, long long src_stride, const int* index, void* out, int rows, int D, int rows_per_batch,
+                     int index_batch, qimg_stream_t stream);
 /* Same on a slice of the stream: x / y point at the slice, row_base is the global index of its first row (selects the
  * batch's modulation row).  Sequence-parallel engine mode. */
 int qimg_ln_modulate_rows(const void* x, const void* shift, const void* scale, void* y, int rows, int row_base, int D,

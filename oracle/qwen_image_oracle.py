@@ -94,12 +94,22 @@ def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
     return (xf.to(weight.dtype) * weight).to(orig)
 
 
-def ada_layer_norm(x: torch.Tensor, mod: torch.Tensor, eps: float):
+def ada_layer_norm(x: torch.Tensor, mod: torch.Tensor, eps: float, index: torch.Tensor = None):
     """AdaLayerNorm.forward_native (layers/adalayernorm.py:94-102); chunk order
-    (shift, scale, gate) from :29.  x [B,S,D], mod [B,3D] -> (y [B,S,D], gate [B,1,D])."""
+    (shift, scale, gate) from :29.  x [B,S,D], mod [B,3D] -> (y [B,S,D], gate [B,1,D]).
+    With `index` [B,S] (`preprocess`, :31-54): mod has 2B rows, token (b, s) takes row b when index == 0 and row B + b
+    otherwise; the gate is then per token [B,S,D]."""
     shift, scale, gate = mod.chunk(3, dim=-1)
-    y = F.layer_norm(x, (x.shape[-1],), None, None, eps) * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
-    return y, gate.unsqueeze(1)
+    if index is not None:
+        B = shift.size(0) // 2
+        sel = (index == 0).unsqueeze(-1)
+        shift = torch.where(sel, shift[:B].unsqueeze(1), shift[B:].unsqueeze(1))
+        scale = torch.where(sel, scale[:B].unsqueeze(1), scale[B:].unsqueeze(1))
+        gate = torch.where(sel, gate[:B].unsqueeze(1), gate[B:].unsqueeze(1))
+    else:
+        shift, scale, gate = shift.unsqueeze(1), scale.unsqueeze(1), gate.unsqueeze(1)
+    y = F.layer_norm(x, (x.shape[-1],), None, None, eps) * (1 + scale) + shift
+    return y, gate
 
 
 def rope_tables(frame, height: int = None, width: int = None, txt_len: int = None, axes=(16, 56, 56), theta: float = 10000.0):

@@ -89,6 +89,24 @@ def test_ln_modulate(B, S, D):
     assert O.rel_fro(y, ref32) < TOL_KERNEL
 
 
+def test_adalayernorm_token_index_matches_reference_golden(golden_dir):
+    """Per-token modulation select (`zero_cond_t` models; AdaLayerNorm with `index`, layers/adalayernorm.py:31-54): the fused
+    kernel + the gate gather against the unmodified reference layer's outputs, through the CustomOp plug-in."""
+    from vllm_omni_b200.diffusion.layers.adalayernorm import AdaLayerNorm
+    gold = torch.load(os.path.join(golden_dir, "adaln_index.pt"))
+    for name, c in gold.items():
+        D = c["x"].shape[-1]
+        y, gate = AdaLayerNorm(D, eps=1e-6).forward_cuda(c["x"].to(dev), c["mod"].to(dev), c["index"].to(dev))
+        assert torch.equal(gate.cpu(), c["gate"]), name                       # a gather: exact
+        assert O.rel_fro(y.cpu(), c["y"]) < 1e-3, name                        # vs the reference's bf16 output
+        assert O.rel_fro(y.cpu(), c["y_fp32"]) < TOL_KERNEL, name             # vs fp32
+        # all-zero index == the un-indexed path on the first half of the modulation rows
+        B = c["x"].shape[0]
+        y0, g0 = AdaLayerNorm(D, eps=1e-6).forward_cuda(c["x"].to(dev), c["mod"].to(dev), torch.zeros_like(c["index"]).to(dev))
+        y1, g1 = AdaLayerNorm(D, eps=1e-6).forward_cuda(c["x"].to(dev), c["mod"][:B].to(dev))
+        assert torch.equal(y0, y1) and torch.equal(g0, g1.expand_as(g0))
+
+
 def test_adalayernorm_custom_op_plugin():
     from vllm_omni_b200.diffusion.layers.adalayernorm import AdaLayerNorm
     g = gen(2)

@@ -161,3 +161,12 @@ def test_vae_encode_oracle_matches_reference_golden(golden_dir):
     p = vae_oracle.vae_encode(gold["x"], W)
     assert p.shape == gold["params"].shape == (2, 32, 1, 18, 22)
     assert (p - gold["params"]).abs().max().item() < 1e-4
+
+
+def test_adaln_with_token_index_matches_reference_golden(golden_dir):
+    """`ada_layer_norm(..., index)` == the reference's AdaLayerNorm.forward_native with a per-token modulation index
+    (layers/adalayernorm.py:31-54), bit for bit in bf16."""
+    gold = torch.load(os.path.join(golden_dir, "adaln_index.pt"))
+    for name, c in gold.items():
+        y, gate = O.ada_layer_norm(c["x"], c["mod"], 1e-6, c["index"])
+        assert torch.equal(y, c["y"]) and torch.equal(gate.expand_as(c["gate"]), c["gate"]), name

@@ -539,8 +539,9 @@ int qimg_device_check(int* sm_count) {
   return 0;
 }
 
-int qimg_ln_modulate_rows(const void* x, const void* shift, const void* scale, void* y, int rows, int row_base, int D,
-                          int rows_per_batch, long long mod_stride, float eps, qimg_stream_t stream) {
+static int ln_modulate_launch(const void* x, const void* shift, const void* scale, void* y, int rows, int row_base, int D,
+                              int rows_per_batch, long long mod_stride, float eps, const int* index, int index_batch,
+                              qimg_stream_t stream) {
   if (rows <= 0) return 0;
   if (D % 8 || D > EW_MAX_CHUNKS * 256) return fail("qimg_ln_modulate: D must be a multiple of 8 and <= 4096");
   if (rows_per_batch <= 0 || row_base < 0) return fail("qimg_ln_modulate: rows_per_batch / row_base");
@@ -549,21 +550,50 @@ int qimg_ln_modulate_rows(const void* x, const void* shift, const void* scale, v
   const bf16 *xp = (const bf16*)x, *shp = (const bf16*)shift, *scp = (const bf16*)scale;
   const int* skip = launch_predicate();
   if (D == 3072) {  // Qwen-Image width: compile-time row length
-    ln_modulate_fast_kernel<12><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip);
+    ln_modulate_fast_kernel<12><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip,
+                                                      index, index_batch);
   } else if (D == 1024) {
-    ln_modulate_fast_kernel<4><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip);
+    ln_modulate_fast_kernel<4><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip,
+                                                     index, index_batch);
   } else if (D == 256) {
-    ln_modulate_fast_kernel<1><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip);
+    ln_modulate_fast_kernel<1><<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, rows_per_batch, mod_stride, eps, skip,
+                                                     index, index_batch);
   } else {
-    ln_modulate_kernel<<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, D, rows_per_batch, mod_stride, eps, skip);
+    ln_modulate_kernel<<<grid, 128, 0, st>>>(xp, shp, scp, (bf16*)y, rows, row_base, D, rows_per_batch, mod_stride, eps, skip, index,
+                                             index_batch);
   }
   QIMG_LAUNCH_CHECK("ln_modulate_kernel");
   return 0;
 }
 
+int qimg_ln_modulate_rows(const void* x, const void* shift, const void* scale, void* y, int rows, int row_base, int D,
+                          int rows_per_batch, long long mod_stride, float eps, qimg_stream_t stream) {
+  return ln_modulate_launch(x, shift, scale, y, rows, row_base, D, rows_per_batch, mod_stride, eps, nullptr, 0, stream);
+}
+
 int qimg_ln_modulate(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
                      long long mod_stride, float eps, qimg_stream_t stream) {
-  return qimg_ln_modulate_rows(x, shift, scale, y, rows, 0, D, rows_per_batch, mod_stride, eps, stream);
+  return ln_modulate_launch(x, shift, scale, y, rows, 0, D, rows_per_batch, mod_stride, eps, nullptr, 0, stream);
+}
+
+int qimg_ln_modulate_indexed(const void* x, const void* shift, const void* scale, void* y, int rows, int D, int rows_per_batch,
+                             long long mod_stride, float eps, const int* index, int index_batch, qimg_stream_t stream) {
+  if (!index || index_batch < 1) return fail("qimg_ln_modulate_indexed: index [rows] (int32, device) and the batch size are required");
+  return ln_modulate_launch(x, shift, scale, y, rows, 0, D, rows_per_batch, mod_stride, eps, index, index_batch, stream);
+}
+
+int qimg_select_rows(const void* src, long long src_stride, const int* index, void* out, int rows, int D, int rows_per_batch,
+                     int index_batch, qimg_stream_t stream) {
+  if (rows <= 0) return 0;
+  if (!src || !index || !out || D % 8 || rows_per_batch <= 0 || index_batch < 1) return fail("qimg_select_rows: bad arguments (D % 8 == 0)");
+  const long long n_vec = (long long)rows * (D / 8);
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  select_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, src_stride, index, (bf16*)out, n_vec, D,
+                                                                    rows_per_batch, index_batch);
+  QIMG_LAUNCH_CHECK("select_rows_kernel");
+  return 0;
 }
 
 int qimg_rms_norm(const void* x, const void* w, void* y, int rows, int D, float eps, qimg_stream_t stream) {

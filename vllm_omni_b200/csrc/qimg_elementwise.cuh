@@ -17,7 +17,8 @@ constexpr int EW_MAX_CHUNKS = 16;  // 16 x 256 = 4096 elements per row max (D=30
 __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
                                                           const bf16* __restrict__ scale, bf16* __restrict__ y, int rows,
                                                           int row_base, int D, int rows_per_batch, long long mod_stride,
-                                                          float eps, const int* __restrict__ skip) {
+                                                          float eps, const int* __restrict__ skip,
+                                                          const int* __restrict__ mod_index, int index_batch) {
   if (skip && *skip) return;  // step cache: this forward reuses the cached residual (qimg_tea_decide)
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -51,7 +52,10 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const bf16* __restrict
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
   const float nmr = -mean * rstd;
-  const int b = (row_base + row) / rows_per_batch;
+  int b = (row_base + row) / rows_per_batch;
+  // per-token modulation select (AdaLayerNorm.preprocess with `index`, layers/adalayernorm.py:31-54): the modulation
+  // buffer holds 2 * index_batch rows, tokens with index != 0 take the second half
+  if (mod_index && mod_index[row_base + row] != 0) b += index_batch;
   const bf16* sh = shift + (size_t)b * mod_stride;
   const bf16* sc = scale + (size_t)b * mod_stride;
   bf16* yr = y + (size_t)row * D;
@@ -83,7 +87,8 @@ __global__ void __launch_bounds__(128) ln_modulate_fast_kernel(const bf16* __res
                                                                const bf16* __restrict__ scale, bf16* __restrict__ y,
                                                                int rows, int row_base, int rows_per_batch,
                                                                long long mod_stride, float eps,
-                                                               const int* __restrict__ skip) {
+                                                               const int* __restrict__ skip,
+                                                               const int* __restrict__ mod_index, int index_batch) {
   if (skip && *skip) return;
   constexpr int D = NCH * 256;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -120,7 +125,8 @@ __global__ void __launch_bounds__(128) ln_modulate_fast_kernel(const bf16* __res
   }
   const float rstd = rsqrtf(warp_sum(ew_hsum2(ew_add2(q0, q1))) * (1.0f / (float)D) + eps);
   const uint64_t rstd2 = ew_splat2(rstd), zero2 = 0;
-  const int b = (row_base + row) / rows_per_batch;
+  int b = (row_base + row) / rows_per_batch;
+  if (mod_index && mod_index[row_base + row] != 0) b += index_batch;  // per-token modulation select (see the generic kernel)
   const bf16* sh = shift + (size_t)b * mod_stride + lane * 8;
   const bf16* sc = scale + (size_t)b * mod_stride + lane * 8;
   bf16* yr = y + (size_t)row * D + lane * 8;
@@ -475,6 +481,19 @@ __global__ void __launch_bounds__(256) cfg_euler_step_kernel(const bf16* __restr
     for (int k = 0; k < 4; ++k)
       o[k] = pack_bf16x2(bf16lo(xw[k]) + rbf(dtb * noise[2 * k]), bf16hi(xw[k]) + rbf(dtb * noise[2 * k + 1]));
     stg_v4(x + vec * 8, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// out[r, :] = src[(index[r] != 0 ? index_batch : 0) + r / rows_per_batch, :]  — the per-token gate of AdaLayerNorm.preprocess
+// (`torch.where(index == 0, gate_0, gate_1)`, layers/adalayernorm.py:47-49); D % 8 == 0, one uint4 per thread
+__global__ void select_rows_kernel(const bf16* __restrict__ src, long long src_stride, const int* __restrict__ index,
+                                   bf16* __restrict__ out, long long n_vec, int D, int rows_per_batch, int index_batch) {
+  const int vpr = D / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c = (int)(i - r * vpr);
+    const long long b = r / rows_per_batch + (index[r] != 0 ? index_batch : 0);
+    reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(src + b * src_stride) + c);
   }
 }
 

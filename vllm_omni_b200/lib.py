@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "qimg_engine_set_sp_p2p", "qimg_tea_decide", "qimg_tea_residual", "qimg_engine_set_blocks_predicate",
     "qimg_conv2d_nhwc_tf32", "qimg_vae_rms_act", "qimg_vae_upsample2x", "qimg_vae_post_quant", "qimg_vae_conv_out",
     "qimg_vae_softmax_rows", "qimg_vae_transpose", "qimg_set_vae_conv_variant",
-    "qimg_conv2d_down2_nhwc_tf32", "qimg_vae_image_to_nhwc",
+    "qimg_conv2d_down2_nhwc_tf32", "qimg_vae_image_to_nhwc", "qimg_ln_modulate_indexed", "qimg_select_rows",
 ]
 
 
@@ -99,6 +99,8 @@ def load():
     lib.qimg_reset_launch_count.restype = None
     lib.qimg_ln_modulate.argtypes = [vp, vp, vp, vp, i, i, i, ll, f, vp]
     lib.qimg_ln_modulate_rows.argtypes = [vp, vp, vp, vp, i, i, i, i, ll, f, vp]
+    lib.qimg_ln_modulate_indexed.argtypes = [vp, vp, vp, vp, i, i, i, ll, f, vp, i, vp]
+    lib.qimg_select_rows.argtypes = [vp, ll, vp, vp, i, i, i, i, vp]
     lib.qimg_gate_residual.argtypes = [vp, vp, vp, i, i, i, ll, vp]
     lib.qimg_rms_norm.argtypes = [vp, vp, vp, i, i, f, vp]
     lib.qimg_gate_residual_bias.argtypes = [vp, vp, vp, vp, i, i, i, ll, vp]
@@ -258,6 +260,27 @@ def ln_modulate(x, shift, scale, rows_per_batch: int, mod_stride: int, eps: floa
     out = torch.empty_like(x) if out is None else out
     check(load().qimg_ln_modulate(_p(x), _p(shift), _p(scale), _p(out), rows, D, rows_per_batch, mod_stride, eps,
                                   stream_ptr()), "qimg_ln_modulate")
+    return out
+
+
+def ln_modulate_indexed(x, shift, scale, index, batch: int, rows_per_batch: int, mod_stride: int, eps: float = 1e-6):
+    """x [rows, D]; shift / scale: views into a [2 * batch, ...] modulation buffer; index int32 [rows] (0 / 1 per token)."""
+    _bf16c(x)
+    assert index.dtype == torch.int32 and index.is_cuda and index.is_contiguous() and index.numel() == x.shape[0]
+    rows, D = x.shape
+    out = torch.empty_like(x)
+    check(load().qimg_ln_modulate_indexed(_p(x), _p(shift), _p(scale), _p(out), rows, D, rows_per_batch, mod_stride, eps, _p(index),
+                                          batch, stream_ptr()), "qimg_ln_modulate_indexed")
+    return out
+
+
+def select_rows(src, index, batch: int, rows_per_batch: int):
+    """src: view [2 * batch, D] (row stride arbitrary, bf16); index int32 [rows] -> [rows, D] with the token's row of `src`."""
+    assert src.dtype == torch.bfloat16 and src.stride(1) == 1 and index.dtype == torch.int32
+    rows, D = index.numel(), src.shape[1]
+    out = torch.empty((rows, D), dtype=torch.bfloat16, device=src.device)
+    check(load().qimg_select_rows(_p(src), src.stride(0), _p(index), _p(out), rows, D, rows_per_batch, batch, stream_ptr()),
+          "qimg_select_rows")
     return out
 
 
