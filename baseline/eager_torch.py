@@ -166,3 +166,34 @@ def vae_decode_eager(z, W):
         i += 1
     x = F.silu(_vae_rms(x, W["decoder.norm_out.gamma"]))
     return _vae_causal_conv3d(x, W["decoder.conv_out.weight"], W["decoder.conv_out.bias"]).clamp(-1.0, 1.0)
+
+
+def vae_encode_eager(x, W):
+    """TIMING ONLY: the op sequence `AutoencoderKLQwenImage._encode` dispatches on CUDA for one frame
+    (autoencoder_kl_qwenimage.py:793-812): x [B, 3, 1, H, W] fp32 -> posterior parameters [B, 32, 1, H/8, W/8]."""
+    h = _vae_causal_conv3d(x, W["encoder.conv_in.weight"], W["encoder.conv_in.bias"])
+    i = 0
+    while f"encoder.down_blocks.{i}.norm1.gamma" in W or f"encoder.down_blocks.{i}.resample.1.weight" in W:
+        p = f"encoder.down_blocks.{i}"
+        if (p + ".norm1.gamma") in W:
+            h = _vae_resblock(h, W, p)
+        else:  # QwenImageResample "downsample2d/3d" on the first frame (:190-199)
+            b_, c_, t_, h_, w_ = h.shape
+            y = h.permute(0, 2, 1, 3, 4).reshape(b_ * t_, c_, h_, w_)
+            y = F.conv2d(F.pad(y, (0, 1, 0, 1)), W[p + ".resample.1.weight"], W[p + ".resample.1.bias"], stride=2)
+            h = y.view(b_, t_, y.shape[1], y.shape[2], y.shape[3]).permute(0, 2, 1, 3, 4)
+        i += 1
+    h = _vae_resblock(h, W, "encoder.mid_block.resnets.0")
+    p = "encoder.mid_block.attentions.0"
+    B, C, T, hh, ww = h.shape
+    y = h.permute(0, 2, 1, 3, 4).reshape(B * T, C, hh, ww)
+    y = _vae_rms(y, W[p + ".norm.gamma"])
+    qkv = F.conv2d(y, W[p + ".to_qkv.weight"], W[p + ".to_qkv.bias"]).reshape(B * T, 1, 3 * C, -1).permute(0, 1, 3, 2).contiguous()
+    q, k, v = qkv.chunk(3, dim=-1)
+    a = F.scaled_dot_product_attention(q, k, v).squeeze(1).permute(0, 2, 1).reshape(B * T, C, hh, ww)
+    a = F.conv2d(a, W[p + ".proj.weight"], W[p + ".proj.bias"])
+    h = a.view(B, T, C, hh, ww).permute(0, 2, 1, 3, 4) + h
+    h = _vae_resblock(h, W, "encoder.mid_block.resnets.1")
+    h = F.silu(_vae_rms(h, W["encoder.norm_out.gamma"]))
+    h = _vae_causal_conv3d(h, W["encoder.conv_out.weight"], W["encoder.conv_out.bias"])
+    return _vae_causal_conv3d(h, W["quant_conv.weight"], W["quant_conv.bias"])

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from baseline import eager_torch  # noqa: E402
 from vllm_omni_b200 import lib as q  # noqa: E402
 from vllm_omni_b200 import synthetic  # noqa: E402
-from vllm_omni_b200.diffusion.models.qwen_image.vae_decoder import B200VaeDecoder  # noqa: E402
+from vllm_omni_b200.diffusion.models.qwen_image.vae_decoder import B200AutoencoderKLQwenImage  # noqa: E402
 
 # conv / GEMM FLOPs of one decode at latent grid (h, w): 2 * pixels * Cin * Cout * taps per layer
 def decode_flops(h, w):
@@ -49,9 +49,9 @@ def main():
     dev = "cuda"
     shapes = [tuple(int(v) for v in s.split(",")) for s in os.environ.get("VB_SHAPES", "1,128,128;4,128,128").split(";")]
     iters = int(os.environ.get("VB_ITERS", "5"))
-    W = synthetic.synthetic_vae_decoder_weights(seed=6)
+    W = {**synthetic.synthetic_vae_decoder_weights(seed=6), **synthetic.synthetic_vae_encoder_weights(seed=6)}
     Wd = {k: v.to(dev) for k, v in W.items()}
-    vae = B200VaeDecoder(W, device=dev)
+    vae = B200AutoencoderKLQwenImage(W, device=dev)
     for B, h, w in shapes:
         z = torch.randn(B, 16, 1, h, w, generator=torch.Generator().manual_seed(1)).to(dev)
         n0 = q.launch_count()
@@ -75,6 +75,18 @@ def main():
                           "native_vs_eager_tf32_max_abs": round(d.max().item(), 5),
                           "native_vs_eager_fp32_max_abs": round((out - ref32).abs().max().item(), 5),
                           "eager_tf32_vs_fp32_max_abs": round((ref - ref32).abs().max().item(), 5)}), flush=True)
+        # encode side: the edit pipelines' condition image of the same size
+        x = (torch.rand(B, 3, 1, 8 * h, 8 * w, generator=torch.Generator().manual_seed(2)) * 2 - 1).to(dev)
+        n0 = q.launch_count()
+        par = vae.encode(x).latent_dist.parameters
+        launches = q.launch_count() - n0
+        with torch.no_grad():
+            refp = eager_torch.vae_encode_eager(x, Wd)
+            t_ref = timed(lambda: eager_torch.vae_encode_eager(x, Wd), iters)
+        t_nat = timed(lambda: vae.encode(x), iters)
+        print(json.dumps({"encode": True, "B": B, "image": [8 * h, 8 * w], "native_ms": round(t_nat, 3), "eager_cudnn_tf32_ms": round(t_ref, 3),
+                          "speedup": round(t_ref / t_nat, 2), "launches": launches,
+                          "rel_fro_vs_eager_tf32": round(((par - refp).norm() / refp.norm()).item(), 5)}), flush=True)
 
 
 if __name__ == "__main__":
