@@ -559,3 +559,38 @@ def test_edit_pipeline_encodes_pixel_images_like_the_reference_glue():
     assert out.shape == (2, 24 + 12, 64) and sh == [[(1, 8, 6), (1, 4, 6), (1, 2, 6)]] * 2 and torch.equal(out[:, :24], want)
     with pytest.raises(ValueError, match="can encode"):
         QwenImageEditPipeline._encode_vae_image(SimpleNamespace(vae=None), img)
+
+
+def test_vae_c_abi_argument_checks_without_gpu():
+    """The VAE entry points reject bad shapes / strides / pointers before any CUDA call (CPU-only build host, no compute)."""
+    lib = qlib.load()
+    conv = lib.qimg_conv2d_nhwc_tf32
+    ok = dict(x=4096, ldx=96, w=8192, ldw=864, bias=None, res=None, ldr=0, out=12288, ldo=96, N=1, H=16, W=32, Cin=96, Cout=96, taps=9)
+
+    def call(**kw):
+        a = {**ok, **kw}
+        return conv(a["x"], a["ldx"], a["w"], a["ldw"], a["bias"], a["res"], a["ldr"], a["out"], a["ldo"], a["N"], a["H"], a["W"],
+                    a["Cin"], a["Cout"], a["taps"], None)
+
+    assert call(taps=4) != 0 and b"taps" in lib.qimg_last_error()
+    assert call(H=4) != 0 and b"H >= 8" in lib.qimg_last_error()
+    assert call(Cin=80) != 0 and b"Cin" in lib.qimg_last_error()             # 3x3 needs whole 32-channel K blocks
+    assert call(Cin=16, ldw=144) != 0 and b"Cin" in lib.qimg_last_error()
+    assert call(Cout=98) != 0 and b"Cout" in lib.qimg_last_error()
+    assert call(ldw=800) != 0 and b"leading dimensions" in lib.qimg_last_error()
+    assert call(ldx=95) != 0 and call(res=4096, ldr=64) != 0
+    assert call(x=4100) != 0 and b"aligned" in lib.qimg_last_error()
+    assert call(x=None) != 0 and b"null" in lib.qimg_last_error()
+    down = lib.qimg_conv2d_down2_nhwc_tf32
+    assert down(4096, 96, 8192, 864, None, 12288, 96, 1, 17, 32, 96, 96, None) != 0 and b"even" in lib.qimg_last_error()
+    assert down(4096, 96, 8192, 864, None, 12288, 96, 1, 16, 32, 48, 96, None) != 0 and b"Cin" in lib.qimg_last_error()
+    assert lib.qimg_vae_rms_act(4096, 4096, 4096, 10, 100, 1, None) != 0 and b"96, 192 or 384" in lib.qimg_last_error()
+    assert lib.qimg_vae_post_quant(4096, 4096, 4096, 4096, 1, 8, 16, 8, None) != 0 and b"z_dim" in lib.qimg_last_error()
+    assert lib.qimg_vae_conv_out(4096, 4096, 4096, None, None, 1, 8, 16, 96, None) != 0        # neither output requested
+    assert lib.qimg_vae_conv_out(4096, 4096, 4096, 4096, None, 1, 8, 16, 64, None) != 0 and b"96" in lib.qimg_last_error()
+    assert lib.qimg_vae_upsample2x(4096, 4096, 1, 8, 16, 6, None) != 0
+    assert lib.qimg_vae_softmax_rows(4096, 4, 100, 50, 1.0, None) != 0                         # ld < cols
+    assert lib.qimg_vae_image_to_nhwc(4096, 4096, 1, 40, 8, 16, None) != 0
+    assert lib.qimg_set_vae_conv_variant(2) != 0 and lib.qimg_set_vae_conv_variant(0) == 0
+    assert lib.qimg_ln_modulate_indexed(4096, 4096, 4096, 4096, 8, 256, 4, 768, 1e-6, None, 2, None) != 0 and b"index" in lib.qimg_last_error()
+    assert lib.qimg_select_rows(4096, 768, 4096, 4096, 8, 250, 4, 2, None) != 0                # D % 8
