@@ -1,21 +1,27 @@
-// VAE decoder kernels for sm_100a: the post-step of QwenImagePipeline.forward
-// (pipeline_qwen_image.py:736-747 -> AutoencoderKLQwenImage._decode, autoencoder_kl_qwenimage.py:839-862), single-frame latents.
+// VAE kernels for sm_100a: the post-step of QwenImagePipeline.forward — AutoencoderKLQwenImage._decode
+// (pipeline_qwen_image.py:736-747 -> autoencoder_kl_qwenimage.py:839-862) — and the edit pipelines' pre-step, _encode
+// (pipeline_qwen_image_edit.py:458-480 -> :793-812), both for single-frame inputs.
 //
-// The reference runs this in fp32 with cuDNN (TF32 tensor-core convolutions by default) over NCHW tensors, ~70 separate ATen
-// / cuDNN launches with an fp32 pad + conv per layer.  Here:
+// The reference runs these in fp32 with cuDNN (TF32 tensor-core convolutions by default) over NCHW tensors, ~70 separate ATen
+// / cuDNN launches with an fp32 pad + Conv3d on a three-frame tensor per layer.  Here:
 //   * activations live in HBM as fp32 NHWC ([image, y, x, channel]); a 3x3 "same" convolution is an implicit GEMM
 //       out[pixel, co] = sum_{tap, ci} x[pixel + tap, ci] * w[co, tap, ci]
-//     on the 5th-gen tensor cores (tcgen05.mma kind::tf32, fp32 accumulators in TMEM): one CTA owns a 16 x 8 pixel patch
-//     (128 accumulator rows) x 128 output channels; per K block the producer warp issues ONE 4-D TMA box load
-//     {32 channels, 16 x, 8 y, 1 image} at the tap's shifted coordinates — the zero padding of the convolution is TMA's
-//     out-of-bounds fill, no padded copy, no im2col buffer — plus the weight tile; SWIZZLE_128B, 5-stage mbarrier ring,
-//     two TMEM accumulator stages so the epilogue (bias + residual add, fp32, coalesced NHWC stores) of tile i overlaps the
-//     main loop of tile i+1.  1x1 convolutions and the three attention GEMMs of the mid block use the same kernel (taps = 1).
+//     on the 5th-gen tensor cores (tcgen05.mma kind::tf32, fp32 accumulators in TMEM).  The activation operand is a 4-D TMA
+//     box {32 channels, x, y, 1 image} loaded at the tap's shifted coordinates — the zero padding of the convolution is
+//     TMA's out-of-bounds fill: no padded copy, no im2col buffer.  Two kernels:
+//       conv2_tf32_kernel (default)  one box {32, 8 x, 18 y} per (horizontal tap, channel block) serves the three vertical
+//                                    taps as shifted descriptor views; 16 x 16 pixel patch x 96 / 128 / 192 channels per CTA
+//       conv_tf32_kernel  (first)    one box {32, 16 x, 8 y} per tap, 128 pixels x 128 channels per CTA; also the stride-2
+//                                    resamplers of the encoder (the tensor map walks x and y with element stride 2)
+//     both warp-specialised (TMA warp, MMA warp, 8 epilogue warps), SWIZZLE_128B, mbarrier rings, TMEM accumulator stages
+//     so that the epilogue (bias + residual add in fp32, coalesced NHWC stores) of tile i overlaps the main loop of tile i+1.
+//     1x1 convolutions and the attention GEMMs of the mid blocks are the same kernels with taps = 1.
 //   * TF32 inputs / fp32 accumulation is the arithmetic the reference's own GPU path uses for these layers
 //     (torch.backends.cudnn.allow_tf32 defaults to True), so parity against the fp32 oracle is at the reference's own level.
 //   * the bandwidth-bound pieces are single-pass row kernels: RMS-norm (+ SiLU), nearest x2 upsample, row softmax, the
 //     16 -> 16 post_quant_conv fused with the NCHW -> NHWC layout change, and conv_out (96 -> 3 channels: FMA-pipe direct
-//     convolution fused with the clamp and the NHWC -> NCHW change; N = 3 is no tensor-core shape).
+//     convolution fused with the clamp, the NHWC -> NCHW change and the uint8 post-process; N = 3 is no tensor-core shape).
+// What bounds the convolution kernels (shared-memory port; measurements): DESIGN.md §3 "VAE decode".
 #include "../../include/qimg_b200.h"
 
 #include <cstdlib>
